@@ -1,0 +1,79 @@
+/*
+ * piquant_cuda.h -- CUDA-specific extensions of libpiquant.so.  Everything here is NEW surface:
+ * the reference has no stream, no device, no collective.  piquant.h stays ABI-identical to the
+ * reference; callers that only know the reference never need this header.
+ *
+ * All functions abort() on error like the rest of the library unless stated otherwise.
+ */
+#ifndef PIQUANT_CUDA_H
+#define PIQUANT_CUDA_H
+
+#include "piquant.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- stream dispatcher (replaces the reference's thread pool, reference src/piquant.cpp:197-211) */
+
+/* CUDA stream (a cudaStream_t) that device-pointer calls are ordered on.  NULL = legacy default stream. */
+PIQUANT_EXPORT void  piquant_cuda_set_stream(piquant_context_t* ctx, void* cuda_stream);
+PIQUANT_EXPORT void* piquant_cuda_get_stream(piquant_context_t* ctx);
+/* Block until everything this context has enqueued on its stream has finished. */
+PIQUANT_EXPORT void  piquant_cuda_synchronize(piquant_context_t* ctx);
+/* 0 = choose per cell (default), 1 = direct LDG/STG streaming kernels, 2 = TMA (cp.async.bulk) ring kernels. */
+PIQUANT_EXPORT void  piquant_cuda_set_kernel_variant(piquant_context_t* ctx, int variant);
+/* Number of CUDA kernels this context has launched so far (introspection for benchmarks and tests). */
+PIQUANT_EXPORT uint64_t piquant_cuda_kernel_launches(piquant_context_t* ctx);
+/* Number of usable CUDA devices; 0 when there is none (never aborts). */
+PIQUANT_EXPORT int   piquant_cuda_device_count(void);
+
+/* ---- stochastic rounding control.  The reference draws its per-call threshold from a
+ * random_device-seeded generator that no API can reach (reference src/piquant.cpp:194-201). */
+
+/* xi in [0,1): use this threshold for every following STOCHASTIC call; xi < 0: draw per call again. */
+PIQUANT_EXPORT void  piquant_cuda_set_stochastic_threshold(piquant_context_t* ctx, float xi);
+/* Reseed the per-call threshold generator (reproducible runs). */
+PIQUANT_EXPORT void  piquant_cuda_seed(piquant_context_t* ctx, uint64_t seed);
+/* The threshold used by the most recent STOCHASTIC call. */
+PIQUANT_EXPORT float piquant_cuda_last_stochastic_threshold(piquant_context_t* ctx);
+
+/* ---- fused quantize -> dequantize (reference C++ API only: context::quantize_dequantize_fused,
+ * reference include/piquant.hpp:276-285, src/piquant.cpp:342-369).  in and out have dtype
+ * dtype_in_out (F32 / BF16) and numel elements each; the result is not packed. */
+PIQUANT_EXPORT void piquant_cuda_requantize(
+    piquant_context_t* ctx,
+    const void* in, piquant_dtype_t dtype_in_out,
+    void* out, piquant_dtype_t quant_dtype,
+    size_t numel,
+    float scale, int64_t zero_point,
+    piquant_round_mode_t mode, piquant_reduce_op_t op);
+
+/* ---- min/max pieces of compute_quant_params, for tensors sharded over several GPUs ------------- */
+
+/* Asynchronous: reduce x (dtype F32 or BF16, device memory) to four floats {min, max, -min, max} in the
+ * DEVICE buffer out4 (16 bytes, 16-byte aligned), ordered on the context stream.  {-min, max} is the
+ * layout a single MAX all-reduce combines across shards. */
+PIQUANT_EXPORT void piquant_cuda_minmax_async(piquant_context_t* ctx, const void* x, piquant_dtype_t dtype, size_t n, float* out4);
+/* The double-precision scale / zero-point arithmetic of the reference (reference src/piquant.cpp:245-258)
+ * on an already reduced {min, max}. */
+PIQUANT_EXPORT void piquant_cuda_params_from_minmax(float min, float max, piquant_dtype_t target_quant_dtype,
+                                                    float* out_scale, int64_t* out_zero_point);
+
+/* ---- NCCL: whole-tensor quantization parameters for a tensor sharded across ranks ------------- */
+
+/* Fills 128 bytes with an ncclUniqueId (rank 0 calls this and broadcasts the bytes).  Returns 0 on
+ * success, -1 if libnccl could not be loaded (never aborts). */
+PIQUANT_EXPORT int  piquant_cuda_nccl_unique_id(void* out128);
+/* Join a communicator of nranks processes (one GPU each, the current CUDA device).  After this,
+ * piquant_compute_quant_params_* on this context reduces the local shard and then combines
+ * {-min, max} with ONE ncclAllReduce(count=2, float, max) over NVLink, so every rank returns the
+ * parameters of the whole tensor. */
+PIQUANT_EXPORT void piquant_cuda_comm_init_rank(piquant_context_t* ctx, const void* unique_id128, int nranks, int rank);
+/* Leave the communicator; compute_quant_params is local again. */
+PIQUANT_EXPORT void piquant_cuda_comm_destroy(piquant_context_t* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIQUANT_CUDA_H */

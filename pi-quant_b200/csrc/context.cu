@@ -1,0 +1,653 @@
+// context.cu -- the CUDA-stream dispatcher and the C ABI of libpiquant.so.
+//
+// Replaces, for the B200, the reference's host runtime:
+//   * extern "C" shims                      reference src/capi.cpp:19-104
+//   * context / pimpl, fork-join dispatch   reference src/piquant.cpp:113-211
+//   * quantization-parameter arithmetic     reference src/piquant.cpp:213-259, :371-381
+//   * panic()                               reference src/piquant.cpp:88-98
+// The thread pool, per-thread partitioner and CPUID kernel selection have no counterpart: the
+// "threads" are a persistent grid sized to the SM count and the only ISA is sm_100a.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <limits>
+#include <map>
+#include <mutex>
+#include <random>
+
+#include "../../include/piquant.h"
+#include "../../include/piquant_cuda.h"
+#include "pq_kernels.h"
+
+static_assert(pq::DT_F32 == PIQUANT_DTYPE_F32 && pq::DT_BF16 == PIQUANT_DTYPE_BF16 && pq::DT_U2 == PIQUANT_DTYPE_UINT2 &&
+              pq::DT_U4 == PIQUANT_DTYPE_UINT4 && pq::DT_U8 == PIQUANT_DTYPE_UINT8, "dtype enum ABI");
+static_assert(pq::OP_SET == PIQUANT_REDUCE_OP_SET && pq::OP_ADD == PIQUANT_REDUCE_OP_ADD, "reduce-op enum ABI");
+
+namespace pq {
+
+void panic(const char* fmt, ...) {
+    char buf[4096];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "\x1b[31mpiquant: %s\x1b[0m\n", buf);
+    fflush(stderr);
+    abort();
+}
+
+QuantParams make_params(float scale, int64_t zero_point, float xi) {
+    QuantParams P;
+    P.scale = scale;
+    P.inv_scale = 1.0f / scale;                               // IEEE divide, once (kernels_specialized.inl:42)
+    P.xi = xi;
+    P.zp64 = zero_point;
+    P.zp32 = static_cast<int32_t>(static_cast<uint32_t>(static_cast<uint64_t>(zero_point)));   // int64 -> int32 truncation (quantize.inl:112)
+    volatile float nzp = -static_cast<float>(P.zp32);         // two roundings, never contracted
+    P.bias = nzp * scale;
+    P.bigzp = (zero_point > (1ll << 29) || zero_point < -(1ll << 29)) ? 1 : 0;
+    return P;
+}
+
+namespace {
+
+// ---- NCCL, resolved at run time so that the library has no link-time dependency on it ----------
+struct Nccl {
+    using Comm = void*;
+    struct UniqueId { char internal[128]; };
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(Comm) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+
+    static Nccl& get() {
+        static Nccl n = load();
+        return n;
+    }
+    static Nccl load() {
+        Nccl n;
+        void* h = nullptr;
+        const char* env = getenv("PIQUANT_NCCL_LIB");
+        const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+        for (const char* name : names) {
+            if (!name) continue;
+            h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+        if (!h) return n;
+        n.GetUniqueId = reinterpret_cast<decltype(n.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+        n.CommInitRank = reinterpret_cast<decltype(n.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+        n.CommDestroy = reinterpret_cast<decltype(n.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+        n.AllReduce = reinterpret_cast<decltype(n.AllReduce)>(dlsym(h, "ncclAllReduce"));
+        n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+        n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllReduce && n.GetErrorString;
+        return n;
+    }
+};
+constexpr int kNcclFloat32 = 7, kNcclMax = 2;   // nccl.h: ncclFloat32, ncclMax
+
+#define PQ_NCCL_CHECK(expr)                                                                               \
+    do {                                                                                                  \
+        int pq_r__ = (expr);                                                                              \
+        if (pq_r__ != 0) ::pq::panic("%s:%d NCCL error: %s <- %s", __FILE__, __LINE__, Nccl::get().GetErrorString(pq_r__), #expr); \
+    } while (0)
+
+// ---- per-device resources ------------------------------------------------------------------------
+constexpr int kRing = 3;                         // host-pointer pipeline depth
+constexpr size_t kChunkElems = size_t(8) << 20;  // elements per pipeline chunk (f32: 32 MiB in flight per slot)
+
+struct DeviceState {
+    int           device = -1;
+    int           sm_count = 0;
+    MinMaxScratch scratch{};
+    float*        d_result = nullptr;        // 4 floats
+    float*        h_result = nullptr;        // pinned + mapped, 4 floats
+    float*        h_result_dev = nullptr;    // device view of h_result
+    // host-pointer pipeline (lazily created)
+    cudaStream_t  s_h2d = nullptr, s_run = nullptr, s_d2h = nullptr;
+    cudaEvent_t   ev_h2d[kRing]{}, ev_run[kRing]{}, ev_d2h[kRing]{};
+    void*         d_in[kRing]{};
+    void*         d_out[kRing]{};
+    size_t        in_cap = 0, out_cap = 0;
+    bool          pipe_ready = false;
+};
+
+enum class Where { Device, HostPinned, HostPageable };
+
+struct PtrInfo {
+    Where where;
+    int   device;     // owning device for Device memory, -1 otherwise
+};
+
+}  // namespace
+
+struct Context {
+    size_t                     num_threads = 0;
+    cudaStream_t               stream = nullptr;
+    int                        variant = 0;
+    bool                       xi_fixed = false;
+    float                      xi = 0.0f, last_xi = 0.0f;
+    std::mt19937_64            rng{std::random_device{}()};
+    std::mutex                 mu;
+    std::map<int, DeviceState> devs;
+    uint64_t                   launches = 0;
+    Nccl::Comm                 comm = nullptr;
+    int                        host_mode = 0;    // 0 = staged pipeline for every host pointer, 1 = zero-copy kernels on pinned host memory
+
+    ~Context() {
+        if (comm && Nccl::get().ok) Nccl::get().CommDestroy(comm);
+        for (auto& kv : devs) {
+            DeviceState& d = kv.second;
+            int prev = 0;
+            if (cudaGetDevice(&prev) != cudaSuccess) break;
+            cudaSetDevice(d.device);
+            cudaFree(d.scratch.partials);
+            cudaFree(d.scratch.ticket);
+            cudaFree(d.d_result);
+            cudaFreeHost(d.h_result);
+            if (d.pipe_ready) {
+                for (int i = 0; i < kRing; ++i) {
+                    cudaFree(d.d_in[i]);
+                    cudaFree(d.d_out[i]);
+                    cudaEventDestroy(d.ev_h2d[i]);
+                    cudaEventDestroy(d.ev_run[i]);
+                    cudaEventDestroy(d.ev_d2h[i]);
+                }
+                cudaStreamDestroy(d.s_h2d);
+                cudaStreamDestroy(d.s_run);
+                cudaStreamDestroy(d.s_d2h);
+            }
+            cudaSetDevice(prev);
+        }
+    }
+
+    float draw_xi() {
+        // one threshold per call, U[0,1) (reference src/piquant.cpp:199-201)
+        last_xi = xi_fixed ? xi : std::uniform_real_distribution<float>{0.0f, 1.0f}(rng);
+        return last_xi;
+    }
+
+    DeviceState& dev_state(int device) {
+        auto it = devs.find(device);
+        if (it != devs.end()) return it->second;
+        DeviceState d;
+        d.device = device;
+        cudaDeviceProp prop{};
+        PQ_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            panic("device %d (%s) has compute capability %d.%d; this library contains sm_100a code only", device, prop.name,
+                  prop.major, prop.minor);
+        d.sm_count = prop.multiProcessorCount;
+        d.scratch.max_blocks = d.sm_count * 16;
+        PQ_CUDA_CHECK(cudaMalloc(&d.scratch.partials, sizeof(float2) * d.scratch.max_blocks));
+        PQ_CUDA_CHECK(cudaMalloc(&d.scratch.ticket, sizeof(unsigned)));
+        PQ_CUDA_CHECK(cudaMemset(d.scratch.ticket, 0, sizeof(unsigned)));
+        PQ_CUDA_CHECK(cudaMalloc(&d.d_result, 4 * sizeof(float)));
+        PQ_CUDA_CHECK(cudaHostAlloc(&d.h_result, 4 * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
+        PQ_CUDA_CHECK(cudaHostGetDevicePointer(&d.h_result_dev, d.h_result, 0));
+        PQ_CUDA_CHECK(cudaDeviceSynchronize());
+        return devs.emplace(device, d).first->second;
+    }
+
+    void ensure_pipe(DeviceState& d, size_t in_bytes, size_t out_bytes) {
+        if (!d.pipe_ready) {
+            PQ_CUDA_CHECK(cudaStreamCreateWithFlags(&d.s_h2d, cudaStreamNonBlocking));
+            PQ_CUDA_CHECK(cudaStreamCreateWithFlags(&d.s_run, cudaStreamNonBlocking));
+            PQ_CUDA_CHECK(cudaStreamCreateWithFlags(&d.s_d2h, cudaStreamNonBlocking));
+            for (int i = 0; i < kRing; ++i) {
+                PQ_CUDA_CHECK(cudaEventCreateWithFlags(&d.ev_h2d[i], cudaEventDisableTiming));
+                PQ_CUDA_CHECK(cudaEventCreateWithFlags(&d.ev_run[i], cudaEventDisableTiming));
+                PQ_CUDA_CHECK(cudaEventCreateWithFlags(&d.ev_d2h[i], cudaEventDisableTiming));
+            }
+            d.pipe_ready = true;
+        }
+        if (in_bytes > d.in_cap) {
+            for (int i = 0; i < kRing; ++i) {
+                if (d.d_in[i]) PQ_CUDA_CHECK(cudaFree(d.d_in[i]));
+                PQ_CUDA_CHECK(cudaMalloc(&d.d_in[i], in_bytes));
+            }
+            d.in_cap = in_bytes;
+        }
+        if (out_bytes > d.out_cap) {
+            for (int i = 0; i < kRing; ++i) {
+                if (d.d_out[i]) PQ_CUDA_CHECK(cudaFree(d.d_out[i]));
+                PQ_CUDA_CHECK(cudaMalloc(&d.d_out[i], out_bytes));
+            }
+            d.out_cap = out_bytes;
+        }
+    }
+};
+
+namespace {
+
+int require_device() {
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        panic("no usable CUDA device (%s); libpiquant.so has no CPU path -- the B200 build runs on sm_100a only",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    int cur = 0;
+    PQ_CUDA_CHECK(cudaGetDevice(&cur));
+    return cur;
+}
+
+PtrInfo classify(const void* p) {
+    cudaPointerAttributes attr{};
+    const cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return {Where::HostPageable, -1};
+    }
+    switch (attr.type) {
+        case cudaMemoryTypeDevice:
+        case cudaMemoryTypeManaged: return {Where::Device, attr.device};
+        case cudaMemoryTypeHost: return {Where::HostPinned, -1};
+        default: return {Where::HostPageable, -1};
+    }
+}
+
+// RAII: run on `device`, restore the caller's current device afterwards
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    DeviceGuard(int current, int device) : prev(current) {
+        if (device != current) {
+            PQ_CUDA_CHECK(cudaSetDevice(device));
+            switched = true;
+        }
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+enum class Cmd { Quant, Dequant, Requant };
+
+struct Job {
+    Cmd         cmd;
+    const void* in;
+    int         dt_in;
+    void*       out;
+    int         dt_out;      // for Requant: the quantized dtype
+    size_t      numel;
+    QuantParams P;
+    int         mode;
+    int         op;
+};
+
+// bytes of the `in` / `out` buffers for a range of `n` elements
+size_t job_in_bytes(const Job& j, size_t n) { return storage_bytes(j.dt_in, n); }
+size_t job_out_bytes(const Job& j, size_t n) { return j.cmd == Cmd::Requant ? storage_bytes(j.dt_in, n) : storage_bytes(j.dt_out, n); }
+
+int launch_job(const Job& j, const void* in, void* out, size_t n, const LaunchCfg& cfg) {
+    switch (j.cmd) {
+        case Cmd::Quant: return launch_quantize(in, j.dt_in, out, j.dt_out, static_cast<int64_t>(n), j.P, j.mode, cfg);
+        case Cmd::Dequant: return launch_dequantize(in, j.dt_in, out, j.dt_out, static_cast<int64_t>(n), j.P, j.op, cfg);
+        default: return launch_requantize(in, j.dt_in, out, j.dt_out, static_cast<int64_t>(n), j.P, j.mode, j.op, cfg);
+    }
+}
+
+// Host-pointer path: stream the tensor through the GPU in chunks, three stages overlapped on three
+// streams (H2D copy of chunk i+1 | kernel on chunk i | D2H copy of chunk i-1).  Synchronous.
+void run_staged(Context& c, DeviceState& d, const Job& j, bool in_host, bool out_host) {
+    const size_t chunk = kChunkElems;     // multiple of every pack width and of 128 elements
+    const bool out_rmw = j.op == OP_ADD && j.cmd != Cmd::Quant;
+    c.ensure_pipe(d, in_host ? job_in_bytes(j, chunk) : 0, out_host ? job_out_bytes(j, chunk) : 0);
+    // everything already queued on the context stream (producers of device-side operands) goes first
+    cudaEvent_t& gate = d.ev_h2d[0];
+    PQ_CUDA_CHECK(cudaEventRecord(gate, c.stream));
+    PQ_CUDA_CHECK(cudaStreamWaitEvent(d.s_h2d, gate, 0));
+    PQ_CUDA_CHECK(cudaStreamWaitEvent(d.s_run, gate, 0));
+    LaunchCfg cfg{d.s_run, d.sm_count, c.variant};
+    size_t i = 0;
+    for (size_t e0 = 0; e0 < j.numel; e0 += chunk, ++i) {
+        const size_t n = (j.numel - e0 < chunk) ? j.numel - e0 : chunk;
+        const int k = static_cast<int>(i % kRing);
+        const char* src = static_cast<const char*>(j.in) + job_in_bytes(j, e0);
+        char* dst = static_cast<char*>(j.out) + job_out_bytes(j, e0);
+        const void* k_in = src;
+        void* k_out = dst;
+        if (i >= kRing) {
+            // slot reuse: its previous kernel must have consumed d_in, its previous D2H must have drained d_out
+            PQ_CUDA_CHECK(cudaStreamWaitEvent(d.s_h2d, d.ev_run[k], 0));
+            PQ_CUDA_CHECK(cudaStreamWaitEvent(d.s_h2d, d.ev_d2h[k], 0));
+        }
+        if (in_host) {
+            PQ_CUDA_CHECK(cudaMemcpyAsync(d.d_in[k], src, job_in_bytes(j, n), cudaMemcpyHostToDevice, d.s_h2d));
+            k_in = d.d_in[k];
+        }
+        if (out_host) {
+            if (out_rmw) PQ_CUDA_CHECK(cudaMemcpyAsync(d.d_out[k], dst, job_out_bytes(j, n), cudaMemcpyHostToDevice, d.s_h2d));
+            k_out = d.d_out[k];
+        }
+        PQ_CUDA_CHECK(cudaEventRecord(d.ev_h2d[k], d.s_h2d));
+        PQ_CUDA_CHECK(cudaStreamWaitEvent(d.s_run, d.ev_h2d[k], 0));
+        c.launches += launch_job(j, k_in, k_out, n, cfg);
+        PQ_CUDA_CHECK(cudaEventRecord(d.ev_run[k], d.s_run));
+        if (out_host) {
+            PQ_CUDA_CHECK(cudaStreamWaitEvent(d.s_d2h, d.ev_run[k], 0));
+            PQ_CUDA_CHECK(cudaMemcpyAsync(dst, d.d_out[k], job_out_bytes(j, n), cudaMemcpyDeviceToHost, d.s_d2h));
+        }
+        PQ_CUDA_CHECK(cudaEventRecord(d.ev_d2h[k], d.s_d2h));
+    }
+    PQ_CUDA_CHECK(cudaStreamSynchronize(d.s_h2d));
+    PQ_CUDA_CHECK(cudaStreamSynchronize(d.s_run));
+    PQ_CUDA_CHECK(cudaStreamSynchronize(d.s_d2h));
+}
+
+void run_job(Context& c, const Job& j) {
+    if (j.numel == 0) return;
+    std::lock_guard<std::mutex> lock(c.mu);
+    const int cur = require_device();
+    const PtrInfo pi = classify(j.in), po = classify(j.out);
+    int device = cur;
+    if (pi.where == Where::Device) device = pi.device;
+    else if (po.where == Where::Device) device = po.device;
+    if (pi.where == Where::Device && po.where == Where::Device && pi.device != po.device)
+        panic("input lives on device %d but output on device %d; shard-local buffers are required", pi.device, po.device);
+    DeviceGuard guard(cur, device);
+    DeviceState& d = c.dev_state(device);
+    const bool zero_copy = c.host_mode == 1;
+    const bool in_host = pi.where == Where::HostPageable || (pi.where == Where::HostPinned && !zero_copy);
+    const bool out_host = po.where == Where::HostPageable || (po.where == Where::HostPinned && !zero_copy);
+    if (!in_host && !out_host) {
+        const void* in = j.in;
+        void* out = j.out;
+        if (pi.where == Where::HostPinned) PQ_CUDA_CHECK(cudaHostGetDevicePointer(const_cast<void**>(&in), const_cast<void*>(j.in), 0));
+        if (po.where == Where::HostPinned) PQ_CUDA_CHECK(cudaHostGetDevicePointer(&out, j.out, 0));
+        LaunchCfg cfg{c.stream, d.sm_count, c.variant};
+        c.launches += launch_job(j, in, out, j.numel, cfg);
+        // pinned host operands: keep the reference's synchronous contract
+        if (pi.where == Where::HostPinned || po.where == Where::HostPinned) PQ_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        return;
+    }
+    run_staged(c, d, j, in_host, out_host);
+}
+
+int64_t x86_cvttsd_i64(double a) {
+    return (a >= -9223372036854775808.0 && a < 9223372036854775808.0) ? static_cast<int64_t>(a) : std::numeric_limits<int64_t>::min();
+}
+
+// compute_quant_config after the gather (reference src/piquant.cpp:245-258), same double arithmetic
+void params_from_minmax(double r_min, double r_max, int dt_quant, float* scale, int64_t* zero_point) {
+    pq_assert(dtype_is_quant(dt_quant), "type %s is not a quantization type", dtype_name(dt_quant));
+    const uint64_t type_max = (1ull << dtype_bits(dt_quant)) - 1;
+    const int64_t type_min = 0;
+    float s;
+    int64_t z;
+    if (r_max == r_min) {
+        s = 1.0f;
+        z = static_cast<int64_t>((type_max + static_cast<uint64_t>(type_min)) >> 1);
+    } else {
+        const double q_min = static_cast<double>(type_min), q_max = static_cast<double>(type_max);
+        const double sd = (r_max - r_min) / (q_max - q_min);
+        double zp = q_min - r_min / sd;
+        zp = std::fmax(std::fmin(static_cast<double>(x86_cvttsd_i64(std::round(zp))), q_max), q_min);
+        s = static_cast<float>(sd);
+        z = x86_cvttsd_i64(zp);
+    }
+    pq_assert(!std::isnan(s) && s >= 0.0f, "scale must be positive");      // reference src/piquant.cpp:373
+    *scale = s;
+    *zero_point = z;
+}
+
+void compute_params(Context& c, const void* x, int dt_in, size_t n, int dt_quant, float* out_scale, int64_t* out_zp) {
+    pq_assert(dtype_is_quant(dt_quant), "type %s is not a quantization type", dtype_name(dt_quant));
+    std::lock_guard<std::mutex> lock(c.mu);
+    const int cur = require_device();
+    const PtrInfo pi = classify(x);
+    const int device = pi.where == Where::Device ? pi.device : cur;
+    DeviceGuard guard(cur, device);
+    DeviceState& d = c.dev_state(device);
+    float mn = std::numeric_limits<float>::max(), mx = std::numeric_limits<float>::lowest();
+    // an empty shard contributes {+FLT_MAX, -FLT_MAX}; an empty whole tensor ends in a negative scale -> abort below,
+    // exactly what the reference does (reference src/piquant.cpp:238-244, :373)
+    if (n > 0) {
+        if (pi.where == Where::Device || (pi.where == Where::HostPinned && c.host_mode == 1)) {
+            const void* xp = x;
+            if (pi.where == Where::HostPinned) PQ_CUDA_CHECK(cudaHostGetDevicePointer(const_cast<void**>(&xp), const_cast<void*>(x), 0));
+            LaunchCfg cfg{c.stream, d.sm_count, c.variant};
+            c.launches += launch_minmax(xp, dt_in, static_cast<int64_t>(n), d.scratch, d.d_result, c.comm ? nullptr : d.h_result_dev, cfg);
+        } else {
+            // host tensor: chunks through the ring, partial results folded on the host
+            const size_t chunk = kChunkElems * 2;
+            const size_t isz = static_cast<size_t>(dtype_bits(dt_in) / 8);
+            c.ensure_pipe(d, chunk * isz, 0);
+            LaunchCfg cfg{d.s_run, d.sm_count, c.variant};
+            float* h_parts = nullptr;
+            const size_t n_chunks = (n + chunk - 1) / chunk;
+            PQ_CUDA_CHECK(cudaHostAlloc(&h_parts, n_chunks * 4 * sizeof(float), cudaHostAllocMapped));
+            float* h_parts_dev = nullptr;
+            PQ_CUDA_CHECK(cudaHostGetDevicePointer(&h_parts_dev, h_parts, 0));
+            size_t i = 0;
+            for (size_t e0 = 0; e0 < n; e0 += chunk, ++i) {
+                const size_t m = (n - e0 < chunk) ? n - e0 : chunk;
+                const int k = static_cast<int>(i % kRing);
+                if (i >= kRing) PQ_CUDA_CHECK(cudaStreamWaitEvent(d.s_h2d, d.ev_run[k], 0));
+                PQ_CUDA_CHECK(cudaMemcpyAsync(d.d_in[k], static_cast<const char*>(x) + e0 * isz, m * isz, cudaMemcpyHostToDevice, d.s_h2d));
+                PQ_CUDA_CHECK(cudaEventRecord(d.ev_h2d[k], d.s_h2d));
+                PQ_CUDA_CHECK(cudaStreamWaitEvent(d.s_run, d.ev_h2d[k], 0));
+                c.launches += launch_minmax(d.d_in[k], dt_in, static_cast<int64_t>(m), d.scratch, d.d_result, h_parts_dev + 4 * i, cfg);
+                PQ_CUDA_CHECK(cudaEventRecord(d.ev_run[k], d.s_run));
+            }
+            PQ_CUDA_CHECK(cudaStreamSynchronize(d.s_run));
+            for (size_t q = 0; q < n_chunks; ++q) {
+                mn = std::fmin(mn, h_parts[4 * q]);
+                mx = std::fmax(mx, h_parts[4 * q + 1]);
+            }
+            PQ_CUDA_CHECK(cudaFreeHost(h_parts));
+            if (c.comm) {
+                const float r[4] = {mn, mx, -mn, mx};
+                PQ_CUDA_CHECK(cudaMemcpyAsync(d.d_result, r, sizeof(r), cudaMemcpyHostToDevice, c.stream));
+            } else {
+                d.h_result[0] = mn;
+                d.h_result[1] = mx;
+            }
+        }
+    } else {
+        const float r[4] = {mn, mx, -mn, mx};
+        if (c.comm) PQ_CUDA_CHECK(cudaMemcpyAsync(d.d_result, r, sizeof(r), cudaMemcpyHostToDevice, c.stream));
+        d.h_result[0] = mn;
+        d.h_result[1] = mx;
+    }
+    if (c.comm) {
+        // the one exchange step of a sharded tensor: max over ranks of {-min, max}
+        PQ_NCCL_CHECK(Nccl::get().AllReduce(d.d_result + 2, d.d_result + 2, 2, kNcclFloat32, kNcclMax, c.comm, c.stream));
+        PQ_CUDA_CHECK(cudaMemcpyAsync(d.h_result, d.d_result, 4 * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+        PQ_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        mn = -d.h_result[2];
+        mx = d.h_result[3];
+    } else {
+        PQ_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        mn = d.h_result[0];
+        mx = d.h_result[1];
+    }
+    params_from_minmax(static_cast<double>(mn), static_cast<double>(mx), dt_quant, out_scale, out_zp);
+}
+
+Context* as_ctx(piquant_context_t* p) {
+    pq_assert(p != nullptr, "context must not be NULL");
+    return reinterpret_cast<Context*>(p);
+}
+
+void check_float_ptr(const void* p, int dt, const char* what) {
+    pq_assert(p != nullptr, "%s pointer must not be NULL", what);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    pq_assert(a % static_cast<uintptr_t>(dtype_bits(dt) / 8) == 0, "%s pointer %p is not aligned for %s", what, p, dtype_name(dt));
+}
+
+}  // namespace
+}  // namespace pq
+
+using namespace pq;
+
+// -------------------------------------------------------------------------------------------------
+// piquant.h
+// -------------------------------------------------------------------------------------------------
+
+extern "C" piquant_context_t* piquant_context_create(size_t num_threads) {
+    Context* c = new Context();      // no CUDA call here: the Python package creates a context at import time
+    c->num_threads = num_threads;
+    if (const char* v = getenv("PIQUANT_CUDA_VARIANT")) c->variant = atoi(v);
+    if (const char* v = getenv("PIQUANT_CUDA_HOST_MODE")) c->host_mode = (strcmp(v, "zerocopy") == 0 || strcmp(v, "1") == 0) ? 1 : 0;
+    return reinterpret_cast<piquant_context_t*>(c);
+}
+
+extern "C" void piquant_context_destroy(piquant_context_t* ctx) { delete reinterpret_cast<Context*>(ctx); }
+
+extern "C" void piquant_quantize(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                 piquant_dtype_t dtype_out, size_t numel, float scale, int64_t zero_point,
+                                 piquant_round_mode_t mode) {
+    Context* c = as_ctx(ctx);
+    // reference src/piquant.cpp:288-289
+    pq_assert(dtype_is_float(dtype_in), "input dtype (%s) must be a dequantized type", dtype_name(dtype_in));
+    pq_assert(dtype_is_quant(dtype_out), "output dtype (%s) must be a quantized type", dtype_name(dtype_out));
+    pq_assert(mode == PIQUANT_NEAREST || mode == PIQUANT_STOCHASTIC, "invalid round mode %d", static_cast<int>(mode));
+    if (numel == 0) return;
+    check_float_ptr(in, dtype_in, "input");
+    pq_assert(out != nullptr, "output pointer must not be NULL");
+    const float xi = mode == PIQUANT_STOCHASTIC ? c->draw_xi() : 0.0f;
+    Job j{Cmd::Quant, in, dtype_in, out, dtype_out, numel, make_params(scale, zero_point, xi), static_cast<int>(mode), OP_SET};
+    run_job(*c, j);
+}
+
+extern "C" void piquant_dequantize(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                   piquant_dtype_t dtype_out, size_t numel, float scale, int64_t zero_point,
+                                   piquant_reduce_op_t op) {
+    Context* c = as_ctx(ctx);
+    // reference src/piquant.cpp:321-322
+    pq_assert(dtype_is_quant(dtype_in), "input dtype (%s) must be a quantized type", dtype_name(dtype_in));
+    pq_assert(dtype_is_float(dtype_out), "output dtype (%s) must be a dequantized type", dtype_name(dtype_out));
+    pq_assert(op == PIQUANT_REDUCE_OP_SET || op == PIQUANT_REDUCE_OP_ADD, "invalid reduce op %d", static_cast<int>(op));
+    if (numel == 0) return;
+    pq_assert(in != nullptr, "input pointer must not be NULL");
+    check_float_ptr(out, dtype_out, "output");
+    Job j{Cmd::Dequant, in, dtype_in, out, dtype_out, numel, make_params(scale, zero_point, 0.0f), 0, static_cast<int>(op)};
+    run_job(*c, j);
+}
+
+extern "C" void piquant_compute_quant_params_float32(piquant_context_t* ctx, const float* x, size_t n,
+                                                     piquant_dtype_t target_quant_dtype, float* out_scale,
+                                                     int64_t* out_zero_point) {
+    if (n) check_float_ptr(x, DT_F32, "input");
+    compute_params(*as_ctx(ctx), x, DT_F32, n, target_quant_dtype, out_scale, out_zero_point);
+}
+
+extern "C" void piquant_compute_quant_params_bfloat16(piquant_context_t* ctx, const uint16_t* x, size_t n,
+                                                      piquant_dtype_t target_quant_dtype, float* out_scale,
+                                                      int64_t* out_zero_point) {
+    if (n) check_float_ptr(x, DT_BF16, "input");
+    compute_params(*as_ctx(ctx), x, DT_BF16, n, target_quant_dtype, out_scale, out_zero_point);
+}
+
+// -------------------------------------------------------------------------------------------------
+// piquant_cuda.h
+// -------------------------------------------------------------------------------------------------
+
+extern "C" void piquant_cuda_set_stream(piquant_context_t* ctx, void* cuda_stream) {
+    as_ctx(ctx)->stream = static_cast<cudaStream_t>(cuda_stream);
+}
+extern "C" void* piquant_cuda_get_stream(piquant_context_t* ctx) { return as_ctx(ctx)->stream; }
+
+extern "C" void piquant_cuda_synchronize(piquant_context_t* ctx) {
+    require_device();
+    PQ_CUDA_CHECK(cudaStreamSynchronize(as_ctx(ctx)->stream));
+}
+
+extern "C" void piquant_cuda_set_kernel_variant(piquant_context_t* ctx, int variant) {
+    pq_assert(variant >= 0 && variant <= 2, "kernel variant must be 0 (auto), 1 (direct) or 2 (tma), got %d", variant);
+    as_ctx(ctx)->variant = variant;
+}
+
+extern "C" uint64_t piquant_cuda_kernel_launches(piquant_context_t* ctx) { return as_ctx(ctx)->launches; }
+
+extern "C" int piquant_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" void piquant_cuda_set_stochastic_threshold(piquant_context_t* ctx, float xi) {
+    Context* c = as_ctx(ctx);
+    if (xi < 0.0f) {
+        c->xi_fixed = false;
+    } else {
+        pq_assert(xi < 1.0f, "stochastic threshold must be in [0, 1), got %f", static_cast<double>(xi));
+        c->xi_fixed = true;
+        c->xi = xi;
+    }
+}
+
+extern "C" void piquant_cuda_seed(piquant_context_t* ctx, uint64_t seed) { as_ctx(ctx)->rng.seed(seed); }
+
+extern "C" float piquant_cuda_last_stochastic_threshold(piquant_context_t* ctx) { return as_ctx(ctx)->last_xi; }
+
+extern "C" void piquant_cuda_requantize(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in_out, void* out,
+                                        piquant_dtype_t quant_dtype, size_t numel, float scale, int64_t zero_point,
+                                        piquant_round_mode_t mode, piquant_reduce_op_t op) {
+    Context* c = as_ctx(ctx);
+    // reference src/piquant.cpp:353-354
+    pq_assert(dtype_is_float(dtype_in_out), "input dtype must be a dequantized type");
+    pq_assert(dtype_is_quant(quant_dtype), "quant dtype must be a quantized type");
+    if (numel == 0) return;
+    check_float_ptr(in, dtype_in_out, "input");
+    check_float_ptr(out, dtype_in_out, "output");
+    const float xi = mode == PIQUANT_STOCHASTIC ? c->draw_xi() : 0.0f;
+    Job j{Cmd::Requant, in, dtype_in_out, out, quant_dtype, numel, make_params(scale, zero_point, xi), static_cast<int>(mode), static_cast<int>(op)};
+    run_job(*c, j);
+}
+
+extern "C" void piquant_cuda_minmax_async(piquant_context_t* ctx, const void* x, piquant_dtype_t dtype, size_t n, float* out4) {
+    Context* c = as_ctx(ctx);
+    pq_assert(dtype_is_float(dtype), "min/max input must be f32 or bf16");
+    pq_assert(n > 0, "min/max of an empty tensor");
+    std::lock_guard<std::mutex> lock(c->mu);
+    const int cur = require_device();
+    const PtrInfo pi = classify(x), po = classify(out4);
+    pq_assert(pi.where == Where::Device && po.where == Where::Device, "piquant_cuda_minmax_async needs device pointers");
+    DeviceGuard guard(cur, pi.device);
+    DeviceState& d = c->dev_state(pi.device);
+    LaunchCfg cfg{c->stream, d.sm_count, c->variant};
+    c->launches += launch_minmax(x, dtype, static_cast<int64_t>(n), d.scratch, out4, nullptr, cfg);
+}
+
+extern "C" void piquant_cuda_params_from_minmax(float min, float max, piquant_dtype_t target_quant_dtype, float* out_scale,
+                                                int64_t* out_zero_point) {
+    params_from_minmax(static_cast<double>(min), static_cast<double>(max), target_quant_dtype, out_scale, out_zero_point);
+}
+
+extern "C" int piquant_cuda_nccl_unique_id(void* out128) {
+    Nccl& n = Nccl::get();
+    if (!n.ok) return -1;
+    Nccl::UniqueId id;
+    if (n.GetUniqueId(&id) != 0) return -1;
+    memcpy(out128, id.internal, sizeof(id.internal));
+    return 0;
+}
+
+extern "C" void piquant_cuda_comm_init_rank(piquant_context_t* ctx, const void* unique_id128, int nranks, int rank) {
+    Context* c = as_ctx(ctx);
+    Nccl& n = Nccl::get();
+    pq_assert(n.ok, "libnccl.so.2 could not be loaded (set PIQUANT_NCCL_LIB)");
+    pq_assert(c->comm == nullptr, "context already has a communicator");
+    require_device();
+    Nccl::UniqueId id;
+    memcpy(id.internal, unique_id128, sizeof(id.internal));
+    PQ_NCCL_CHECK(n.CommInitRank(&c->comm, nranks, id, rank));
+}
+
+extern "C" void piquant_cuda_comm_destroy(piquant_context_t* ctx) {
+    Context* c = as_ctx(ctx);
+    if (c->comm) {
+        PQ_NCCL_CHECK(Nccl::get().CommDestroy(c->comm));
+        c->comm = nullptr;
+    }
+}

@@ -1,0 +1,177 @@
+// minmax.cu -- whole-tensor {min, max} of an f32 / bf16 stream in ONE launch (sm_100a).
+//
+// Replaces find_min_max_f32 / find_min_max_bf16 (src/kernels/kernels_specialized.inl:1418-1607) and
+// the per-thread partial gather of compute_quant_config (src/piquant.cpp:222-244).
+//
+// Read-only HBM stream, 4 (f32) or 2 (bf16) bytes per element: every thread keeps 4 x LDG.256 in
+// flight, folds them with FMNMX (f32) or packed HMNMX2.BF16 (two bf16 lanes per instruction),
+// then warp shuffles -> one {min,max} per CTA -> the last CTA to finish (atomic ticket) folds the
+// per-CTA partials and publishes the result; no second kernel, no host-side gather.
+// min/max over non-NaN floats is associative and exact, so the result is bit-identical to the
+// reference for any reduction order.  NaNs never win a comparison (the reference's scalar loops use
+// `<` / `>`); accumulators start at +-inf and are clamped to +-FLT_MAX at the end, which equals the
+// reference's +-FLT_MAX start for every input.
+#include <cfloat>
+
+#include "pq_kernels.h"
+
+namespace pq {
+
+__device__ __forceinline__ uint32_t min_bf16x2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("min.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+struct MinMaxArgs {
+    const char* x;
+    int64_t     numel;
+    int64_t     head;       // elements in front of the 32-byte aligned region
+    int64_t     n_items;    // 32-byte items in the aligned region
+    float2*     partials;
+    unsigned*   ticket;
+    float*      result;         // device: {min, max, -min, max}
+    float*      mapped_result;  // device-mapped pinned host copy of the same, or nullptr
+};
+
+template <int IN_DT>
+__global__ void __launch_bounds__(kThreads) minmax_kernel(const MinMaxArgs a) {
+    constexpr int ISZ = IN_DT == DT_F32 ? 4 : 2;
+    constexpr int EPI = 32 / ISZ;     // elements per 32-byte item
+    constexpr int U = 4;
+    constexpr int64_t TILE = static_cast<int64_t>(kThreads) * U;
+    const char* base = a.x + a.head * ISZ;
+    const int64_t n_tiles = (a.n_items + TILE - 1) / TILE;
+
+    float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+    uint32_t pmn = 0x7f807f80u, pmx = 0xff80ff80u;      // packed bf16x2 accumulators (+inf,+inf) / (-inf,-inf)
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t first = tile * TILE + threadIdx.x;
+        uint32_t w[U][8];
+        if (tile * TILE + TILE <= a.n_items) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) ldg_stream(base + (first + static_cast<int64_t>(u) * kThreads) * 32, w[u]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t item = first + static_cast<int64_t>(u) * kThreads;
+                if (item < a.n_items) ldg_stream(base + item * 32, w[u]);
+                else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) w[u][k] = IN_DT == DT_F32 ? 0x7fc00000u : 0x7fc07fc0u;   // NaN: never wins
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if constexpr (IN_DT == DT_F32) {
+                    const float v = __uint_as_float(w[u][k]);
+                    mn = fminf(mn, v);
+                    mx = fmaxf(mx, v);
+                } else {
+                    pmn = min_bf16x2(pmn, w[u][k]);
+                    pmx = max_bf16x2(pmx, w[u][k]);
+                }
+            }
+        }
+    }
+    if constexpr (IN_DT == DT_BF16) {
+        mn = fminf(bf16_lo(pmn), bf16_hi(pmn));
+        mx = fmaxf(bf16_lo(pmx), bf16_hi(pmx));
+    }
+    // ragged head / tail elements: last CTA, scalar loads
+    if (blockIdx.x == gridDim.x - 1) {
+        auto fold = [&](int64_t e) {
+            float v;
+            if constexpr (IN_DT == DT_F32) v = __ldg(reinterpret_cast<const float*>(a.x) + e);
+            else v = bf16_bits_to_f32(__ldg(reinterpret_cast<const unsigned short*>(a.x) + e));
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+        };
+        for (int64_t e = threadIdx.x; e < a.head; e += kThreads) fold(e);
+        for (int64_t e = a.head + a.n_items * EPI + threadIdx.x; e < a.numel; e += kThreads) fold(e);
+    }
+
+    __shared__ float s_mn[kThreads / 32], s_mx[kThreads / 32];
+    __shared__ bool s_last;
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 1; i < kThreads / 32; ++i) { mn = fminf(mn, s_mn[i]); mx = fmaxf(mx, s_mx[i]); }
+        a.partials[blockIdx.x] = make_float2(mn, mx);
+        __threadfence();
+        const unsigned t = atomicAdd(a.ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    mn = __int_as_float(0x7f800000);
+    mx = __int_as_float(0xff800000);
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads) {
+        const float2 p = __ldcg(a.partials + i);
+        mn = fminf(mn, p.x);
+        mx = fmaxf(mx, p.y);
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    __syncthreads();
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 1; i < kThreads / 32; ++i) { mn = fminf(mn, s_mn[i]); mx = fmaxf(mx, s_mx[i]); }
+        mn = fminf(mn, FLT_MAX);       // nothing below FLT_MAX seen -> the reference's start value
+        mx = fmaxf(mx, -FLT_MAX);
+        a.result[0] = mn; a.result[1] = mx; a.result[2] = -mn; a.result[3] = mx;
+        if (a.mapped_result) {
+            a.mapped_result[0] = mn; a.mapped_result[1] = mx; a.mapped_result[2] = -mn; a.mapped_result[3] = mx;
+            __threadfence_system();
+        }
+        *a.ticket = 0u;                // ready for the next launch on this stream
+    }
+}
+
+int launch_minmax(const void* x, int dt, int64_t numel, const MinMaxScratch& scratch, float* result,
+                  float* mapped_result, const LaunchCfg& cfg) {
+    const int isz = dt == DT_F32 ? 4 : 2;
+    const int epi = 32 / isz;
+    MinMaxArgs a;
+    a.x = static_cast<const char*>(x);
+    a.numel = numel;
+    a.partials = scratch.partials;
+    a.ticket = scratch.ticket;
+    a.result = result;
+    a.mapped_result = mapped_result;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(x);
+    int64_t head = static_cast<int64_t>(((32 - (addr & 31u)) & 31u) / isz);   // natural alignment of x is assumed
+    if (head > numel) head = numel;
+    a.head = head;
+    a.n_items = (numel - head) / epi;
+    auto fn = dt == DT_F32 ? minmax_kernel<DT_F32> : minmax_kernel<DT_BF16>;
+    int per_sm = 0;
+    PQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
+    const int64_t tile = static_cast<int64_t>(kThreads) * 4;
+    int64_t blocks_needed = (a.n_items + tile - 1) / tile;
+    int64_t grid = static_cast<int64_t>(cfg.sm_count) * (per_sm > 0 ? per_sm : 1);
+    if (grid > scratch.max_blocks) grid = scratch.max_blocks;
+    if (blocks_needed < grid) grid = blocks_needed;
+    if (grid < 1) grid = 1;
+    fn<<<static_cast<unsigned>(grid), kThreads, 0, cfg.stream>>>(a);
+    PQ_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+}  // namespace pq

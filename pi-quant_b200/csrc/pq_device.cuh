@@ -1,0 +1,294 @@
+// pq_device.cuh -- device-side building blocks of the sm_100a pi-quant kernels.
+//
+// Everything here is per-element arithmetic or register-level packing; the streaming structure
+// (who loads what, how many bytes are in flight) lives in the kernels that include this file.
+//
+// Arithmetic contract (citations are file:line under the reference tree, /root/reference):
+//   * nearest quantize  == one lane of the reference's widest SIMD body
+//       (src/kernels/kernels_specialized.inl:57-82 for f32->u8; :344-361 u4; :686-709 u2):
+//       p = x*inv (RN, no fma), a = p +- 0.5 (RN), t = x86 cvtt(a) (NaN / |a| >= 2^31 -> INT32_MIN),
+//       q = t + zp (32-bit wrap), clamp to [0, qmax].
+//   * f32->u2 nearest   == the generic scalar step, std::round + int64 (src/kernels/quantize.inl:21-26).
+//   * stochastic        == src/kernels/quantize.inl:8-19 with ONE threshold xi per call
+//       (src/piquant.cpp:199-201).
+//   * dequantize        == src/kernels/kernels_specialized.inl:729-1416 bodies, generic
+//       src/kernels/dequantize.inl:8-11 for u2->f32.
+// No fast-math, no FTZ, no implicit contraction: every rounding is spelled with an _rn intrinsic.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pq {
+
+// same numeric values as include/piquant.h (reference include/piquant.h:33-40)
+enum : int { DT_F32 = 0, DT_BF16 = 1, DT_U2 = 2, DT_U4 = 3, DT_U8 = 4 };
+// which per-element formula a quantize cell uses
+enum : int { STEP_BODY = 0, STEP_ROUND64 = 1, STEP_STOCH = 2 };
+enum : int { OP_SET = 0, OP_ADD = 1 };
+
+struct QuantParams {
+    float   inv_scale;   // 1.0f / scale, IEEE divide done once on the host (kernels_specialized.inl:42)
+    float   scale;
+    float   xi;          // per-call stochastic threshold
+    float   bias;        // -(float)zp32 * scale, for the fma-form dequantize (kernels_specialized.inl:1204)
+    int32_t zp32;        // (int32_t)zero_point, the truncation of quantize.inl:112-128
+    int32_t bigzp;       // |zero_point| > 2^29: the int32 fast path of the int64 formulas is not valid
+    int64_t zp64;
+};
+
+// ------------------------------------------------------------------------------------------------
+// global memory access: 4/8/16/32-byte vector loads and stores with streaming cache hints.
+// 32-byte accesses assemble to LDG.E.256 / STG.E.256 on sm_100a: one full 32 B sector per thread.
+// ------------------------------------------------------------------------------------------------
+
+// read-only streaming load (data never written by this kernel): non-coherent path, no L1 allocation
+__device__ __forceinline__ void ldg_stream(const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void ldg_stream(const void* p, uint32_t (&r)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
+}
+__device__ __forceinline__ void ldg_stream(const void* p, uint32_t (&r)[2]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "l"(p));
+}
+__device__ __forceinline__ void ldg_stream(const void* p, uint32_t (&r)[1]) {
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r[0]) : "l"(p));
+}
+
+// coherent load of data this kernel will overwrite (the accumulator of dequantize-ADD)
+__device__ __forceinline__ void ldg_rmw(const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p) : "memory");
+}
+__device__ __forceinline__ void ldg_rmw(const void* p, uint32_t (&r)[4]) {
+    asm volatile("ld.global.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p) : "memory");
+}
+
+__device__ __forceinline__ void stg_stream(void* p, const uint32_t (&r)[8]) {
+    asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void stg_stream(void* p, const uint32_t (&r)[4]) {
+    asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+
+// Load NW 32-bit words from a NW*4-byte aligned address (A32: 32-byte LDG.256, else 16-byte LDG.128).
+template <int NW, bool A32>
+__device__ __forceinline__ void load_words(const void* p, uint32_t (&w)[NW]) {
+    if constexpr (NW >= 8 && A32) {
+        static_assert(NW % 8 == 0);
+#pragma unroll
+        for (int i = 0; i < NW / 8; ++i) {
+            uint32_t t[8];
+            ldg_stream(static_cast<const char*>(p) + 32 * i, t);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[8 * i + k] = t[k];
+        }
+    } else if constexpr (NW >= 4) {
+        static_assert(NW % 4 == 0);
+#pragma unroll
+        for (int i = 0; i < NW / 4; ++i) {
+            uint32_t t[4];
+            ldg_stream(static_cast<const char*>(p) + 16 * i, t);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w[4 * i + k] = t[k];
+        }
+    } else if constexpr (NW == 2) {
+        ldg_stream(p, w);
+    } else {
+        static_assert(NW == 1);
+        ldg_stream(p, w);
+    }
+}
+
+template <int NW, bool A32>
+__device__ __forceinline__ void load_words_rmw(const void* p, uint32_t (&w)[NW]) {
+    if constexpr (A32) {
+        static_assert(NW % 8 == 0);
+#pragma unroll
+        for (int i = 0; i < NW / 8; ++i) {
+            uint32_t t[8];
+            ldg_rmw(static_cast<const char*>(p) + 32 * i, t);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[8 * i + k] = t[k];
+        }
+    } else {
+        static_assert(NW % 4 == 0);
+#pragma unroll
+        for (int i = 0; i < NW / 4; ++i) {
+            uint32_t t[4];
+            ldg_rmw(static_cast<const char*>(p) + 16 * i, t);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w[4 * i + k] = t[k];
+        }
+    }
+}
+
+template <int NW, bool A32>
+__device__ __forceinline__ void store_words(void* p, const uint32_t (&w)[NW]) {
+    if constexpr (A32 && NW >= 8) {
+        static_assert(NW % 8 == 0);
+#pragma unroll
+        for (int i = 0; i < NW / 8; ++i) {
+            uint32_t t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] = w[8 * i + k];
+            stg_stream(static_cast<char*>(p) + 32 * i, t);
+        }
+    } else {
+        static_assert(NW % 4 == 0);
+#pragma unroll
+        for (int i = 0; i < NW / 4; ++i) {
+            uint32_t t[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[k] = w[4 * i + k];
+            stg_stream(static_cast<char*>(p) + 16 * i, t);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bf16 <-> f32
+// ------------------------------------------------------------------------------------------------
+
+// bfp16_t -> fp32_t is a 16-bit shift (include/piquant.hpp:95)
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ float bf16_bits_to_f32(uint16_t b) { return __uint_as_float(static_cast<uint32_t>(b) << 16); }
+
+// two f32 -> packed bf16x2, round-to-nearest-even (include/piquant.hpp:86-90,
+// kernels_specialized.inl:15-32).  Identical to the reference for every non-NaN input; NaN comes
+// out as the canonical quiet NaN (the reference's own two bf16 paths do not agree on NaN payloads).
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint16_t f32_to_bf16_bits(float x) { return static_cast<uint16_t>(pack_bf16x2(x, 0.0f) & 0xffffu); }
+
+// element `e` of an item whose input words are w[]: f32 = one word, bf16 = half a word
+template <int IN_DT, int NW>
+__device__ __forceinline__ float item_elem(const uint32_t (&w)[NW], int e) {
+    if constexpr (IN_DT == DT_F32) return __uint_as_float(w[e]);
+    else return (e & 1) ? bf16_hi(w[e >> 1]) : bf16_lo(w[e >> 1]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// quantize steps
+// ------------------------------------------------------------------------------------------------
+
+// One lane of the reference's SIMD bodies.  copysign(0.5, p) equals the reference's
+// (p >= 0 ? +0.5 : -0.5) after truncation for every p: they differ only at p == -0.0
+// (-0.5 vs +0.5, both truncate to 0) and p == NaN (a is NaN either way).
+__device__ __forceinline__ int32_t quant_step_body(float x, float inv, int32_t zp32, int32_t qmax) {
+    const float p = __fmul_rn(x, inv);
+    const float h = __uint_as_float(0x3f000000u | (__float_as_uint(p) & 0x80000000u));
+    const float a = __fadd_rn(p, h);
+    int32_t t = __float2int_rz(a);                 // saturating; x86 cvttps2dq gives INT32_MIN instead:
+    if (!(a < 2147483648.0f)) t = INT32_MIN;       // NaN and a >= 2^31 ("integer indefinite"); a < -2^31 saturates to it already
+    const int32_t q = static_cast<int32_t>(static_cast<uint32_t>(t) + static_cast<uint32_t>(zp32));   // vpaddd wraps
+    return min(max(q, 0), qmax);
+}
+
+// static_cast<int64_t>(float) on x86-64 (cvttss2si r64): out of range and NaN give INT64_MIN
+__device__ __forceinline__ long long x86_cvtt_i64(float a) {
+    return (a >= -9223372036854775808.0f && a < 9223372036854775808.0f) ? __float2ll_rz(a) : LLONG_MIN;
+}
+
+// clamp(int64(rnd) + zp, 0, qmax) for an integer-valued (or NaN/inf) float `rnd`.
+// Fast path in 32-bit arithmetic when it is provably exact: |rnd| < 2^30 and |zp| <= 2^29.
+__device__ __forceinline__ int32_t finish_i64(float rnd, const QuantParams& P, int32_t qmax) {
+    if (!P.bigzp && fabsf(rnd) < 1073741824.0f) {
+        return min(max(__float2int_rz(rnd) + P.zp32, 0), qmax);
+    }
+    const long long t = x86_cvtt_i64(rnd);
+    const long long q = static_cast<long long>(static_cast<unsigned long long>(t) + static_cast<unsigned long long>(P.zp64));
+    return static_cast<int32_t>(q < 0 ? 0ll : (q > static_cast<long long>(qmax) ? static_cast<long long>(qmax) : q));
+}
+
+// quant_step_scalar_nearest (quantize.inl:21-26)
+__device__ __forceinline__ int32_t quant_step_round64(float x, const QuantParams& P, int32_t qmax) {
+    return finish_i64(roundf(__fmul_rn(x, P.inv_scale)), P, qmax);
+}
+
+// quant_step_scalar_stochastic (quantize.inl:8-19)
+__device__ __forceinline__ int32_t quant_step_stochastic(float x, const QuantParams& P, int32_t qmax) {
+    const float r = __fmul_rn(x, P.inv_scale);
+    const float tr = truncf(r);
+    const float dec = fabsf(__fsub_rn(r, tr));
+    float adj = (P.xi < dec) ? 1.0f : 0.0f;
+    if (r < 0.0f) adj = -adj;
+    return finish_i64(__fadd_rn(tr, adj), P, qmax);
+}
+
+template <int STEP>
+__device__ __forceinline__ int32_t quant_step(float x, const QuantParams& P, int32_t qmax) {
+    if constexpr (STEP == STEP_BODY) return quant_step_body(x, P.inv_scale, P.zp32, qmax);
+    else if constexpr (STEP == STEP_ROUND64) return quant_step_round64(x, P, qmax);
+    else return quant_step_stochastic(x, P, qmax);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dequantize steps
+// ------------------------------------------------------------------------------------------------
+
+// value of one dequantized element before the store op; HAS_BODY selects the SIMD-body formula
+// family of the reference, the other branch is the generic dequant_step (u2->f32 only).
+//   u8/u4 -> f32, u8 -> bf16 : float(int32(q) - zp32) * scale            (kernels_specialized.inl:748-761, :1030-1052, :946-966)
+//   u4/u2 -> bf16            : fma(float(q), scale, -float(zp32)*scale)   (:1204,:1236-1243, :1318,:1361)
+//   u2    -> f32             : float(int64(q) - zp64) * scale             (dequantize.inl:8-11)
+template <int BITS, int OUT_DT>
+__device__ __forceinline__ float dequant_term(uint32_t q, const QuantParams& P) {
+    if constexpr (BITS == 2 && OUT_DT == DT_F32) {
+        return P.bigzp ? __ll2float_rn(static_cast<long long>(static_cast<unsigned long long>(q) - static_cast<unsigned long long>(P.zp64)))
+                       : static_cast<float>(static_cast<int32_t>(q) - P.zp32);
+    } else {
+        return static_cast<float>(static_cast<int32_t>(q - static_cast<uint32_t>(P.zp32)));
+    }
+}
+
+// Final f32 value for out dtype f32 (`prev` used only for ADD).  GCC contracts the reference's
+// mul + add(o) into one fma in its FMA-enabled translation units; we state that fma explicitly.
+template <int BITS, int OP>
+__device__ __forceinline__ float dequant_f32(uint32_t q, float prev, const QuantParams& P) {
+    const float d = dequant_term<BITS, DT_F32>(q, P);
+    if constexpr (OP == OP_ADD) return __fmaf_rn(d, P.scale, prev);
+    else return __fmul_rn(d, P.scale);
+}
+
+// Final f32 value that is then rounded to bf16.
+template <int BITS, int OP>
+__device__ __forceinline__ float dequant_bf16_pre(uint32_t q, float prev, const QuantParams& P) {
+    if constexpr (BITS == 8) {
+        const float d = dequant_term<8, DT_BF16>(q, P);
+        if constexpr (OP == OP_ADD) return __fmaf_rn(d, P.scale, prev);
+        else return __fmul_rn(d, P.scale);
+    } else {
+        const float f = __fmaf_rn(static_cast<float>(q), P.scale, P.bias);
+        if constexpr (OP == OP_ADD) return __fadd_rn(f, prev);
+        else return f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reductions
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace pq

@@ -1,0 +1,96 @@
+// pq_kernels.h -- host-side launch interface of the sm_100a kernels (internal; the public
+// boundary is include/piquant.h + include/piquant_cuda.h).
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "pq_device.cuh"
+
+namespace pq {
+
+constexpr int kThreads = 256;   // threads per CTA of every streaming kernel
+
+struct LaunchCfg {
+    cudaStream_t stream;
+    int          sm_count;   // 148 on B200; grids are sized in multiples of it
+    int          variant;    // 0 = auto, 1 = direct LDG/STG kernels, 2 = TMA (cp.async.bulk) ring kernels
+};
+
+// [[noreturn]] abort with a red message on stderr -- the reference's error convention
+// (src/piquant.cpp:88-98): every violated precondition, CUDA errors included, ends the process.
+[[noreturn]] void panic(const char* fmt, ...);
+
+#define PQ_CUDA_CHECK(expr)                                                                          \
+    do {                                                                                             \
+        cudaError_t pq_err__ = (expr);                                                               \
+        if (pq_err__ != cudaSuccess)                                                                 \
+            ::pq::panic("%s:%d CUDA error %s: %s <- %s", __FILE__, __LINE__, cudaGetErrorName(pq_err__), \
+                        cudaGetErrorString(pq_err__), #expr);                                        \
+    } while (0)
+
+#define pq_assert(expr, msg, ...)                                                                    \
+    do {                                                                                             \
+        if (!(expr)) ::pq::panic("%s:%d Assertion failed: " #expr " <- " msg, __FILE__, __LINE__, ##__VA_ARGS__); \
+    } while (0)
+
+inline int dtype_bits(int dt) {
+    switch (dt) {
+        case DT_F32: return 32;
+        case DT_BF16: return 16;
+        case DT_U2: return 2;
+        case DT_U4: return 4;
+        case DT_U8: return 8;
+        default: return 0;
+    }
+}
+inline bool dtype_is_quant(int dt) { return dt == DT_U2 || dt == DT_U4 || dt == DT_U8; }
+inline bool dtype_is_float(int dt) { return dt == DT_F32 || dt == DT_BF16; }
+inline const char* dtype_name(int dt) {
+    switch (dt) {
+        case DT_F32: return "f32";
+        case DT_BF16: return "bf16";
+        case DT_U2: return "uint2";
+        case DT_U4: return "uint4";
+        case DT_U8: return "uint8";
+        default: return "?";
+    }
+}
+// ceil(numel * bits / 8): storage bytes of a packed quantized tensor (reference src/piquant_internal.hpp:41-44)
+inline size_t packed_bytes(int dt, size_t numel) {
+    const size_t per = 8u / static_cast<size_t>(dtype_bits(dt));
+    return (numel + per - 1) / per;
+}
+inline size_t storage_bytes(int dt, size_t numel) {
+    return dtype_is_quant(dt) ? packed_bytes(dt, numel) : numel * static_cast<size_t>(dtype_bits(dt) / 8);
+}
+
+QuantParams make_params(float scale, int64_t zero_point, float xi);
+
+// Device pointers (or device-accessible mapped host pointers) only.  All launches are asynchronous
+// on cfg.stream.  `mode`: 0 nearest, 1 stochastic (P.xi).  Returns the number of kernels launched.
+int launch_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int mode,
+                    const LaunchCfg& cfg);
+int launch_dequantize(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int op,
+                      const LaunchCfg& cfg);
+// fused quantize -> dequantize, unpacked (reference src/kernels/kernels.inl:30-52)
+int launch_requantize(const void* in, int dt_inout, void* out, int dt_quant, int64_t numel, const QuantParams& P,
+                      int mode, int op, const LaunchCfg& cfg);
+
+// Scratch owned by the context, one set per device.
+struct MinMaxScratch {
+    float2*   partials;   // [max_blocks]
+    unsigned* ticket;     // last-block-done counter, self-resetting
+    int       max_blocks;
+};
+// Writes result[0..3] = {min, max, -min, max} (device memory) and, if `mapped_result` is not null,
+// the same four floats to that device-mapped pinned host address.  min/max start from +-FLT_MAX and
+// NaNs never win, like the reference (src/kernels/kernels_specialized.inl:1418-1607).
+int launch_minmax(const void* x, int dt, int64_t numel, const MinMaxScratch& scratch, float* result,
+                  float* mapped_result, const LaunchCfg& cfg);
+
+// names of the kernels a call with these arguments would launch (introspection for tests / docs)
+const char* quantize_kernel_name(int dt_in, int dt_out, int mode, bool aligned32, int variant);
+
+}  // namespace pq

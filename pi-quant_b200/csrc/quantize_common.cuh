@@ -1,0 +1,38 @@
+// quantize_common.cuh -- pieces shared by the direct (quantize.cu) and TMA (quantize_tma.cu) quantize kernels.
+#pragma once
+
+#include "pq_kernels.h"
+
+namespace pq {
+
+struct QuantArgs {
+    const char* in;          // first element
+    uint8_t*    out;         // first packed byte
+    int64_t     numel;
+    int64_t     head_bytes;  // output bytes in front of the vectorised region
+    int64_t     n_items;     // full 16-byte output items in the vectorised region
+    QuantParams P;
+};
+
+template <int IN_DT>
+__device__ __forceinline__ float load_elem(const char* in, int64_t e) {
+    if constexpr (IN_DT == DT_F32) return __ldg(reinterpret_cast<const float*>(in) + e);
+    else return bf16_bits_to_f32(__ldg(reinterpret_cast<const unsigned short*>(in) + e));
+}
+
+// One packed output byte from up to 8/BITS elements; elements past numel leave zero bits
+// (reference quantize.inl:67-70, :90-98).
+template <int IN_DT, int BITS, int STEP>
+__device__ __forceinline__ void quant_one_byte(const QuantArgs& a, int64_t b) {
+    constexpr int PER = 8 / BITS;
+    constexpr int QMAX = (1 << BITS) - 1;
+    uint32_t byte = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int64_t e = b * PER + k;
+        if (e < a.numel) byte |= static_cast<uint32_t>(quant_step<STEP>(load_elem<IN_DT>(a.in, e), a.P, QMAX)) << (k * BITS);
+    }
+    a.out[b] = static_cast<uint8_t>(byte);
+}
+
+}  // namespace pq

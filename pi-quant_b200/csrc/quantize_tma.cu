@@ -1,0 +1,222 @@
+// quantize_tma.cu -- TMA (cp.async.bulk) ring variant of the quantize kernels for sm_100a.
+//
+// Same arithmetic and same item / ragged decomposition as quantize.cu; what changes is how bytes move:
+//   producer (warp 0, one lane)  : cp.async.bulk global -> shared, 16 KiB input tiles into an
+//                                  S-stage ring, completion counted on a `full` mbarrier per stage
+//                                  (SASS: UBLKCP.S.G + SYNCS.ARRIVE.TRANS64);
+//   consumers (8 warps)          : wait `full`, read 16-byte vectors from shared memory
+//                                  (conflict-free LDS.128), quantize + pack in registers, write the
+//                                  packed bytes to a shared-memory output tile, arrive on `empty`;
+//   store                        : one elected consumer issues cp.async.bulk shared -> global of the
+//                                  packed tile (UBLKCP.G.S), double-buffered with bulk-group waits.
+// No thread computes a global address per element and the loads in flight are bounded by shared
+// memory (S x 16 KiB per CTA, several CTAs per SM), not by registers.
+#include "quantize_common.cuh"
+
+namespace pq {
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kTileVecs = 1024;                 // 16-byte vectors per input tile (16 KiB)
+constexpr int kConsumers = 256;
+constexpr int kTmaThreads = kConsumers + 32;    // warp 0 = producer
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {   // try_wait suspends the thread in hardware for a bounded time; loop until the phase flips
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (TMA, no tensor map needed)
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// 1-D bulk copy shared -> global, tracked by bulk async-groups
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+// order generic-proxy shared-memory writes before async-proxy (TMA) reads of the same bytes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
+
+template <int IN_DT, int BITS>
+struct TmaShape {
+    static constexpr int ISZ = IN_DT == DT_F32 ? 4 : 2;
+    static constexpr int EV = 16 / ISZ;                 // elements per 16-byte vector
+    static constexpr int OBV = EV * BITS / 8;           // packed output bytes per vector: 1, 2, 4 or 8
+    static constexpr int IN_TILE = kTileVecs * 16;
+    static constexpr int OUT_TILE = kTileVecs * OBV;
+    static constexpr int SMEM = kStages * IN_TILE + 2 * OUT_TILE + 2 * kStages * 8;
+};
+
+template <int IN_DT, int BITS, int STEP>
+__global__ void __launch_bounds__(kTmaThreads) quant_tma_kernel(const QuantArgs a) {
+    using S = TmaShape<IN_DT, BITS>;
+    constexpr int PER = 8 / BITS;
+    constexpr int QMAX = (1 << BITS) - 1;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* s_in = smem;
+    unsigned char* s_out = smem + kStages * S::IN_TILE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_out + 2 * S::OUT_TILE);
+    uint64_t* empty = full + kStages;
+
+    const char* in = a.in + a.head_bytes * PER * S::ISZ;
+    uint8_t* out = a.out + a.head_bytes;
+    const int64_t n_vecs = a.n_items * 16 / S::OBV;     // 16-byte input vectors in the vectorised region
+    const int64_t n_tiles = (n_vecs + kTileVecs - 1) / kTileVecs;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kConsumers / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) {
+            int i = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+                const int s = i % kStages;
+                mbar_wait(empty + s, ((i / kStages) & 1) ^ 1);
+                const int64_t v0 = tile * kTileVecs;
+                const int64_t rem = n_vecs - v0;
+                const uint32_t bytes = static_cast<uint32_t>((rem < kTileVecs ? rem : kTileVecs) * 16);
+                mbar_expect_tx(full + s, bytes);
+                tma_load_1d(s_in + s * S::IN_TILE, in + v0 * 16, bytes, full + s);
+            }
+        }
+        return;
+    }
+
+    const int t = threadIdx.x - 32;
+    int i = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+        const int s = i % kStages;
+        const int64_t v0 = tile * kTileVecs;
+        const int64_t rem = n_vecs - v0;
+        const int vecs = static_cast<int>(rem < kTileVecs ? rem : kTileVecs);
+        unsigned char* ob = s_out + (i & 1) * S::OUT_TILE;
+        mbar_wait(full + s, (i / kStages) & 1);
+        const uint4* src = reinterpret_cast<const uint4*>(s_in + s * S::IN_TILE);
+        uint4 v[kTileVecs / kConsumers];
+#pragma unroll
+        for (int j = 0; j < kTileVecs / kConsumers; ++j)
+            if (j * kConsumers + t < vecs) v[j] = src[j * kConsumers + t];
+        __syncwarp();
+        if ((t & 31) == 0) mbar_arrive(empty + s);      // this warp is done with the input stage
+#pragma unroll
+        for (int j = 0; j < kTileVecs / kConsumers; ++j) {
+            const int vi = j * kConsumers + t;
+            if (vi < vecs) {
+                const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                uint32_t o[2] = {0u, 0u};
+#pragma unroll
+                for (int e = 0; e < S::EV; ++e) {
+                    const uint32_t q = static_cast<uint32_t>(quant_step<STEP>(item_elem<IN_DT, 4>(w, e), a.P, QMAX));
+                    o[(e * BITS) / 32] |= q << ((e * BITS) % 32);
+                }
+                if constexpr (S::OBV == 8) *reinterpret_cast<uint2*>(ob + vi * 8) = make_uint2(o[0], o[1]);
+                else if constexpr (S::OBV == 4) *reinterpret_cast<uint32_t*>(ob + vi * 4) = o[0];
+                else if constexpr (S::OBV == 2) *reinterpret_cast<uint16_t*>(ob + vi * 2) = static_cast<uint16_t>(o[0]);
+                else ob[vi] = static_cast<uint8_t>(o[0]);
+            }
+        }
+        fence_proxy_async();
+        if (t == 0) tma_store_wait_read<0>();           // the previous tile's store has drained its buffer
+        consumer_barrier();
+        if (t == 0) {
+            tma_store_1d(out + v0 * S::OBV, ob, static_cast<uint32_t>(vecs * S::OBV));
+            tma_store_commit();
+        }
+    }
+    if (t == 0) tma_store_wait_all<0>();
+
+    if (blockIdx.x == gridDim.x - 1) {
+        const int64_t total = (a.numel + PER - 1) / PER;
+        for (int64_t b = t; b < a.head_bytes; b += kConsumers) quant_one_byte<IN_DT, BITS, STEP>(a, b);
+        for (int64_t b = a.head_bytes + a.n_items * 16 + t; b < total; b += kConsumers) quant_one_byte<IN_DT, BITS, STEP>(a, b);
+    }
+}
+
+template <int IN_DT, int BITS, int STEP>
+void launch_tma_cell(const QuantArgs& a, const LaunchCfg& cfg) {
+    using S = TmaShape<IN_DT, BITS>;
+    auto fn = quant_tma_kernel<IN_DT, BITS, STEP>;
+    static bool configured = false;
+    if (!configured) {
+        PQ_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
+        configured = true;
+    }
+    int per_sm = 0;
+    PQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTmaThreads, S::SMEM));
+    const int64_t n_vecs = a.n_items * 16 / S::OBV;
+    const int64_t n_tiles = (n_vecs + kTileVecs - 1) / kTileVecs;
+    int64_t grid = static_cast<int64_t>(cfg.sm_count) * (per_sm > 0 ? per_sm : 1);
+    if (n_tiles < grid) grid = n_tiles;
+    if (grid < 1) grid = 1;
+    fn<<<static_cast<unsigned>(grid), kTmaThreads, S::SMEM, cfg.stream>>>(a);
+    PQ_CUDA_CHECK(cudaGetLastError());
+}
+
+template <int IN_DT, int BITS>
+void launch_tma_mode(const QuantArgs& a, int mode, const LaunchCfg& cfg) {
+    if (mode == 1) launch_tma_cell<IN_DT, BITS, STEP_STOCH>(a, cfg);
+    else if (IN_DT == DT_F32 && BITS == 2) launch_tma_cell<IN_DT, BITS, STEP_ROUND64>(a, cfg);
+    else launch_tma_cell<IN_DT, BITS, STEP_BODY>(a, cfg);
+}
+
+}  // namespace
+
+int launch_quantize_tma(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int mode,
+                        const LaunchCfg& cfg) {
+    const int per = 8 / dtype_bits(dt_out);
+    const int isz = dtype_bits(dt_in) / 8;
+    QuantArgs a;
+    a.in = static_cast<const char*>(in);
+    a.out = static_cast<uint8_t*>(out);
+    a.numel = numel;
+    a.P = P;
+    const int64_t full_bytes = numel / per;
+    int64_t head = static_cast<int64_t>((16 - (reinterpret_cast<uintptr_t>(out) & 15u)) & 15u);
+    if (head > full_bytes) head = full_bytes;
+    a.head_bytes = head;
+    a.n_items = (full_bytes - head) / 16;
+    const uintptr_t in_vec = reinterpret_cast<uintptr_t>(in) + static_cast<uintptr_t>(head) * per * isz;
+    if (a.n_items <= 0 || (in_vec & 15u) != 0) return 0;     // bulk copies need 16-byte aligned addresses
+    if (dt_in == DT_F32) {
+        if (dt_out == DT_U8) launch_tma_mode<DT_F32, 8>(a, mode, cfg);
+        else if (dt_out == DT_U4) launch_tma_mode<DT_F32, 4>(a, mode, cfg);
+        else launch_tma_mode<DT_F32, 2>(a, mode, cfg);
+    } else {
+        if (dt_out == DT_U8) launch_tma_mode<DT_BF16, 8>(a, mode, cfg);
+        else if (dt_out == DT_U4) launch_tma_mode<DT_BF16, 4>(a, mode, cfg);
+        else launch_tma_mode<DT_BF16, 2>(a, mode, cfg);
+    }
+    return 1;
+}
+
+}  // namespace pq

@@ -1,0 +1,179 @@
+// requantize.cu -- fused quantize -> dequantize ("fake quantization") for sm_100a, output unpacked
+// in the input's float type.  Replaces requant_generic (src/kernels/kernels.inl:30-52), reached in
+// the reference through context::quantize_dequantize_fused (src/piquant.cpp:342-369).
+//
+// Arithmetic is the reference's scalar path for every cell: quant_step_scalar (std::round or the
+// per-call stochastic threshold, int64) followed by the generic dequant_step
+// (src/kernels/dequantize.inl:8-11), which for bf16 multiplies in bf16 arithmetic with the scale
+// rounded to bf16 (include/piquant.hpp:97-103).
+//
+// One thread owns 32 contiguous input bytes (LDG.256) and writes the matching 32 output bytes
+// (STG.256); 4 items per thread per tile.  The quantized integer never leaves registers, so the
+// pass costs one read and one write of the float tensor (plus one read of `out` for ADD).
+#include <cstring>
+
+#include "pq_kernels.h"
+
+namespace pq {
+
+struct RequantArgs {
+    const char* in;
+    char*       out;
+    int64_t     numel;
+    int64_t     head;      // elements in front of the 32-byte aligned region
+    int64_t     n_items;   // 32-byte items
+    QuantParams P;
+    float       scale_bf16;   // scale rounded to bf16 and widened again
+};
+
+template <int DT, int STEP, int OP>
+__device__ __forceinline__ uint32_t requant_elem(float x, uint32_t prev_bits, const RequantArgs& a, int32_t qmax) {
+    const int32_t q = quant_step<STEP>(x, a.P, qmax);
+    const float d = a.P.bigzp
+        ? __ll2float_rn(static_cast<long long>(static_cast<unsigned long long>(static_cast<long long>(q)) - static_cast<unsigned long long>(a.P.zp64)))
+        : static_cast<float>(q - a.P.zp32);
+    if constexpr (DT == DT_F32) {
+        const float prev = __uint_as_float(prev_bits);
+        return __float_as_uint(OP == OP_ADD ? __fmaf_rn(d, a.P.scale, prev) : __fmul_rn(d, a.P.scale));
+    } else {
+        const float db = bf16_bits_to_f32(f32_to_bf16_bits(d));
+        uint16_t r = f32_to_bf16_bits(__fmul_rn(db, a.scale_bf16));
+        if constexpr (OP == OP_ADD) r = f32_to_bf16_bits(__fadd_rn(bf16_bits_to_f32(static_cast<uint16_t>(prev_bits)), bf16_bits_to_f32(r)));
+        return r;
+    }
+}
+
+template <int DT, int STEP, int OP>
+__device__ __forceinline__ void requant_scalar(const RequantArgs& a, int64_t e, int32_t qmax) {
+    if constexpr (DT == DT_F32) {
+        const float x = __ldg(reinterpret_cast<const float*>(a.in) + e);
+        uint32_t* o = reinterpret_cast<uint32_t*>(a.out) + e;
+        *o = requant_elem<DT, STEP, OP>(x, OP == OP_ADD ? *o : 0u, a, qmax);
+    } else {
+        const float x = bf16_bits_to_f32(__ldg(reinterpret_cast<const unsigned short*>(a.in) + e));
+        uint16_t* o = reinterpret_cast<uint16_t*>(a.out) + e;
+        *o = static_cast<uint16_t>(requant_elem<DT, STEP, OP>(x, OP == OP_ADD ? *o : 0u, a, qmax));
+    }
+}
+
+template <int DT, int STEP, int OP>
+__global__ void __launch_bounds__(kThreads) requant_stream_kernel(const RequantArgs a, const int32_t qmax) {
+    constexpr int ISZ = DT == DT_F32 ? 4 : 2;
+    constexpr int EPI = 32 / ISZ;
+    constexpr int U = 4;
+    constexpr int64_t TILE = static_cast<int64_t>(kThreads) * U;
+    const char* in = a.in + a.head * ISZ;
+    char* out = a.out + a.head * ISZ;
+    const int64_t n_tiles = (a.n_items + TILE - 1) / TILE;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t first = tile * TILE + threadIdx.x;
+        uint32_t w[U][8];
+        uint32_t p[U][OP == OP_ADD ? 8 : 1];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t item = first + static_cast<int64_t>(u) * kThreads;
+            if (item < a.n_items) {
+                ldg_stream(in + item * 32, w[u]);
+                if constexpr (OP == OP_ADD) ldg_rmw(out + item * 32, p[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t item = first + static_cast<int64_t>(u) * kThreads;
+            if (item < a.n_items) {
+                uint32_t o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t pw = OP == OP_ADD ? p[u][OP == OP_ADD ? k : 0] : 0u;
+                    if constexpr (DT == DT_F32) {
+                        o[k] = requant_elem<DT, STEP, OP>(__uint_as_float(w[u][k]), pw, a, qmax);
+                    } else {
+                        const uint32_t lo = requant_elem<DT, STEP, OP>(bf16_lo(w[u][k]), pw & 0xffffu, a, qmax);
+                        const uint32_t hi = requant_elem<DT, STEP, OP>(bf16_hi(w[u][k]), pw >> 16, a, qmax);
+                        o[k] = lo | (hi << 16);
+                    }
+                }
+                stg_stream(out + item * 32, o);
+            }
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1) {
+        for (int64_t e = threadIdx.x; e < a.head; e += kThreads) requant_scalar<DT, STEP, OP>(a, e, qmax);
+        for (int64_t e = a.head + a.n_items * EPI + threadIdx.x; e < a.numel; e += kThreads) requant_scalar<DT, STEP, OP>(a, e, qmax);
+    }
+}
+
+// in / out do not share a 32-byte phase: one element per thread
+template <int DT, int STEP, int OP>
+__global__ void __launch_bounds__(kThreads) requant_scalar_kernel(const RequantArgs a, const int32_t qmax) {
+    for (int64_t e = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; e < a.numel;
+         e += static_cast<int64_t>(gridDim.x) * kThreads)
+        requant_scalar<DT, STEP, OP>(a, e, qmax);
+}
+
+template <int DT, int STEP, int OP>
+static void launch_cell(RequantArgs a, int32_t qmax, bool vec, const LaunchCfg& cfg) {
+    auto fn = vec ? requant_stream_kernel<DT, STEP, OP> : requant_scalar_kernel<DT, STEP, OP>;
+    int64_t blocks_needed;
+    if (vec) {
+        const int64_t tile = static_cast<int64_t>(kThreads) * 4;
+        blocks_needed = (a.n_items + tile - 1) / tile;
+    } else {
+        a.head = 0;
+        a.n_items = 0;
+        blocks_needed = (a.numel + kThreads - 1) / kThreads;
+    }
+    int per_sm = 0;
+    PQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
+    int64_t grid = static_cast<int64_t>(cfg.sm_count) * (per_sm > 0 ? per_sm : 1);
+    if (blocks_needed < grid) grid = blocks_needed;
+    if (grid < 1) grid = 1;
+    fn<<<static_cast<unsigned>(grid), kThreads, 0, cfg.stream>>>(a, qmax);
+    PQ_CUDA_CHECK(cudaGetLastError());
+}
+
+template <int DT>
+static void launch_dt(const RequantArgs& a, int32_t qmax, int mode, int op, bool vec, const LaunchCfg& cfg) {
+    if (mode == 1) {
+        if (op == OP_ADD) launch_cell<DT, STEP_STOCH, OP_ADD>(a, qmax, vec, cfg);
+        else launch_cell<DT, STEP_STOCH, OP_SET>(a, qmax, vec, cfg);
+    } else {
+        if (op == OP_ADD) launch_cell<DT, STEP_ROUND64, OP_ADD>(a, qmax, vec, cfg);
+        else launch_cell<DT, STEP_ROUND64, OP_SET>(a, qmax, vec, cfg);
+    }
+}
+
+static float round_to_bf16(float x) {   // include/piquant.hpp:86-90
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) u = ((u >> 16) | 64u) << 16;
+    else u = ((u + (0x7fffu + ((u >> 16) & 1u))) >> 16) << 16;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+
+int launch_requantize(const void* in, int dt_inout, void* out, int dt_quant, int64_t numel, const QuantParams& P,
+                      int mode, int op, const LaunchCfg& cfg) {
+    if (numel <= 0) return 0;
+    const int isz = dtype_bits(dt_inout) / 8;
+    RequantArgs a;
+    a.in = static_cast<const char*>(in);
+    a.out = static_cast<char*>(out);
+    a.numel = numel;
+    a.P = P;
+    a.scale_bf16 = round_to_bf16(P.scale);
+    const uintptr_t ia = reinterpret_cast<uintptr_t>(in), oa = reinterpret_cast<uintptr_t>(out);
+    int64_t head = static_cast<int64_t>(((32 - (ia & 31u)) & 31u) / isz);
+    if (head > numel) head = numel;
+    a.head = head;
+    a.n_items = (numel - head) / (32 / isz);
+    const bool vec = ((ia & 31u) == (oa & 31u)) && a.n_items > 0;
+    const int32_t qmax = (1 << dtype_bits(dt_quant)) - 1;
+    if (dt_inout == DT_F32) launch_dt<DT_F32>(a, qmax, mode, op, vec, cfg);
+    else launch_dt<DT_BF16>(a, qmax, mode, op, vec, cfg);
+    return 1;
+}
+
+}  // namespace pq

@@ -1,0 +1,198 @@
+"""piquant -- B200-native drop-in for the pi-quant Python package.
+
+Mirrors the public names of the reference package (reference python/src/piquant/__init__.py:20-142):
+``RoundMode``, ``ReduceOp``, ``DataType`` and ``Context`` with its ``*_ptr`` methods, bound to
+``libpiquant.so`` through the same C ABI.  Pointers may be CUDA device pointers (the normal case
+here) or host pointers; see ``include/piquant.h`` for the semantics of each.
+"""
+from __future__ import annotations
+
+__version__ = "0.1.0+b200"
+
+import importlib.util
+import multiprocessing
+import weakref
+from enum import Enum, unique
+from functools import lru_cache
+from typing import Optional, Tuple, Union
+
+from piquant._bootstrap import C, ffi
+
+
+@unique
+class RoundMode(Enum):
+    NEAREST = C.PIQUANT_NEAREST
+    STOCHASTIC = C.PIQUANT_STOCHASTIC
+
+
+@unique
+class ReduceOp(Enum):
+    SET = C.PIQUANT_REDUCE_OP_SET
+    ADD = C.PIQUANT_REDUCE_OP_ADD
+
+
+@unique
+class DataType(Enum):
+    F32 = C.PIQUANT_DTYPE_F32
+    BF16 = C.PIQUANT_DTYPE_BF16
+    UINT2 = C.PIQUANT_DTYPE_UINT2
+    UINT4 = C.PIQUANT_DTYPE_UINT4
+    UINT8 = C.PIQUANT_DTYPE_UINT8
+
+    @property
+    def bit_size(self) -> int:
+        return {DataType.F32: 32, DataType.BF16: 16, DataType.UINT2: 2, DataType.UINT4: 4, DataType.UINT8: 8}[self]
+
+    @property
+    def is_quantized(self) -> bool:
+        return self in (DataType.UINT2, DataType.UINT4, DataType.UINT8)
+
+    @property
+    def is_dequantized(self) -> bool:
+        return self in (DataType.F32, DataType.BF16)
+
+    @property
+    def stride(self) -> int:
+        """Bytes of one storage unit (a packed byte for the sub-byte types)."""
+        return max(8, self.bit_size) >> 3
+
+    def storage_bytes(self, numel: int) -> int:
+        """Bytes a contiguous tensor of ``numel`` elements occupies (packed for UINT2/UINT4)."""
+        if self.is_quantized:
+            per = 8 // self.bit_size
+            return (numel + per - 1) // per
+        return numel * (self.bit_size >> 3)
+
+
+class Context:
+    """Owns the dispatcher state of the native library (stream, scratch, stochastic RNG, NCCL comm).
+
+    ``num_threads`` is accepted for source compatibility with the reference
+    (reference python/src/piquant/__init__.py:64-71); the CUDA grid replaces the thread pool.
+    Creating a context never initialises CUDA -- the default one is created at import time.
+    """
+
+    def __init__(self, num_threads: Union[int, None] = None) -> None:
+        if num_threads is None:
+            num_threads = max(multiprocessing.cpu_count() - 1, 1)
+        self._num_threads = num_threads
+        self._ctx = C.piquant_context_create(self._num_threads)
+        self._finalizer = weakref.finalize(self, C.piquant_context_destroy, self._ctx)
+
+    @staticmethod
+    @lru_cache(maxsize=1)
+    def get() -> "Context":
+        """Process-wide default context."""
+        return Context()
+
+    # ---- the reference's pointer-level API --------------------------------------------------------
+
+    def quantize_ptr(self, ptr_in: int, dtype_in: DataType, ptr_out: int, dtype_out: DataType, numel: int,
+                     scale: float, zero_point: int, round_mode: RoundMode) -> None:
+        assert dtype_in.is_dequantized, f"Input dtype must be a dequantized type, but is: {dtype_in}"
+        assert dtype_out.is_quantized, f"Output dtype must be a quantized type, but is: {dtype_out}"
+        assert ptr_in != 0, "Input arr pointer must not be NULL"
+        assert ptr_out != 0, "Output arr pointer must not be NULL"
+        C.piquant_quantize(self._ctx, ffi.cast("const void*", ptr_in), dtype_in.value, ffi.cast("void*", ptr_out),
+                           dtype_out.value, numel, scale, zero_point, round_mode.value)
+
+    def dequantize_ptr(self, ptr_in: int, dtype_in: DataType, ptr_out: int, dtype_out: DataType, numel: int,
+                       scale: float, zero_point: int, reduce_op: ReduceOp) -> None:
+        assert dtype_in.is_quantized, f"Input dtype must be a quantized type, but is: {dtype_in}"
+        assert dtype_out.is_dequantized, f"Output dtype must be a dequantized type, but is: {dtype_out}"
+        assert ptr_in != 0, "Input arr pointer must not be NULL"
+        assert ptr_out != 0, "Output arr pointer must not be NULL"
+        C.piquant_dequantize(self._ctx, ffi.cast("const void*", ptr_in), dtype_in.value, ffi.cast("void*", ptr_out),
+                             dtype_out.value, numel, scale, zero_point, reduce_op.value)
+
+    def compute_quant_params_ptr_float32(self, ptr: int, target_quant_dtype: DataType, numel: int) -> Tuple[float, int]:
+        assert target_quant_dtype.is_quantized, f"Target dtype must be a quantized type, but is: {target_quant_dtype}"
+        assert ptr != 0, "Input arr pointer must not be NULL"
+        scale, zero_point = ffi.new("float*"), ffi.new("int64_t*")
+        C.piquant_compute_quant_params_float32(self._ctx, ffi.cast("const float*", ptr), numel, target_quant_dtype.value,
+                                               scale, zero_point)
+        return scale[0], zero_point[0]
+
+    def compute_quant_params_ptr_bfloat16(self, ptr: int, target_quant_dtype: DataType, numel: int) -> Tuple[float, int]:
+        assert target_quant_dtype.is_quantized, f"Target dtype must be a quantized type, but is: {target_quant_dtype}"
+        assert ptr != 0, "Input arr pointer must not be NULL"
+        scale, zero_point = ffi.new("float*"), ffi.new("int64_t*")
+        C.piquant_compute_quant_params_bfloat16(self._ctx, ffi.cast("const uint16_t*", ptr), numel,
+                                                target_quant_dtype.value, scale, zero_point)
+        return scale[0], zero_point[0]
+
+    # ---- CUDA extensions (include/piquant_cuda.h) -------------------------------------------------
+
+    def requantize_ptr(self, ptr_in: int, dtype_in_out: DataType, ptr_out: int, quant_dtype: DataType, numel: int,
+                       scale: float, zero_point: int, round_mode: RoundMode = RoundMode.NEAREST,
+                       reduce_op: ReduceOp = ReduceOp.SET) -> None:
+        """Fused quantize->dequantize (reference C++ API: context::quantize_dequantize_fused)."""
+        assert dtype_in_out.is_dequantized and quant_dtype.is_quantized
+        assert ptr_in != 0 and ptr_out != 0
+        C.piquant_cuda_requantize(self._ctx, ffi.cast("const void*", ptr_in), dtype_in_out.value,
+                                  ffi.cast("void*", ptr_out), quant_dtype.value, numel, scale, zero_point,
+                                  round_mode.value, reduce_op.value)
+
+    def set_stream(self, cuda_stream: int) -> None:
+        """Order device-pointer calls on this ``cudaStream_t`` (0 = legacy default stream)."""
+        C.piquant_cuda_set_stream(self._ctx, ffi.cast("void*", cuda_stream))
+
+    def get_stream(self) -> int:
+        return int(ffi.cast("uintptr_t", C.piquant_cuda_get_stream(self._ctx)))
+
+    def synchronize(self) -> None:
+        C.piquant_cuda_synchronize(self._ctx)
+
+    def set_kernel_variant(self, variant: int) -> None:
+        """0 = auto, 1 = direct LDG/STG kernels, 2 = TMA ring kernels."""
+        C.piquant_cuda_set_kernel_variant(self._ctx, variant)
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(C.piquant_cuda_kernel_launches(self._ctx))
+
+    def set_stochastic_threshold(self, xi: Optional[float]) -> None:
+        """Fix the per-call stochastic threshold (None: draw a fresh one per call, like the reference)."""
+        C.piquant_cuda_set_stochastic_threshold(self._ctx, -1.0 if xi is None else xi)
+
+    def seed(self, seed: int) -> None:
+        C.piquant_cuda_seed(self._ctx, seed)
+
+    @property
+    def last_stochastic_threshold(self) -> float:
+        return float(C.piquant_cuda_last_stochastic_threshold(self._ctx))
+
+    def minmax_async_ptr(self, ptr: int, dtype: DataType, numel: int, ptr_out4: int) -> None:
+        C.piquant_cuda_minmax_async(self._ctx, ffi.cast("const void*", ptr), dtype.value, numel,
+                                    ffi.cast("float*", ptr_out4))
+
+    @staticmethod
+    def params_from_minmax(mn: float, mx: float, target_quant_dtype: DataType) -> Tuple[float, int]:
+        scale, zero_point = ffi.new("float*"), ffi.new("int64_t*")
+        C.piquant_cuda_params_from_minmax(mn, mx, target_quant_dtype.value, scale, zero_point)
+        return scale[0], zero_point[0]
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = ffi.new("char[128]")
+        if C.piquant_cuda_nccl_unique_id(buf) != 0:
+            raise RuntimeError("libnccl could not be loaded by libpiquant.so")
+        return bytes(ffi.buffer(buf, 128))
+
+    def comm_init_rank(self, unique_id: bytes, nranks: int, rank: int) -> None:
+        assert len(unique_id) == 128
+        C.piquant_cuda_comm_init_rank(self._ctx, ffi.from_buffer(unique_id), nranks, rank)
+
+    def comm_destroy(self) -> None:
+        C.piquant_cuda_comm_destroy(self._ctx)
+
+
+def cuda_device_count() -> int:
+    return int(C.piquant_cuda_device_count())
+
+
+if importlib.util.find_spec("torch") is not None:
+    try:
+        from . import torch  # noqa: F401
+    except ImportError:
+        pass

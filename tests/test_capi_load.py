@@ -1,0 +1,123 @@
+"""CPU-side checks of the drop-in boundary: libpiquant.so builds, loads without a GPU, exports every
+symbol that include/*.h declares with the reference's enum values, never initialises CUDA at context
+creation, and fails LOUDLY (abort, like the reference's panic()) when asked to compute without a device."""
+from __future__ import annotations
+
+import ctypes
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+PKG = ROOT / "pi-quant_b200"
+LIB = PKG / "piquant" / "libpiquant.so"
+
+
+@pytest.fixture(scope="module")
+def lib():
+    sys.path.insert(0, str(PKG))
+    import build as pq_build      # pi-quant_b200/build.py
+
+    pq_build.build()
+    assert LIB.exists()
+    return ctypes.CDLL(str(LIB))
+
+
+def declared_functions(header: Path) -> list[str]:
+    text = re.sub(r"/\*.*?\*/", "", header.read_text(), flags=re.S)
+    return re.findall(r"\b(piquant_\w+)\s*\(", text)
+
+
+def test_exports_every_declared_symbol(lib):
+    names = declared_functions(ROOT / "include" / "piquant.h") + declared_functions(ROOT / "include" / "piquant_cuda.h")
+    assert len(names) >= 21
+    for name in names:
+        assert hasattr(lib, name), f"{name} is declared in include/ but not exported by libpiquant.so"
+    # the reference ABI, name by name (reference include/piquant.h:42-85)
+    for name in ("piquant_context_create", "piquant_context_destroy", "piquant_quantize", "piquant_dequantize",
+                 "piquant_compute_quant_params_float32", "piquant_compute_quant_params_bfloat16"):
+        assert name in names
+
+
+def test_exports_nothing_else(lib):
+    out = subprocess.run(["nm", "-D", "--defined-only", str(LIB)], capture_output=True, text=True, check=True).stdout
+    exported = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    assert exported and all(s.startswith("piquant_") for s in exported), exported
+
+
+def test_enum_values_match_reference_abi():
+    """reference include/piquant.h:23-40, locked by static_asserts in reference src/capi.cpp:9-13"""
+    text = (ROOT / "include" / "piquant.h").read_text()
+    for name, value in (("PIQUANT_NEAREST", 0), ("PIQUANT_STOCHASTIC", 1), ("PIQUANT_REDUCE_OP_SET", 0),
+                        ("PIQUANT_REDUCE_OP_ADD", 1), ("PIQUANT_DTYPE_F32", 0), ("PIQUANT_DTYPE_BF16", 1),
+                        ("PIQUANT_DTYPE_UINT2", 2), ("PIQUANT_DTYPE_UINT4", 3), ("PIQUANT_DTYPE_UINT8", 4)):
+        assert re.search(rf"\b{name}\s*=\s*{value}\b", text), name
+
+
+def test_python_package_mirrors_reference_surface(lib):
+    import piquant
+    from piquant import Context, DataType, ReduceOp, RoundMode
+
+    assert [m.value for m in DataType] == [0, 1, 2, 3, 4]
+    assert RoundMode.NEAREST.value == 0 and RoundMode.STOCHASTIC.value == 1
+    assert ReduceOp.SET.value == 0 and ReduceOp.ADD.value == 1
+    assert DataType.UINT4.bit_size == 4 and DataType.UINT4.is_quantized and DataType.BF16.is_dequantized
+    assert DataType.UINT2.storage_bytes(7) == 2 and DataType.UINT4.storage_bytes(7) == 4 and DataType.F32.storage_bytes(7) == 28
+    for name in ("quantize_ptr", "dequantize_ptr", "compute_quant_params_ptr_float32", "compute_quant_params_ptr_bfloat16"):
+        assert callable(getattr(Context, name))
+    import piquant.torch as pt
+    for name in ("compute_quant_params", "quantize", "dequantize", "torch_to_piquant_dtype", "piquant_to_torch_dtype"):
+        assert callable(getattr(pt, name))
+    ctx = Context(4)                      # no CUDA call: works on a machine without a GPU
+    ctx.set_stochastic_threshold(0.25)
+    ctx.seed(123)
+    assert ctx.kernel_launches == 0
+    assert Context.get() is Context.get()
+    assert piquant.cuda_device_count() >= 0
+
+
+def test_params_from_minmax_is_host_arithmetic(lib):
+    """The double-precision scale / zero-point math runs on the host; check it against the oracle
+    without any GPU (reference src/piquant.cpp:245-258)."""
+    from oracle import port
+    from piquant import Context, DataType
+
+    dt = {port.UINT2: DataType.UINT2, port.UINT4: DataType.UINT4, port.UINT8: DataType.UINT8}
+    cases = [(-1.0, 1.0), (0.0, 1.0), (1.0, 2.0), (-5.0, -1.0), (42.0, 42.0), (-3.0, 5.0), (-3e38, 3e38), (1e-30, 2e-30)]
+    for mn, mx in cases:
+        for d in (port.UINT2, port.UINT4, port.UINT8):
+            assert Context.params_from_minmax(mn, mx, dt[d]) == port.params_from_minmax(mn, mx, d)
+
+
+_ABORT_SNIPPET = r"""
+import ctypes, sys
+lib = ctypes.CDLL(sys.argv[1])
+lib.piquant_context_create.restype = ctypes.c_void_p
+ctx = lib.piquant_context_create(ctypes.c_size_t(1))
+{call}
+print("survived")
+"""
+
+
+def run_snippet(call: str) -> subprocess.CompletedProcess:
+    return subprocess.run([sys.executable, "-c", _ABORT_SNIPPET.format(call=call), str(LIB)], capture_output=True, text=True)
+
+
+def test_invalid_dtype_combination_aborts_like_the_reference(lib):
+    """reference src/piquant.cpp:288-289: wrong dtype class -> panic() -> abort()."""
+    buf = "b = ctypes.create_string_buffer(64)\n"
+    r = run_snippet(buf + "lib.piquant_quantize(ctypes.c_void_p(ctx), b, 4, b, 0, ctypes.c_size_t(8), ctypes.c_float(1.0), ctypes.c_int64(0), 0)")
+    assert r.returncode == -6 and "must be a dequantized type" in r.stderr and "survived" not in r.stdout
+
+
+def test_compute_without_a_gpu_aborts_loudly(lib):
+    import piquant
+
+    if piquant.cuda_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    buf = "b = ctypes.create_string_buffer(64)\n"
+    r = run_snippet(buf + "lib.piquant_quantize(ctypes.c_void_p(ctx), b, 0, b, 4, ctypes.c_size_t(8), ctypes.c_float(1.0), ctypes.c_int64(0), 0)")
+    assert r.returncode == -6 and "no usable CUDA device" in r.stderr and "survived" not in r.stdout

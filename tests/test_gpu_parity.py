@@ -1,0 +1,299 @@
+"""GPU parity: the sm_100a kernels, called through the C ABI of libpiquant.so, against the CPU oracle
+(oracle/piquant_oracle.c, SEM_BODY semantics = what the CUDA library implements) and against the
+committed golden vectors produced by the unmodified reference.
+
+Bar: bit-exact for every integer / packed output, for (scale, zero_point) and for every f32 output;
+bf16 outputs bit-exact except NaN payloads (hardware cvt gives the canonical NaN).
+"""
+from __future__ import annotations
+
+import itertools
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import DEQUANT_CELLS, QUANT_CELLS, as_f32, cell_id, make_input, special_values, unpack
+from oracle import port
+from oracle.port import (ADD, BF16, BITS, F32, NEAREST, SEM_BODY, SET, STOCHASTIC, UINT2, UINT4, UINT8, f32_to_bf16_bits,
+                         packed_bytes)
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = Path(__file__).parent / "golden" / "piquant_golden.npz"
+DTN = {"f32": F32, "bf16": BF16, "u2": UINT2, "u4": UINT4, "u8": UINT8}
+EDGE_SIZES = (1, 2, 3, 4, 5, 15, 16, 17, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 1023, 1025, 4095, 4097)
+VARIANTS = (1, 2)     # 1 = direct LDG/STG kernels, 2 = TMA ring kernels
+
+
+@pytest.fixture(scope="module", params=VARIANTS, ids=("direct", "tma"))
+def gpu(request):
+    from gpu_util import Gpu
+    return Gpu(variant=request.param)
+
+
+@pytest.fixture(scope="module")
+def gpu0():
+    from gpu_util import Gpu
+    return Gpu(variant=0)
+
+
+def bf16_equal(a: np.ndarray, b: np.ndarray) -> bool:
+    """bit-equal, except that any NaN matches any NaN"""
+    an = (a & 0x7FFF) > 0x7F80
+    bn = (b & 0x7FFF) > 0x7F80
+    return bool(np.array_equal(an, bn) and np.array_equal(a[~an], b[~bn]))
+
+
+# ------------------------------------------------------------------------------------------------
+# quantize
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("cell", QUANT_CELLS, ids=cell_id)
+def test_quantize_nearest_sizes_bit_exact(gpu, cell):
+    dt_in, dt_out = cell
+    rng = np.random.default_rng(0x9032002)      # seed of the reference's own tests (test/quant.cpp:31)
+    sizes = list(EDGE_SIZES) + [int(rng.integers(5000, 15000)) for _ in range(6)] + [100003, 1 << 20, (1 << 20) + 77]
+    for n in sizes:
+        scale = float(np.float32(rng.uniform(0.1, 1.0)))
+        zp = int(rng.integers(-128, 256))
+        x = make_input(rng, n, dt_in, -3.0, 3.0)
+        want = port.quantize(x, dt_out, scale, zp, NEAREST, semantics=SEM_BODY)
+        got = gpu.quantize(x, dt_out, scale, zp, NEAREST)
+        assert np.array_equal(got, want), f"n={n} scale={scale} zp={zp}: {np.flatnonzero(got != want)[:8]}"
+
+
+@pytest.mark.parametrize("cell", QUANT_CELLS, ids=cell_id)
+def test_quantize_nearest_any_alignment(gpu, cell):
+    """void* ABI: no alignment promise.  Every (input, output) byte phase takes the head / ragged / byte path."""
+    dt_in, dt_out = cell
+    rng = np.random.default_rng(5)
+    isz = 4 if dt_in == F32 else 2
+    for in_off, out_off in itertools.product((0, isz, 3 * isz, 16, 16 + isz), (0, 1, 3, 7, 13, 16)):
+        n = int(rng.integers(900, 9000))
+        x = make_input(rng, n, dt_in)
+        scale, zp = port.compute_quant_params(x, dt_out)
+        want = port.quantize(x, dt_out, scale, zp, NEAREST, semantics=SEM_BODY)
+        got = gpu.quantize(x, dt_out, scale, zp, NEAREST, in_off=in_off, out_off=out_off)
+        assert np.array_equal(got, want), f"in_off={in_off} out_off={out_off} n={n}"
+
+
+@pytest.mark.parametrize("cell", QUANT_CELLS, ids=cell_id)
+def test_quantize_nearest_adversarial(gpu, cell):
+    """NaN, +-inf, |x/scale| >= 2^31, ties, pred(0.5), zero points outside int32: x86 'integer indefinite'
+    conversion and wrapping adds are reproduced exactly."""
+    dt_in, dt_out = cell
+    rng = np.random.default_rng(1)
+    for scale in (1.0, 0.25, 0.1, 0.0078431):
+        sp = special_values(scale)
+        for zp in (0, 1, 7, 128, 255, -1, -128, 2**31 - 1, -2**31, 2**31, 2**40 + 3, -2**40 - 5, 2**29, 2**29 + 1, -2**29 - 1):
+            pad = rng.uniform(-2, 2, 130).astype(np.float32)
+            xf = np.concatenate([pad, sp, pad, sp, pad[:7]])
+            x = xf if dt_in == F32 else f32_to_bf16_bits(xf)
+            want = port.quantize(x, dt_out, scale, zp, NEAREST, semantics=SEM_BODY)
+            got = gpu.quantize(x, dt_out, scale, zp, NEAREST)
+            assert np.array_equal(got, want), f"scale={scale} zp={zp}: {np.flatnonzero(got != want)[:8]}"
+
+
+@pytest.mark.parametrize("cell", QUANT_CELLS, ids=cell_id)
+def test_quantize_stochastic_bit_exact_for_a_given_threshold(gpu, cell):
+    dt_in, dt_out = cell
+    rng = np.random.default_rng(7)
+    qmax = (1 << BITS[dt_out]) - 1
+    for n in (1, 17, 4097, 12345, 1 << 18):
+        for xi in (0.0, 0.25, 0.5, 0.999):
+            scale = float(np.float32(rng.uniform(0.1, 1.0)))
+            zp = int(rng.integers(0, qmax + 1))
+            x = make_input(rng, n, dt_in, -4.0, 4.0)
+            if n > 100:
+                sp = special_values(scale)
+                x[10:10 + sp.size] = sp if dt_in == F32 else f32_to_bf16_bits(sp)
+            want = port.quantize(x, dt_out, scale, zp, STOCHASTIC, xi=xi, semantics=SEM_BODY)
+            got = gpu.quantize(x, dt_out, scale, zp, STOCHASTIC, xi=xi)
+            assert np.array_equal(got, want), f"n={n} xi={xi}"
+    # big zero points take the 64-bit path
+    x = make_input(rng, 5000, dt_in, -4.0, 4.0)
+    for zp in (2**40 + 3, -2**40 - 5, 2**63 - 1, -2**63):
+        want = port.quantize(x, dt_out, 0.5, zp, STOCHASTIC, xi=0.3, semantics=SEM_BODY)
+        got = gpu.quantize(x, dt_out, 0.5, zp, STOCHASTIC, xi=0.3)
+        assert np.array_equal(got, want), f"zp={zp}"
+
+
+def test_quantize_stochastic_default_draws_one_threshold_per_call(gpu0):
+    """Without an explicit threshold every call draws one xi in [0,1) shared by all elements
+    (reference src/piquant.cpp:199-201): constant input quantizes to a constant."""
+    x = np.full(10000, 0.3, np.float32)
+    seen = set()
+    for _ in range(40):
+        q = gpu0.quantize(x, UINT8, 1.0, 0, STOCHASTIC, xi=None)
+        assert (q == q[0]).all() and q[0] in (0, 1)
+        xi = gpu0.ctx.last_stochastic_threshold
+        assert 0.0 <= xi < 1.0 and q[0] == (1 if xi < np.float32(0.3) else 0)
+        seen.add(int(q[0]))
+    assert seen == {0, 1}
+
+
+def test_quantize_matches_reference_golden(gpu):
+    g = np.load(GOLDEN)
+    for key in [str(k) for k in g["__keys__"] if str(k).startswith("quant/")]:
+        _, dti, dto, mode, n = key.split("/")
+        x, out = g[key + "/x"], g[key + "/out"]
+        scale, zp, xi = g[key + "/p"]
+        got = gpu.quantize(x, DTN[dto], float(scale), int(zp), STOCHASTIC if mode == "st" else NEAREST, xi=float(xi) if mode == "st" else None)
+        assert np.array_equal(got, out), key
+
+
+# ------------------------------------------------------------------------------------------------
+# dequantize
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("cell", DEQUANT_CELLS, ids=cell_id)
+def test_dequantize_bit_exact(gpu0, cell):
+    dt_in, dt_out, op = cell
+    rng = np.random.default_rng(2)
+    sizes = list(EDGE_SIZES) + [int(rng.integers(3000, 40000)) for _ in range(5)] + [1 << 20, (1 << 20) + 5]
+    for n in sizes:
+        q = rng.integers(0, 256, packed_bytes(dt_in, n)).astype(np.uint8)
+        scale = float(np.float32(rng.uniform(0.001, 1.0)))
+        zp = int(rng.integers(0, 1 << BITS[dt_in]))
+        prev = rng.uniform(-1, 1, n).astype(np.float32)
+        prev = prev if dt_out == F32 else f32_to_bf16_bits(prev)
+        want = port.dequantize(q, dt_in, n, dt_out, scale, zp, op, out=prev.copy(), semantics=SEM_BODY)
+        got = gpu0.dequantize(q, dt_in, n, dt_out, scale, zp, op, prev=prev)
+        if dt_out == F32:
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"n={n} scale={scale} zp={zp}"
+        else:
+            assert bf16_equal(got, want), f"n={n} scale={scale} zp={zp}"
+
+
+@pytest.mark.parametrize("cell", DEQUANT_CELLS, ids=cell_id)
+def test_dequantize_any_alignment_and_odd_zero_points(gpu0, cell):
+    dt_in, dt_out, op = cell
+    rng = np.random.default_rng(3)
+    osz = 4 if dt_out == F32 else 2
+    for in_off, out_off in itertools.product((0, 1, 3, 4, 8, 17), (0, osz, 3 * osz, 16, 32 + osz)):
+        n = int(rng.integers(700, 6000))
+        q = rng.integers(0, 256, packed_bytes(dt_in, n)).astype(np.uint8)
+        zp = int(rng.choice([0, 3, -7, 300, -2**31, 2**31 - 1, 2**40 + 1, -2**35]))
+        scale = float(np.float32(rng.uniform(0.01, 2.0)))
+        prev = rng.uniform(-1, 1, n).astype(np.float32)
+        prev = prev if dt_out == F32 else f32_to_bf16_bits(prev)
+        want = port.dequantize(q, dt_in, n, dt_out, scale, zp, op, out=prev.copy(), semantics=SEM_BODY)
+        got = gpu0.dequantize(q, dt_in, n, dt_out, scale, zp, op, prev=prev, in_off=in_off, out_off=out_off)
+        if dt_out == F32:
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"in_off={in_off} out_off={out_off} n={n} zp={zp}"
+        else:
+            assert bf16_equal(got, want), f"in_off={in_off} out_off={out_off} n={n} zp={zp}"
+
+
+def test_dequantize_uint2_f32_add_tail_quirk_is_kept(gpu0):
+    """The reference's generic u2->f32 kernel SETs its 1-3 element tail even for ADD (dequantize.inl:72-86)."""
+    q = np.array([0b11100100, 0b00011011], dtype=np.uint8)
+    prev = np.full(7, 100.0, np.float32)
+    got = gpu0.dequantize(q, UINT2, 7, F32, 1.0, 0, ADD, prev=prev)
+    assert got.tolist() == [100.0, 101.0, 102.0, 103.0, 3.0, 2.0, 1.0]
+
+
+def test_dequantize_matches_reference_golden(gpu0):
+    g = np.load(GOLDEN)
+    for key in [str(k) for k in g["__keys__"] if str(k).startswith("dequant/")]:
+        _, dti, dto, op, n = key.split("/")
+        q, prev, out = g[key + "/q"], g[key + "/prev"], g[key + "/out"]
+        scale, zp = g[key + "/p"]
+        got = gpu0.dequantize(q, DTN[dti], int(n), DTN[dto], float(scale), int(zp), ADD if op == "add" else SET, prev=prev)
+        if dto == "f32":
+            assert np.array_equal(got, out), key
+        else:
+            # the golden's last n % body-width elements come from the reference's scalar tails, which round
+            # twice (see test_oracle_golden.py); the SIMD-body part must be bit-equal
+            body = {"u8": 64, "u4": 128, "u2": 256}[dti]
+            nb = (int(n) // 4 // body) * body
+            assert np.array_equal(got[:nb], out[:nb]), key
+            a, b = port.bf16_bits_to_f32(got).astype(np.float64), port.bf16_bits_to_f32(out).astype(np.float64)
+            qmax = (1 << BITS[DTN[dti]]) - 1
+            assert (np.abs(a - b) <= (np.maximum(np.abs(a), np.abs(b)) + qmax * scale) * 2.0**-7 + scale * 1e-6).all(), key
+
+
+# ------------------------------------------------------------------------------------------------
+# round trips and fused requantize
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("cell", QUANT_CELLS, ids=cell_id)
+def test_round_trip_within_half_a_step(gpu0, cell):
+    """north star: |dequantize(quantize(x)) - x| <= 0.5 * scale (+ bf16 rounding of the output)."""
+    dt_in, dt_q = cell
+    rng = np.random.default_rng(11)
+    n = 200003
+    x = make_input(rng, n, dt_in)
+    scale, zp = gpu0.compute_quant_params(x, dt_q)
+    q = gpu0.quantize(x, dt_q, scale, zp, NEAREST)
+    y = gpu0.dequantize(q, dt_q, n, dt_in, scale, zp, SET)
+    err = np.abs(as_f32(y).astype(np.float64) - as_f32(x).astype(np.float64))
+    tol = 0.5 * scale * (1 + 1e-6) + (2.0**-8 * np.abs(as_f32(x)) + 2.0**-8 * scale if dt_in == BF16 else 1e-7)
+    assert (err <= tol).all(), f"max err {err.max()} vs {scale}"
+
+
+@pytest.mark.parametrize("dt_io,dt_q,op,mode", list(itertools.product((F32, BF16), (UINT2, UINT4, UINT8), (SET, ADD), (NEAREST, STOCHASTIC))),
+                         ids=lambda v: str(v))
+def test_requantize_bit_exact(gpu0, dt_io, dt_q, op, mode):
+    rng = np.random.default_rng(3)
+    for n, off in ((1, 0), (7, 0), (4099, 0), (20000, 4), (1 << 18, 0)):
+        x = make_input(rng, n, dt_io, -2.0, 2.0)
+        scale, zp = port.compute_quant_params(x, dt_q)
+        prev = rng.uniform(-1, 1, n).astype(np.float32)
+        prev = prev if dt_io == F32 else f32_to_bf16_bits(prev)
+        want = port.requantize(x, dt_q, scale, zp, mode, 0.4, op, out=prev.copy(), fma_add=True)
+        got = gpu0.requantize(x, dt_q, scale, zp, mode, 0.4, op, prev=prev, in_off=off, out_off=off)
+        if dt_io == F32:
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"n={n}"
+        else:
+            assert bf16_equal(got, want), f"n={n}"
+
+
+# ------------------------------------------------------------------------------------------------
+# min/max -> (scale, zero_point)
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("dt_in", (F32, BF16), ids=("f32", "bf16"))
+@pytest.mark.parametrize("dt_q", (UINT2, UINT4, UINT8), ids=("u2", "u4", "u8"))
+def test_compute_quant_params_bit_equal(gpu0, dt_in, dt_q):
+    rng = np.random.default_rng(4)
+    isz = 4 if dt_in == F32 else 2
+    cases = [(make_input(rng, n, dt_in, lo, hi), off)
+             for (lo, hi), n, off in zip(((-1, 1), (0, 1), (1, 2), (-5, -1), (-1e-3, 1e3), (-3e38, 3e38), (-1, 1), (-2, 7)),
+                                         (1, 7, 50000, 4097, 1 << 20, 33333, (1 << 22) + 3, 12345),
+                                         (0, 0, 0, isz, 0, 3 * isz, 16, 32 - isz))]
+    consts = [np.full(100, v, np.float32) for v in (42.0, 0.0, -7.5)]
+    cases += [(c if dt_in == F32 else f32_to_bf16_bits(c), 0) for c in consts]
+    nan_mix = rng.uniform(-1, 1, 10000).astype(np.float32)
+    nan_mix[::7] = np.nan
+    cases.append((nan_mix if dt_in == F32 else f32_to_bf16_bits(nan_mix), 0))
+    for x, off in cases:
+        want = port.compute_quant_params(x, dt_q)
+        got = gpu0.compute_quant_params(x, dt_q, in_off=off)
+        assert np.float32(got[0]).tobytes() == np.float32(want[0]).tobytes() and got[1] == want[1], f"n={x.size} off={off}: {got} vs {want}"
+
+
+def test_quant_params_match_reference_golden(gpu0):
+    g = np.load(GOLDEN)
+    for key in [str(k) for k in g["__keys__"] if str(k).startswith("params/")]:
+        dtq = key.split("/")[-1]
+        x = g[key + "/x"]
+        bits, zp = g[key + "/p"]
+        s, z = gpu0.compute_quant_params(x, DTN[dtq])
+        assert int(np.float32(s).view(np.uint32)) == int(bits) and z == int(zp), key
+
+
+def test_known_answers(gpu0):
+    """SURVEY section 8c values probed from the reference build; identity KAT of test/quant.cpp:198-217."""
+    pm1 = np.array([-1, 1], np.float32)
+    assert gpu0.compute_quant_params(pm1, UINT4) == (pytest.approx(0.13333334028720856, abs=0), 8)
+    assert gpu0.compute_quant_params(pm1, UINT2) == (pytest.approx(0.6666666865348816, abs=0), 2)
+    assert gpu0.compute_quant_params(np.array([-3, 5, 1], np.float32), UINT8) == (pytest.approx(0.0313725508749485, abs=0), 96)
+    assert gpu0.compute_quant_params(np.array([1, 2], np.float32), UINT8) == (pytest.approx(0.003921568859368563, abs=0), 0)
+    c = np.full(8191, 42.0, np.float32)
+    s, z = gpu0.compute_quant_params(c, UINT8)
+    assert (s, z) == (1.0, 127)
+    q = gpu0.quantize(c, UINT8, s, z)
+    y = gpu0.dequantize(q, UINT8, c.size, F32, s, z, ADD, prev=np.zeros_like(c))
+    assert np.abs(y - 42.0).max() <= 1e-6
