@@ -1,0 +1,459 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the B200 pi-quant library.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): Gelem/s of f32 -> uint8 nearest-rounding quantize with a per-tensor scale.
+Workload: numel = 1e9 elements PER GPU (the size the metric's roofline target is quoted on), x ~ U(-1,1),
+(scale, zero_point) from compute_quant_params.  One step = one quantize pass over the rank's shard
+= ONE kernel launch through the C ABI (piquant_quantize on device pointers).  Shards are independent
+(no collective on the data path), so N GPUs is weak scaling: value = N * 1e9 / max-over-ranks step time.
+
+Printed JSON keys beyond the base contract:
+  roofline      dominant kernel vs the measured HBM copy peak (MEASURED_PEAKS.json); algorithmic 5 B/elem
+  e2e           same metric through piquant_quantize with PINNED HOST buffers: H2D + kernel + D2H per step
+  cpu_baseline  the unmodified reference (oracle/_ref/libpiquant_ref.so) on this box's host cores, N=1 only
+  extra         the other BASELINE configs, timed the same way (kernel-only, per GPU)
+--impl reference times the reference's own CPU implementation (all host threads) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (str(ROOT), str(ROOT / "pi-quant_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "f32->uint8 nearest quantize throughput"
+UNIT = "Gelem/s"
+NUMEL = int(os.environ.get("PIQUANT_BENCH_NUMEL", 1_000_000_000))
+BYTES_PER_ELEM = 5.0          # 4 B read + 1 B written
+
+
+def measured_peak() -> tuple[float, str]:
+    try:
+        return float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {
+        "workload": f"f32->uint8 nearest-round quantize, per-tensor scale, numel={NUMEL} per GPU (BASELINE metric at its 1e9 size)",
+        "numel_per_gpu": NUMEL,
+        "shards": n_gpus,
+        "input": "x ~ U(-1,1) f32, scale/zero_point from compute_quant_params",
+        "l2": "inputs larger than L2: 5 GB of traffic per step vs 126 MB L2, no flush needed",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.rows: list[list[str]] = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self) -> None:
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) == 8:
+                self.rows.append(parts)
+
+    def mark(self) -> int:
+        return len(self.rows)
+
+    def stop(self) -> None:
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, lo: int, hi: int, window: str) -> dict:
+        rows = self.rows[lo:hi] or self.rows
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "window": "nvidia-smi unavailable"}
+        busy = [r for r in rows if r[3].isdigit() and int(r[3]) >= 50] or rows
+        sm = [float(r[0]) for r in busy if r[0].replace(".", "").isdigit()]
+        reasons = []
+        for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+            if any(r[4 + i].lower().startswith("active") for r in busy):
+                reasons.append(name)
+        power = [float(r[2]) for r in busy if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][1]) if rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(busy), "power_w_max": max(power) if power else None, "window": window}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import piquant
+    from piquant import DataType as D, ReduceOp, RoundMode
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}"
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path behind libpiquant.so)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier() -> None:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = piquant.Context()
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    n = NUMEL
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    x = torch.empty(n, dtype=torch.float32, device=dev).uniform_(-1, 1, generator=gen)
+    q = torch.empty(n, dtype=torch.uint8, device=dev)
+    scale, zp = ctx.compute_quant_params_ptr_float32(x.data_ptr(), D.UINT8, n)
+
+    def step() -> None:
+        ctx.quantize_ptr(x.data_ptr(), D.F32, q.data_ptr(), D.UINT8, n, scale, zp, RoundMode.NEAREST)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = ctx.kernel_launches
+    mark0 = sampler.mark() if sampler else 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = ctx.kernel_launches - launches0
+    window = "timed region"
+    if sampler and total_ms < 600.0:
+        # the timed region is shorter than a few nvidia-smi periods: keep the identical loop running (untimed)
+        # so that the clock samples are taken under the same load
+        t_end = time.perf_counter() + 1.0
+        while time.perf_counter() < t_end:
+            for _ in range(50):
+                step()
+            torch.cuda.synchronize()
+        window = "timed region + 1.0 s untimed continuation of the same step loop"
+    mark1 = sampler.mark() if sampler else 0
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end to end through the C ABI with pinned host buffers ---------------------------------
+    xh = torch.empty(n, dtype=torch.float32).pin_memory()
+    qh = torch.empty(n, dtype=torch.uint8).pin_memory()
+    xh.copy_(x)
+    torch.cuda.synchronize()
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step() -> None:       # synchronous: H2D chunks | kernel | D2H chunks, overlapped inside the library
+        ctx.quantize_ptr(xh.data_ptr(), D.F32, qh.data_ptr(), D.UINT8, n, scale, zp, RoundMode.NEAREST)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    barrier()
+    e2e_value = world * n / e2e_s / 1e9
+    e2e_ok = bool(torch.equal(qh[: 1 << 24], q[: 1 << 24].cpu()))
+
+    # ---- the other BASELINE configs, kernel-only, this rank's GPU -------------------------------
+    extra = {}
+    if rank == 0:
+        extra = run_extra(torch, ctx, D, RoundMode, ReduceOp, x, q, scale, zp, dev)
+    if world > 1:
+        extra_sharded = sharded_params(torch, dist, piquant, ctx, D, x, world, rank, dev)
+        if rank == 0:
+            extra["C3_sharded_compute_quant_params"] = extra_sharded
+
+    # ---- CPU baseline beside it (rank 0, N=1) ----------------------------------------------------
+    cpu_baseline = None
+    parity = None
+    if rank == 0 and world == 1:
+        cpu_baseline, parity = cpu_reference_leg(xh.numpy(), qh.numpy(), scale, zp)
+
+    if sampler:
+        sampler.stop()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_ELEM * n / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get("quantize_f32_u8_1e9_bytes_per_launch")
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32->u8 (f32 multiply/add, int32 clamp)", "data": "synthetic U(-1,1), seeded per rank",
+        "config": workload_config(world),
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_ELEM * n,
+                     "kernel": "quantize f32->u8 (one launch per step)", "of_nominal_8000": round(achieved / 8000.0, 4)},
+        "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": 4 * n * world, "d2h_bytes_per_step": n * world,
+                "steps": e2e_steps, "path": "piquant_quantize(host pinned in, host pinned out): chunked H2D | kernel | D2H pipeline",
+                "output_matches_device_path": e2e_ok},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(mark0, mark1, window),
+        "cpu_baseline": cpu_baseline,
+        "parity_vs_cpu_reference": parity,
+        "extra": extra,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_launches(torch, fn, reps: int, warm: int = 3) -> float:
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
+def run_extra(torch, ctx, D, RoundMode, ReduceOp, x, q, scale, zp, dev) -> dict:
+    peak, _ = measured_peak()
+    out = {}
+
+    def rec(name, numel, bytes_per_elem, t, note=""):
+        gbs = bytes_per_elem * numel / t / 1e9
+        out[name] = {"numel": numel, "ms": round(t * 1e3, 4), "Gelem/s": round(numel / t / 1e9, 1), "GB/s": round(gbs, 1),
+                     "frac_of_measured_peak": round(gbs / peak, 4), "note": note}
+
+    n = x.numel()
+    # C1: the reference's own benchmark size; 3 rotating buffer pairs (409 MB) so that L2 (126 MB) cannot serve it
+    n1 = 27_264_000
+    if n >= 3 * n1:
+        xs = [x[i * n1:(i + 1) * n1] for i in range(3)]
+        qs = [q[i * n1:(i + 1) * n1] for i in range(3)]
+        state = {"i": 0}
+
+        def c1():
+            i = state["i"] = (state["i"] + 1) % 3
+            ctx.quantize_ptr(xs[i].data_ptr(), D.F32, qs[i].data_ptr(), D.UINT8, n1, scale, zp, RoundMode.NEAREST)
+        rec("C1_f32_u8_nearest_27.264M", n1, 5, time_launches(torch, c1, 60, 6), "3 rotating buffer pairs, back-to-back launches")
+    # C2: bf16 -> quint4x2 quantize and dequantize round trip, numel = 1e8
+    n2 = min(100_000_000, n)
+    xb = x[:n2].to(torch.bfloat16)
+    q4 = torch.empty((n2 + 1) // 2, dtype=torch.uint8, device=dev)
+    yb = torch.empty(n2, dtype=torch.bfloat16, device=dev)
+    s4, z4 = ctx.compute_quant_params_ptr_bfloat16(xb.data_ptr(), D.UINT4, n2)
+    rec("C2_bf16_u4_quantize_1e8", n2, 2.5, time_launches(torch, lambda: ctx.quantize_ptr(xb.data_ptr(), D.BF16, q4.data_ptr(), D.UINT4, n2, s4, z4, RoundMode.NEAREST), 20),
+        "250 MB per launch: partly L2-resident on a 126 MB L2")
+    rec("C2_u4_bf16_dequantize_1e8", n2, 2.5, time_launches(torch, lambda: ctx.dequantize_ptr(q4.data_ptr(), D.UINT4, yb.data_ptr(), D.BF16, n2, s4, z4, ReduceOp.SET), 20))
+    err = (yb.float() - xb.float()).abs().max().item()
+    out["C2_round_trip_max_abs_err_over_scale"] = round(err / s4, 4)
+    del xb, q4, yb
+    # C3: compute_quant_params (min/max reduce, synchronous: returns host scalars)
+    t0 = time.perf_counter()
+    reps = 10
+    for _ in range(reps):
+        ctx.compute_quant_params_ptr_float32(x.data_ptr(), D.UINT8, n)
+    rec("C3_compute_quant_params_f32", n, 4, (time.perf_counter() - t0) / reps, "wall clock, includes the stream sync and 16 B D2H")
+    # C4: stochastic rounding
+    rec("C4_f32_u8_stochastic", n, 5, time_launches(torch, lambda: ctx.quantize_ptr(x.data_ptr(), D.F32, q.data_ptr(), D.UINT8, n, scale, zp, RoundMode.STOCHASTIC), 10))
+    # C5: dequantize with ADD store op into an f32 accumulator (one 1/8 shard of 1e9 and the full size)
+    n5 = max(n // 8, 1)
+    acc = torch.zeros(n5, dtype=torch.float32, device=dev)
+    rec("C5_u8_f32_dequantize_add_shard", n5, 9, time_launches(torch, lambda: ctx.dequantize_ptr(q.data_ptr(), D.UINT8, acc.data_ptr(), D.F32, n5, scale, zp, ReduceOp.ADD), 20),
+        "one 1/8 shard of numel")
+    del acc
+    return out
+
+
+def sharded_params(torch, dist, piquant, ctx, D, x, world, rank, dev) -> dict:
+    """BASELINE config 3 on N GPUs: each rank reduces its shard, ONE ncclAllReduce(max) of {-min, max} inside
+    piquant_compute_quant_params_float32 (library-owned communicator, bootstrapped over torch.distributed)."""
+    uid = [piquant.Context.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init_rank(uid[0], world, rank)
+    n = x.numel()
+    for _ in range(3):
+        res = ctx.compute_quant_params_ptr_float32(x.data_ptr(), D.UINT8, n)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 10
+    for _ in range(reps):
+        res = ctx.compute_quant_params_ptr_float32(x.data_ptr(), D.UINT8, n)
+    t = (time.perf_counter() - t0) / reps
+    tt = torch.tensor([t], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ctx.comm_destroy()
+    t = float(tt.item())
+    return {"numel_total": n * world, "ms": round(t * 1e3, 4), "Gelem/s": round(n * world / t / 1e9, 1), "scale": res[0], "zero_point": res[1],
+            "note": "wall clock max over ranks; shard min/max kernel + one 2-float NCCL max all-reduce + sync"}
+
+
+def cpu_reference_leg(x_host, q_gpu_host, scale, zp):
+    """The unmodified reference on this box's host cores (oracle/_ref), bounded to ~10 s, and a full-size
+    bit comparison of its output with the GPU library's."""
+    import numpy as np
+
+    try:
+        from oracle import ref
+        if not ref.available():
+            raise RuntimeError("oracle/_ref not built")
+    except Exception as e:   # fall back to the scalar C port on a small sample
+        from oracle import port
+        m = min(x_host.size, 20_000_000)
+        t0 = time.perf_counter()
+        out = port.quantize(x_host[:m], port.UINT8, scale, zp)
+        t = time.perf_counter() - t0
+        mism = int((out != q_gpu_host[:m]).sum())
+        return ({"value": round(m / t / 1e9, 4), "unit": UNIT, "cores": 1, "kind": "port", "sample": f"first {m} elements, 1 pass ({e})"},
+                {"numel": m, "mismatches": mism})
+    cores = os.cpu_count() or 1
+    c = ref.Context(cores)
+    n = x_host.size
+    out = np.empty(n, dtype=np.uint8)
+    c.quantize(x_host, ref_dt("UINT8"), scale, zp, 0, out=out)       # warm-up pass (also the parity pass)
+    passes, t0 = 0, time.perf_counter()
+    while True:
+        c.quantize(x_host, ref_dt("UINT8"), scale, zp, 0, out=out)
+        passes += 1
+        if time.perf_counter() - t0 > 10.0 or passes >= 50:
+            break
+    t = (time.perf_counter() - t0) / passes
+    mism = int(np.count_nonzero(out != q_gpu_host))
+    c.close()
+    return ({"value": round(n / t / 1e9, 3), "unit": UNIT, "cores": cores, "kind": "reference", "isa": ref.cpu_isa(),
+             "sample": f"numel={n} (the full workload), {passes} passes, {cores} threads, mean"},
+            {"numel": n, "mismatches": mism, "what": "GPU e2e output vs reference CPU output, byte for byte"})
+
+
+def ref_dt(name: str) -> int:
+    from oracle import port
+    return getattr(port, name)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation on the host cores
+# ------------------------------------------------------------------------------------------------
+
+def run_reference(args) -> None:
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    import numpy as np
+
+    from oracle import port
+    kind, cores = "reference", os.cpu_count() or 1
+    try:
+        from oracle import ref
+        if not ref.available():
+            raise RuntimeError
+        c = ref.Context(cores)
+        isa = ref.cpu_isa()
+
+        def quant(xs, out):
+            c.quantize(xs, port.UINT8, scale, zp, 0, out=out)
+    except Exception:
+        kind, cores, isa = "port", 1, "scalar C"
+
+        def quant(xs, out):
+            port.quantize(xs, port.UINT8, scale, zp, out=out)
+    n = NUMEL if kind == "reference" else min(NUMEL, 50_000_000)
+    rng = np.random.default_rng(0)
+    x = np.empty(n, dtype=np.float32)
+    blk = 1 << 24
+    for i in range(0, n, blk):
+        x[i:i + blk] = rng.random(min(blk, n - i), dtype=np.float32) * 2 - 1
+    scale, zp = port.compute_quant_params(x[: 1 << 24], port.UINT8) if kind == "port" else c.compute_quant_params(x, port.UINT8)
+    out = np.empty(n, dtype=np.uint8)
+    t0 = time.perf_counter()
+    quant(x, out)
+    t1 = time.perf_counter() - t0
+    steps, warm = args.steps, max(args.warmup, 1)
+    m = n
+    if t1 * (steps + warm) > 240.0:          # bound the whole run to a few minutes
+        m = max(1 << 20, int(n * 240.0 / (t1 * (steps + warm))))
+    xs, outs = x[:m], out[:m]
+    for _ in range(warm):
+        quant(xs, outs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        quant(xs, outs)
+    t = (time.perf_counter() - t0) / steps
+    value = m / t / 1e9
+    sample = f"numel={m} per step ({'the full workload' if m == NUMEL else 'bounded sample of numel=' + str(NUMEL)}), {cores} threads, isa={isa}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": round(t * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32->u8 (f32 multiply/add, int32 clamp)", "data": "synthetic U(-1,1)", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

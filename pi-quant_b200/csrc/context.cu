@@ -49,6 +49,7 @@ QuantParams make_params(float scale, int64_t zero_point, float xi) {
     volatile float nzp = -static_cast<float>(P.zp32);         // two roundings, never contracted
     P.bias = nzp * scale;
     P.bigzp = (zero_point > (1ll << 29) || zero_point < -(1ll << 29)) ? 1 : 0;
+    P.spec_ok32 = (P.zp32 <= (1 << 29) && P.zp32 >= -(1 << 29)) ? 1 : 0;
     return P;
 }
 

@@ -34,6 +34,7 @@ struct QuantParams {
     float   bias;        // -(float)zp32 * scale, for the fma-form dequantize (kernels_specialized.inl:1204)
     int32_t zp32;        // (int32_t)zero_point, the truncation of quantize.inl:112-128
     int32_t bigzp;       // |zero_point| > 2^29: the int32 fast path of the int64 formulas is not valid
+    int32_t spec_ok32;   // |zp32| <= 2^29: the speculative group path is valid for the int32 (SIMD-body) formula
     int64_t zp64;
 };
 
@@ -233,6 +234,99 @@ __device__ __forceinline__ int32_t quant_step(float x, const QuantParams& P, int
     if constexpr (STEP == STEP_BODY) return quant_step_body(x, P.inv_scale, P.zp32, qmax);
     else if constexpr (STEP == STEP_ROUND64) return quant_step_round64(x, P, qmax);
     else return quant_step_stochastic(x, P, qmax);
+}
+
+// ------------------------------------------------------------------------------------------------
+// quantize, group form: the hot loop.
+//
+// The exact steps above cost ~9-14 instructions per element (range check + select for the x86
+// "integer indefinite", two clamps, shift/or packing) and the ALU pipe, not HBM, becomes the limiter
+// under the power cap.  A group of elements owned by one thread is therefore quantized
+// speculatively: per element FMUL, LOP3, FADD, F2I, IADD and half an I2IP (cvt.pack.sat: clamp to
+// [0, 2^b-1] AND pack two elements in one instruction), plus half an FMNMX3.NAN that folds |a| of
+// the group into one range witness.  If the witness shows every |a| < 2^30 (and |zp| <= 2^29, a
+// host-checked flag) no conversion saturated and no add wrapped, so the speculative result IS the
+// reference's; otherwise (NaN, inf, huge values, extreme zero points) the whole group is redone
+// with the exact steps.  Results are bit-identical either way.
+// ------------------------------------------------------------------------------------------------
+
+// d = (c << 2*BITS) | (sat_uBITS(hi) << BITS) | sat_uBITS(lo)      (SASS: I2IP.U8/U4/U2.S32.SAT)
+template <int BITS>
+__device__ __forceinline__ uint32_t pack_sat2(int32_t hi, int32_t lo, uint32_t c) {
+    uint32_t d;
+    if constexpr (BITS == 8) asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(c));
+    else if constexpr (BITS == 4) asm("cvt.pack.sat.u4.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(c));
+    else asm("cvt.pack.sat.u2.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(c));
+    return d;
+}
+
+// max(|a|, |b|, |c|), NaN-propagating (SASS: FMNMX3.NAN with |.| operand modifiers)
+__device__ __forceinline__ float max3_abs_nan(float a, float b, float c) {
+    float d;
+    asm("max.NaN.abs.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// Speculative step: the integer BEFORE zero point and clamp, plus the float whose magnitude decides
+// whether the speculation was valid.
+template <int STEP>
+__device__ __forceinline__ int32_t quant_spec(float x, const QuantParams& P, float& witness) {
+    const float p = __fmul_rn(x, P.inv_scale);
+    if constexpr (STEP == STEP_BODY) {
+        const float h = __uint_as_float(0x3f000000u | (__float_as_uint(p) & 0x80000000u));
+        const float a = __fadd_rn(p, h);
+        witness = a;
+        return __float2int_rz(a);
+    } else {
+        // std::round(p) (STEP_ROUND64) or trunc(p) +- [xi < frac] (STEP_STOCH), in integer form: for |p| < 2^30
+        // t = trunc(p) is exact, frac = |p - t| is exact, and t +- 1 equals the reference's float sum tr + adj
+        // (for |t| >= 2^24 the fraction is 0 and nothing is added)
+        const int32_t t = __float2int_rz(p);
+        const float dec = fabsf(__fsub_rn(p, static_cast<float>(t)));
+        const bool away = (STEP == STEP_ROUND64) ? (dec >= 0.5f) : (P.xi < dec);
+        const int32_t sgn = (static_cast<int32_t>(__float_as_uint(p)) >> 31) | 1;
+        witness = p;
+        return t + (away ? sgn : 0);
+    }
+}
+
+// Quantize the NE elements held in w[] (f32: one per word, bf16: two per word) and pack them,
+// element 0 in the lowest bits, into o[NE*BITS/32 words] (at least one word; unused high bits are 0).
+template <int IN_DT, int BITS, int STEP, int NW>
+__device__ __forceinline__ void quant_group(const uint32_t (&w)[NW], const QuantParams& P,
+                                            uint32_t (&o)[(NW * (IN_DT == DT_F32 ? 1 : 2) * BITS + 31) / 32]) {
+    constexpr int NE = NW * (IN_DT == DT_F32 ? 1 : 2);
+    constexpr int OW = (NE * BITS + 31) / 32;
+    constexpr int EPW = 32 / BITS;                      // elements per output word
+    constexpr int QMAX = (1 << BITS) - 1;
+    static_assert(NE % 2 == 0, "groups hold an even number of elements");
+    int32_t t[NE];
+    float wit[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) t[e] = quant_spec<STEP>(item_elem<IN_DT, NW>(w, e), P, wit[e]);
+    float m = 0.0f;
+#pragma unroll
+    for (int e = 0; e < NE; e += 2) m = max3_abs_nan(m, wit[e], wit[e + 1]);
+    const bool spec_ok = (STEP == STEP_BODY) ? (P.spec_ok32 != 0) : (P.bigzp == 0);
+    if (spec_ok && m < 1073741824.0f) {
+#pragma unroll
+        for (int j = 0; j < OW; ++j) {
+            uint32_t d = 0;
+            constexpr int LAST = EPW < NE ? EPW : NE;
+#pragma unroll
+            for (int k = LAST - 2; k >= 0; k -= 2)
+                d = pack_sat2<BITS>(t[j * EPW + k + 1] + P.zp32, t[j * EPW + k] + P.zp32, d);
+            o[j] = d;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < OW; ++j) o[j] = 0u;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const uint32_t q = static_cast<uint32_t>(quant_step<STEP>(item_elem<IN_DT, NW>(w, e), P, QMAX));
+            o[(e * BITS) / 32] |= q << ((e * BITS) % 32);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

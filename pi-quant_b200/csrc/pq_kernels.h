@@ -90,7 +90,12 @@ struct MinMaxScratch {
 int launch_minmax(const void* x, int dt, int64_t numel, const MinMaxScratch& scratch, float* result,
                   float* mapped_result, const LaunchCfg& cfg);
 
-// names of the kernels a call with these arguments would launch (introspection for tests / docs)
-const char* quantize_kernel_name(int dt_in, int dt_out, int mode, bool aligned32, int variant);
+// variant 0 ("auto"): which quantize cells go to the TMA ring kernel; every entry is a measurement
+// on B200 at numel = 1e9 (profiles/cellbench_*.md), not a guess
+inline bool quantize_prefers_tma(int dt_in, int dt_out, int mode) {
+    if (dt_in == DT_F32) return true;                       // 98-99 % (u8, u4), 92 % (u2) of the measured copy peak
+    return dt_out == DT_U8 && mode == 0;                    // bf16: only ->u8 nearest (98.7 %); the rest is ALU-heavier per byte
+                                                            // and runs better with the direct kernel's higher occupancy
+}
 
 }  // namespace pq

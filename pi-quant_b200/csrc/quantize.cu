@@ -1,56 +1,83 @@
-// quantize.cu -- f32|bf16 -> uint8|uint4|uint2 streaming kernels for sm_100a.
+// quantize.cu -- f32|bf16 -> uint8|uint4|uint2 direct (LDG/STG) streaming kernels for sm_100a, and
+// the per-cell dispatch between them and the TMA ring kernels of quantize_tma.cu.
 //
 // Replaces the reference's quant_generic router and its 5 SIMD quantize kernels
 // (src/kernels/quantize.inl:101-149, src/kernels/kernels_specialized.inl:35-727).
 //
 // Work decomposition (HBM-bound, every element crosses HBM exactly once):
-//   item  = the elements that produce 16 packed output bytes (16 u8 / 32 u4 / 64 u2 elements);
-//           one thread owns one item: it reads the item's V*sizeof(In) contiguous input bytes with
-//           32-byte LDG.256 (one full DRAM sector per instruction, so no sector is fetched twice)
-//           and writes one 16-byte STG.128 -- a warp writes 512 contiguous bytes.
-//   tile  = kThreads * U items; U is chosen so every thread has >= 128 B of loads in flight.
-//   grid  = persistent: (resident CTAs per SM) x 148 SMs, tiles dealt round-robin so that
-//           concurrently running CTAs stream neighbouring DRAM pages.
-//   ragged= output bytes before the 16-byte aligned region and after the last full item are
-//           produced byte-by-byte by the last CTA of the same launch (no second kernel).
+//   vector = 32 contiguous input bytes (8 f32 / 16 bf16): ONE LDG.256 = one full DRAM sector per
+//            thread.  Vectors are dealt to threads warp-interleaved -- lane l of a warp reads vector
+//            (j*kThreads + tid) -- so each load instruction of a warp covers 1 KiB of contiguous
+//            memory (8 cache lines = 8 L1 wavefronts).  [Measured on B200: giving each thread
+//            64-256 contiguous bytes instead makes one instruction touch 16-32 lines and the L1
+//            wavefront rate, not HBM, bounds the kernel: 36 % of peak for f32->u4.]
+//   tile   = kThreads * 4 vectors: every thread has 4 x 32 B of loads in flight before it converts.
+//   pack   = the 8/16 elements of a vector become 2..16 packed bytes in registers (quant_group: clamp
+//            and pack fused in I2IP) and leave with one STG.{16,32,64,128}; a warp's stores are
+//            contiguous, full sectors.
+//   grid   = persistent: (resident CTAs per SM) x 148 SMs, tiles dealt round-robin.
+//   ragged = output bytes before the 16-byte aligned region and after the last full vector are
+//            produced byte-by-byte by the last CTA of the same launch (no second kernel).
 // Inputs whose alignment rules out vector loads go through the byte-granular kernel.
 #include "quantize_common.cuh"
 
 namespace pq {
 
-template <int IN_DT, int BITS, int STEP, bool A32>
+namespace {
+constexpr int kVecPerThread = 4;
+
+template <int OB>
+__device__ __forceinline__ void store_packed(uint8_t* p, const uint32_t* o) {
+    if constexpr (OB == 16) {
+        const uint32_t t[4] = {o[0], o[1], o[2], o[3]};
+        stg_stream(p, t);
+    } else if constexpr (OB == 8) {
+        asm volatile("st.global.L1::no_allocate.v2.b32 [%0], {%1,%2};" ::"l"(p), "r"(o[0]), "r"(o[1]) : "memory");
+    } else if constexpr (OB == 4) {
+        asm volatile("st.global.L1::no_allocate.b32 [%0], %1;" ::"l"(p), "r"(o[0]) : "memory");
+    } else {
+        static_assert(OB == 2);
+        asm volatile("st.global.L1::no_allocate.b16 [%0], %1;" ::"l"(p), "h"(static_cast<uint16_t>(o[0])) : "memory");
+    }
+}
+}  // namespace
+
+template <int IN_DT, int BITS, int STEP>
 __global__ void __launch_bounds__(kThreads) quant_stream_kernel(const QuantArgs a) {
     constexpr int PER = 8 / BITS;                       // elements per packed byte
-    constexpr int V = 16 * PER;                         // elements per item (16 output bytes)
     constexpr int ISZ = IN_DT == DT_F32 ? 4 : 2;
-    constexpr int NW = V * ISZ / 4;                     // input words per item
-    constexpr int U = (NW * 4 >= 128) ? 1 : 128 / (NW * 4);
-    constexpr int QMAX = (1 << BITS) - 1;
-    constexpr int64_t TILE = static_cast<int64_t>(kThreads) * U;
+    constexpr int EV = 32 / ISZ;                        // elements per 32-byte vector
+    constexpr int OB = EV * BITS / 8;                   // packed output bytes per vector: 2..16
+    constexpr int J = kVecPerThread;
+    constexpr int64_t TILE = static_cast<int64_t>(kThreads) * J;
 
     const char* in = a.in + a.head_bytes * PER * ISZ;
     uint8_t* out = a.out + a.head_bytes;
-    const int64_t n_tiles = (a.n_items + TILE - 1) / TILE;
+    const int64_t n_vecs = a.n_items * 16 / OB;
+    const int64_t n_tiles = (n_vecs + TILE - 1) / TILE;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t first = tile * TILE + threadIdx.x;
-        uint32_t w[U][NW];
+        uint32_t w[J][8];
+        if (tile * TILE + TILE <= n_vecs) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t item = first + static_cast<int64_t>(u) * kThreads;
-            if (item < a.n_items) load_words<NW, A32>(in + item * (NW * 4), w[u]);
-        }
+            for (int j = 0; j < J; ++j) ldg_stream(in + (first + static_cast<int64_t>(j) * kThreads) * 32, w[j]);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t item = first + static_cast<int64_t>(u) * kThreads;
-            if (item < a.n_items) {
-                uint32_t o[4] = {0u, 0u, 0u, 0u};
+            for (int j = 0; j < J; ++j) {
+                uint32_t o[(OB + 3) / 4];
+                quant_group<IN_DT, BITS, STEP, 8>(w[j], a.P, o);
+                store_packed<OB>(out + (first + static_cast<int64_t>(j) * kThreads) * OB, o);
+            }
+        } else {
 #pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    const uint32_t q = static_cast<uint32_t>(quant_step<STEP>(item_elem<IN_DT, NW>(w[u], e), a.P, QMAX));
-                    o[(e * BITS) / 32] |= q << ((e * BITS) % 32);
+            for (int j = 0; j < J; ++j) {
+                const int64_t v = first + static_cast<int64_t>(j) * kThreads;
+                if (v < n_vecs) {
+                    ldg_stream(in + v * 32, w[j]);
+                    uint32_t o[(OB + 3) / 4];
+                    quant_group<IN_DT, BITS, STEP, 8>(w[j], a.P, o);
+                    store_packed<OB>(out + v * OB, o);
                 }
-                stg_stream(out + item * 16, o);
             }
         }
     }
@@ -80,18 +107,16 @@ __global__ void __launch_bounds__(kThreads) quant_bytes_kernel(const QuantArgs a
 using QuantKernel = void (*)(const QuantArgs);
 
 template <int IN_DT, int BITS, int STEP>
-static void launch_cell(const QuantArgs& a0, bool vec, bool a32, const LaunchCfg& cfg) {
+static void launch_cell(const QuantArgs& a0, bool vec, const LaunchCfg& cfg) {
     QuantArgs a = a0;
     constexpr int PER = 8 / BITS;
-    constexpr int ISZ = IN_DT == DT_F32 ? 4 : 2;
-    constexpr int NW = 16 * PER * ISZ / 4;
-    constexpr int U = (NW * 4 >= 128) ? 1 : 128 / (NW * 4);
+    constexpr int OB = (32 / (IN_DT == DT_F32 ? 4 : 2)) * BITS / 8;
     QuantKernel fn;
     int64_t blocks_needed;
     if (vec) {
-        fn = a32 ? quant_stream_kernel<IN_DT, BITS, STEP, true> : quant_stream_kernel<IN_DT, BITS, STEP, false>;
-        const int64_t tile = static_cast<int64_t>(kThreads) * U;
-        blocks_needed = (a.n_items + tile - 1) / tile;
+        fn = quant_stream_kernel<IN_DT, BITS, STEP>;
+        const int64_t tile = static_cast<int64_t>(kThreads) * kVecPerThread;
+        blocks_needed = (a.n_items * 16 / OB + tile - 1) / tile;
     } else {
         fn = quant_bytes_kernel<IN_DT, BITS, STEP>;
         a.head_bytes = 0;
@@ -109,18 +134,18 @@ static void launch_cell(const QuantArgs& a0, bool vec, bool a32, const LaunchCfg
 }
 
 template <int IN_DT, int BITS>
-static void launch_mode(const QuantArgs& a, int mode, bool vec, bool a32, const LaunchCfg& cfg) {
-    if (mode == 1) launch_cell<IN_DT, BITS, STEP_STOCH>(a, vec, a32, cfg);
-    else if (IN_DT == DT_F32 && BITS == 2) launch_cell<IN_DT, BITS, STEP_ROUND64>(a, vec, a32, cfg);   // no SIMD body in the reference: quantize.inl:132-148
-    else launch_cell<IN_DT, BITS, STEP_BODY>(a, vec, a32, cfg);
+static void launch_mode(const QuantArgs& a, int mode, bool vec, const LaunchCfg& cfg) {
+    if (mode == 1) launch_cell<IN_DT, BITS, STEP_STOCH>(a, vec, cfg);
+    else if (IN_DT == DT_F32 && BITS == 2) launch_cell<IN_DT, BITS, STEP_ROUND64>(a, vec, cfg);   // no SIMD body in the reference: quantize.inl:132-148
+    else launch_cell<IN_DT, BITS, STEP_BODY>(a, vec, cfg);
 }
 
 template <int IN_DT>
-static void launch_out(const QuantArgs& a, int dt_out, int mode, bool vec, bool a32, const LaunchCfg& cfg) {
+static void launch_out(const QuantArgs& a, int dt_out, int mode, bool vec, const LaunchCfg& cfg) {
     switch (dt_out) {
-        case DT_U8: launch_mode<IN_DT, 8>(a, mode, vec, a32, cfg); break;
-        case DT_U4: launch_mode<IN_DT, 4>(a, mode, vec, a32, cfg); break;
-        default:    launch_mode<IN_DT, 2>(a, mode, vec, a32, cfg); break;
+        case DT_U8: launch_mode<IN_DT, 8>(a, mode, vec, cfg); break;
+        case DT_U4: launch_mode<IN_DT, 4>(a, mode, vec, cfg); break;
+        default:    launch_mode<IN_DT, 2>(a, mode, vec, cfg); break;
     }
 }
 
@@ -130,10 +155,6 @@ int launch_quantize_tma(const void* in, int dt_in, void* out, int dt_out, int64_
 int launch_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int mode,
                     const LaunchCfg& cfg) {
     if (numel <= 0) return 0;
-    if (cfg.variant == 2) {
-        const int n = launch_quantize_tma(in, dt_in, out, dt_out, numel, P, mode, cfg);
-        if (n) return n;
-    }
     const int per = 8 / dtype_bits(dt_out);
     const int isz = dtype_bits(dt_in) / 8;
     QuantArgs a;
@@ -141,18 +162,22 @@ int launch_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t nu
     a.out = static_cast<uint8_t*>(out);
     a.numel = numel;
     a.P = P;
-    const int64_t total_bytes = (numel + per - 1) / per;
     const int64_t full_bytes = numel / per;                      // bytes whose elements all exist
     int64_t head = static_cast<int64_t>((16 - (reinterpret_cast<uintptr_t>(out) & 15u)) & 15u);
     if (head > full_bytes) head = full_bytes;
     a.head_bytes = head;
     a.n_items = (full_bytes - head) / 16;
     const uintptr_t in_vec = reinterpret_cast<uintptr_t>(in) + static_cast<uintptr_t>(head) * per * isz;
-    const bool vec = a.n_items > 0 && (in_vec & 15u) == 0;
-    const bool a32 = (in_vec & 31u) == 0;
-    (void)total_bytes;
-    if (dt_in == DT_F32) launch_out<DT_F32>(a, dt_out, mode, vec, a32, cfg);
-    else launch_out<DT_BF16>(a, dt_out, mode, vec, a32, cfg);
+    const bool a16 = a.n_items > 0 && (in_vec & 15u) == 0;      // what cp.async.bulk needs
+    const bool a32 = a.n_items > 0 && (in_vec & 31u) == 0;      // what LDG.256 needs
+    // variant 0 = per-cell choice from measurements on B200 (profiles/); 1 = direct, 2 = TMA where alignment allows
+    const bool want_tma = cfg.variant == 2 || (cfg.variant == 0 && quantize_prefers_tma(dt_in, dt_out, mode)) || !a32;
+    if (a16 && want_tma) {
+        const int n = launch_quantize_tma(in, dt_in, out, dt_out, numel, P, mode, cfg);
+        if (n) return n;
+    }
+    if (dt_in == DT_F32) launch_out<DT_F32>(a, dt_out, mode, a32, cfg);
+    else launch_out<DT_BF16>(a, dt_out, mode, a32, cfg);
     return 1;
 }
 

@@ -77,7 +77,6 @@ template <int IN_DT, int BITS, int STEP>
 __global__ void __launch_bounds__(kTmaThreads) quant_tma_kernel(const QuantArgs a) {
     using S = TmaShape<IN_DT, BITS>;
     constexpr int PER = 8 / BITS;
-    constexpr int QMAX = (1 << BITS) - 1;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* s_in = smem;
     unsigned char* s_out = smem + kStages * S::IN_TILE;
@@ -122,27 +121,31 @@ __global__ void __launch_bounds__(kTmaThreads) quant_tma_kernel(const QuantArgs 
         unsigned char* ob = s_out + (i & 1) * S::OUT_TILE;
         mbar_wait(full + s, (i / kStages) & 1);
         const uint4* src = reinterpret_cast<const uint4*>(s_in + s * S::IN_TILE);
-        uint4 v[kTileVecs / kConsumers];
+        constexpr int NV = kTileVecs / kConsumers;       // 16-byte vectors per thread per tile
+        uint4 v[NV];
+        if (vecs == kTileVecs) {
 #pragma unroll
-        for (int j = 0; j < kTileVecs / kConsumers; ++j)
-            if (j * kConsumers + t < vecs) v[j] = src[j * kConsumers + t];
+            for (int j = 0; j < NV; ++j) v[j] = src[j * kConsumers + t];
+        } else {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) v[j] = (j * kConsumers + t < vecs) ? src[j * kConsumers + t] : make_uint4(0u, 0u, 0u, 0u);
+        }
         __syncwarp();
         if ((t & 31) == 0) mbar_arrive(empty + s);      // this warp is done with the input stage
 #pragma unroll
-        for (int j = 0; j < kTileVecs / kConsumers; ++j) {
-            const int vi = j * kConsumers + t;
-            if (vi < vecs) {
-                const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-                uint32_t o[2] = {0u, 0u};
+        for (int j = 0; j < NV; j += 2) {                // two vectors per speculative group
+            const uint32_t w[8] = {v[j].x, v[j].y, v[j].z, v[j].w, v[j + 1].x, v[j + 1].y, v[j + 1].z, v[j + 1].w};
+            uint32_t o[(2 * S::OBV + 3) / 4];
+            quant_group<IN_DT, BITS, STEP, 8>(w, a.P, o);
 #pragma unroll
-                for (int e = 0; e < S::EV; ++e) {
-                    const uint32_t q = static_cast<uint32_t>(quant_step<STEP>(item_elem<IN_DT, 4>(w, e), a.P, QMAX));
-                    o[(e * BITS) / 32] |= q << ((e * BITS) % 32);
+            for (int h = 0; h < 2; ++h) {
+                const int vi = (j + h) * kConsumers + t;
+                if (vecs == kTileVecs || vi < vecs) {
+                    if constexpr (S::OBV == 8) *reinterpret_cast<uint2*>(ob + vi * 8) = make_uint2(o[2 * h], o[2 * h + 1]);
+                    else if constexpr (S::OBV == 4) *reinterpret_cast<uint32_t*>(ob + vi * 4) = o[h];
+                    else if constexpr (S::OBV == 2) *reinterpret_cast<uint16_t*>(ob + vi * 2) = static_cast<uint16_t>(o[0] >> (16 * h));
+                    else ob[vi] = static_cast<uint8_t>(o[0] >> (8 * h));
                 }
-                if constexpr (S::OBV == 8) *reinterpret_cast<uint2*>(ob + vi * 8) = make_uint2(o[0], o[1]);
-                else if constexpr (S::OBV == 4) *reinterpret_cast<uint32_t*>(ob + vi * 4) = o[0];
-                else if constexpr (S::OBV == 2) *reinterpret_cast<uint16_t*>(ob + vi * 2) = static_cast<uint16_t>(o[0]);
-                else ob[vi] = static_cast<uint8_t>(o[0]);
             }
         }
         fence_proxy_async();
@@ -166,10 +169,12 @@ template <int IN_DT, int BITS, int STEP>
 void launch_tma_cell(const QuantArgs& a, const LaunchCfg& cfg) {
     using S = TmaShape<IN_DT, BITS>;
     auto fn = quant_tma_kernel<IN_DT, BITS, STEP>;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;           // one bit per device: the attribute is per device
+    int dev = 0;
+    PQ_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!(configured >> (dev & 63) & 1ull)) {
         PQ_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
-        configured = true;
+        configured |= 1ull << (dev & 63);
     }
     int per_sm = 0;
     PQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTmaThreads, S::SMEM));
