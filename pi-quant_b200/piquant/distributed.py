@@ -1,0 +1,93 @@
+"""piquant.distributed -- a tensor sharded contiguously over the GPUs of one box.
+
+The reference has no distributed code at all; this module is the B200 side of
+SURVEY.md section 8(e).  Shards are independent for quantize / dequantize / requantize -- every rank
+simply calls ``piquant.torch`` on its shard with the shared ``(scale, zero_point)``, no collective.
+The only exchange step is the whole-tensor min/max behind ``compute_quant_params``: each rank
+reduces its shard on its GPU and the ranks combine ``{-min, max}`` with ONE 2-float MAX all-reduce
+(NCCL over NVLink on GPUs; any ``torch.distributed`` backend works, which is how the host logic is
+tested with ``gloo`` on CPUs).  min/max of non-NaN floats is exact and associative, so every rank
+gets bit-identical parameters, equal to the single-GPU / CPU-reference result.
+
+Two equivalent routes are provided:
+* ``compute_quant_params_sharded``   -- min/max kernel -> ``torch.distributed.all_reduce(MAX)``;
+* ``init_native_comm``               -- hands the native library its own NCCL communicator, after which
+  plain ``piquant.torch.compute_quant_params`` / ``piquant_compute_quant_params_*`` do the same
+  all-reduce inside the C library (kernel and ncclAllReduce on one stream, one host sync).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import Context, DataType
+from .torch import _QUANT_TYPES, _bind_stream, torch_to_piquant_dtype
+
+SHARD_ALIGN = 64    # elements: a multiple of every pack width (4 for uint2); 128 B of bf16, 16 B of packed uint2
+
+
+def shard_bounds(numel: int, world_size: int, rank: int, align: int = SHARD_ALIGN) -> Tuple[int, int]:
+    """[begin, end) of rank's contiguous shard.  Boundaries are multiples of ``align`` elements so that
+    packed bytes never straddle two shards and both streams stay vector-aligned; the last rank takes the
+    remainder (the reference splits ranges over threads the same way, reference src/piquant.cpp:145-157)."""
+    assert 0 <= rank < world_size and numel >= 0
+    per = (numel // world_size) // align * align
+    begin = per * rank
+    end = numel if rank == world_size - 1 else per * (rank + 1)
+    return begin, end
+
+
+def combine_minmax(neg_min_max: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> Tuple[float, float]:
+    """All-reduce(MAX) a 2-float tensor ``{-min, max}`` over ``group``; returns the global (min, max)."""
+    assert neg_min_max.numel() == 2 and neg_min_max.dtype == torch.float32
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(neg_min_max, op=dist.ReduceOp.MAX, group=group)
+    mn, mx = (-neg_min_max[0]).item(), neg_min_max[1].item()
+    return mn, mx
+
+
+def local_neg_min_max(shard: torch.Tensor, ctx: Context = Context.get()) -> torch.Tensor:
+    """``{-min, max}`` of a CUDA shard as a 2-float CUDA tensor (asynchronous: one kernel on the current
+    stream).  An empty shard contributes the identity ``{-FLT_MAX, -FLT_MAX}``."""
+    assert shard.is_cuda, "the min/max kernel runs on the GPU; there is no CPU path"
+    out4 = torch.empty(4, dtype=torch.float32, device=shard.device)
+    if shard.numel() == 0:
+        fmax = torch.finfo(torch.float32).max
+        return torch.full((2,), -fmax, dtype=torch.float32, device=shard.device)
+    shard = shard if shard.is_contiguous() else shard.contiguous()
+    _bind_stream(ctx, shard)
+    ctx.minmax_async_ptr(shard.data_ptr(), torch_to_piquant_dtype(shard.dtype), shard.numel(), out4.data_ptr())
+    return out4[2:4]
+
+
+def compute_quant_params_sharded(shard: torch.Tensor, *, dtype: torch.dtype, group: Optional[dist.ProcessGroup] = None,
+                                 ctx: Context = Context.get()) -> Tuple[float, int]:
+    """Whole-tensor ``(scale, zero_point)`` from this rank's shard; identical on every rank."""
+    assert dtype in _QUANT_TYPES, f"Unsupported quantized dtype: {dtype}. Must be one of {list(_QUANT_TYPES)}"
+    mn, mx = combine_minmax(local_neg_min_max(shard, ctx), group)
+    return params_from_minmax(mn, mx, dtype)
+
+
+def params_from_minmax(mn: float, mx: float, dtype: torch.dtype) -> Tuple[float, int]:
+    """The reference's double-precision scale / zero-point arithmetic (reference src/piquant.cpp:245-258),
+    executed by the native library on the host."""
+    return Context.params_from_minmax(mn, mx, torch_to_piquant_dtype(dtype))
+
+
+def init_native_comm(ctx: Context = Context.get(), group: Optional[dist.ProcessGroup] = None) -> None:
+    """Give ``ctx`` its own NCCL communicator spanning ``group`` (bootstrapped through torch.distributed).
+    Afterwards ``compute_quant_params`` on this context returns whole-tensor parameters."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    uid = [Context.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ctx.comm_init_rank(uid[0], world, rank)
+
+
+def destroy_native_comm(ctx: Context = Context.get()) -> None:
+    ctx.comm_destroy()
+
+
+__all__ = ["SHARD_ALIGN", "shard_bounds", "combine_minmax", "local_neg_min_max", "compute_quant_params_sharded",
+           "params_from_minmax", "init_native_comm", "destroy_native_comm", "DataType"]

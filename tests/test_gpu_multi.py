@@ -1,0 +1,84 @@
+"""Sharded path on real GPUs (needs >= 2 devices; `gpurun --gpus 2 -- python -m pytest tests -m gpu`):
+both routes to whole-tensor parameters -- torch.distributed all-reduce and the native library's own
+NCCL communicator -- must return, on every rank, exactly the oracle's single-tensor answer; shards
+quantized independently must concatenate to the whole-tensor result."""
+from __future__ import annotations
+
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
+    for p in (str(ROOT), str(ROOT / "pi-quant_b200"), str(ROOT / "tests")):
+        sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import piquant
+        import piquant.torch as pt
+        from oracle import port as orc
+        from piquant import distributed as pd
+
+        rng = np.random.default_rng(321)
+        x = rng.uniform(-2, 5, numel).astype(np.float32)
+        b, e = pd.shard_bounds(numel, world, rank)
+        shard = torch.from_numpy(x[b:e]).cuda()
+        ctx = piquant.Context()
+        res = {}
+        for name, tdt, odt in (("u8", torch.quint8, orc.UINT8), ("u4", torch.quint4x2, orc.UINT4)):
+            want = orc.compute_quant_params(x, odt)
+            got_torch = pd.compute_quant_params_sharded(shard, dtype=tdt, ctx=ctx)
+            pd.init_native_comm(ctx)
+            got_native = pt.compute_quant_params(shard, dtype=tdt, ctx=ctx)
+            pd.destroy_native_comm(ctx)
+            got_local = pt.compute_quant_params(shard, dtype=tdt, ctx=ctx)      # local again after destroy
+            want_local = orc.compute_quant_params(x[b:e], odt)
+            qs = pt.quantize(shard, scale=want[0], zero_point=want[1], dtype=tdt, ctx=ctx)
+            nbytes = orc.packed_bytes(odt, e - b)
+            raw = torch.empty(0, dtype=torch.uint8, device=qs.device).set_(qs.untyped_storage())[:nbytes].cpu().numpy()
+            whole = orc.quantize(x, odt, want[0], want[1])
+            per = 8 // orc.BITS[odt]
+            res[name] = (got_torch == want, got_native == want, got_local == want_local,
+                         bool(np.array_equal(raw, whole[b // per: b // per + nbytes])))
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_params_and_quantize_two_gpus():
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 3_000_001, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res in results:
+        for name, flags in res.items():
+            assert all(flags), (rank, name, flags)
