@@ -248,7 +248,7 @@ def run_ours(args) -> None:
         "parity_vs_cpu_reference": parity,
         "extra": extra,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -439,7 +439,24 @@ def run_reference(args) -> None:
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout() -> None:
+    """Only the JSON line may reach stdout: libraries (NCCL prints its version banner there) are sent to stderr."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main() -> None:
@@ -449,6 +466,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(kThreads) dequant_stream_kernel(const DequantA
     const uint8_t* in = a.in + a.head_bytes;
     char* out = a.out + a.head_bytes * PER * OSZ;
     const int64_t n_tiles = (a.n_items + TILE - 1) / TILE;
+    pdl_launch_dependents();
+    pdl_wait();
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t first = tile * TILE + threadIdx.x;
@@ -113,6 +115,8 @@ template <int BITS, int OUT_DT, int OP>
 __global__ void __launch_bounds__(kThreads) dequant_bytes_kernel(const DequantArgs a) {
     constexpr int PER = 8 / BITS;
     const int64_t total = (a.numel + PER - 1) / PER;
+    pdl_launch_dependents();
+    pdl_wait();
     for (int64_t b = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; b < total;
          b += static_cast<int64_t>(gridDim.x) * kThreads)
         dequant_one_byte<BITS, OUT_DT, OP>(a, b);
@@ -175,7 +179,7 @@ static void launch_cell(const void* in, void* out, int64_t numel, const QuantPar
     int64_t grid = static_cast<int64_t>(cfg.sm_count) * (per_sm > 0 ? per_sm : 1);
     if (blocks_needed < grid) grid = blocks_needed;
     if (grid < 1) grid = 1;
-    fn<<<static_cast<unsigned>(grid), kThreads, 0, cfg.stream>>>(a);
+    launch_kernel(fn, static_cast<unsigned>(grid), kThreads, 0, cfg.stream, a);
     PQ_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -50,6 +50,8 @@ __global__ void __launch_bounds__(kThreads) minmax_kernel(const MinMaxArgs a) {
 
     float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
     uint32_t pmn = 0x7f807f80u, pmx = 0xff80ff80u;      // packed bf16x2 accumulators (+inf,+inf) / (-inf,-inf)
+    pdl_launch_dependents();
+    pdl_wait();                                          // also orders this launch after the previous one's use of the scratch
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t first = tile * TILE + threadIdx.x;
@@ -169,7 +171,7 @@ int launch_minmax(const void* x, int dt, int64_t numel, const MinMaxScratch& scr
     if (grid > scratch.max_blocks) grid = scratch.max_blocks;
     if (blocks_needed < grid) grid = blocks_needed;
     if (grid < 1) grid = 1;
-    fn<<<static_cast<unsigned>(grid), kThreads, 0, cfg.stream>>>(a);
+    launch_kernel(fn, static_cast<unsigned>(grid), kThreads, 0, cfg.stream, a);
     PQ_CUDA_CHECK(cudaGetLastError());
     return 1;
 }

@@ -39,6 +39,16 @@ struct QuantParams {
 };
 
 // ------------------------------------------------------------------------------------------------
+// programmatic dependent launch (see launch_kernel in pq_kernels.h)
+// ------------------------------------------------------------------------------------------------
+
+// Let the next kernel on the stream start scheduling its CTAs as SMs free up.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Block until everything launched before this kernel on the stream has completed and is visible.
+// Must precede the first global-memory access.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
 // global memory access: 4/8/16/32-byte vector loads and stores with streaming cache hints.
 // 32-byte accesses assemble to LDG.E.256 / STG.E.256 on sm_100a: one full 32 B sector per thread.
 // ------------------------------------------------------------------------------------------------

@@ -35,6 +35,27 @@ struct LaunchCfg {
         if (!(expr)) ::pq::panic("%s:%d Assertion failed: " #expr " <- " msg, __FILE__, __LINE__, ##__VA_ARGS__); \
     } while (0)
 
+// Every kernel is launched with programmatic stream serialization (PDL): a launch may begin while the
+// previous kernel on the stream drains -- its CTAs get scheduled, set up shared memory / mbarriers and then
+// block in griddepcontrol.wait until the predecessor has completed and flushed.  Back-to-back calls on
+// short tensors (27 M elements is ~21 us at the HBM roofline) lose no time to launch latency and prologue.
+// Kernels of other libraries on the same stream are unaffected: the attribute only relaxes OUR launch, and
+// griddepcontrol.wait is a full dependency on whatever ran before.
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*fn)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid, 1, 1);
+    lc.blockDim = dim3(block, 1, 1);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    PQ_CUDA_CHECK(cudaLaunchKernelEx(&lc, fn, args...));
+}
+
 inline int dtype_bits(int dt) {
     switch (dt) {
         case DT_F32: return 32;

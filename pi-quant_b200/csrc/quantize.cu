@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(kThreads) quant_stream_kernel(const QuantArgs 
     uint8_t* out = a.out + a.head_bytes;
     const int64_t n_vecs = a.n_items * 16 / OB;
     const int64_t n_tiles = (n_vecs + TILE - 1) / TILE;
+    pdl_launch_dependents();
+    pdl_wait();
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t first = tile * TILE + threadIdx.x;
@@ -95,6 +97,8 @@ template <int IN_DT, int BITS, int STEP>
 __global__ void __launch_bounds__(kThreads) quant_bytes_kernel(const QuantArgs a) {
     constexpr int PER = 8 / BITS;
     const int64_t total = (a.numel + PER - 1) / PER;
+    pdl_launch_dependents();
+    pdl_wait();
     for (int64_t b = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; b < total;
          b += static_cast<int64_t>(gridDim.x) * kThreads)
         quant_one_byte<IN_DT, BITS, STEP>(a, b);
@@ -129,7 +133,7 @@ static void launch_cell(const QuantArgs& a0, bool vec, const LaunchCfg& cfg) {
     int64_t grid = static_cast<int64_t>(cfg.sm_count) * (per_sm > 0 ? per_sm : 1);
     if (blocks_needed < grid) grid = blocks_needed;
     if (grid < 1) grid = 1;
-    fn<<<static_cast<unsigned>(grid), kThreads, 0, cfg.stream>>>(a);
+    launch_kernel(fn, static_cast<unsigned>(grid), kThreads, 0, cfg.stream, a);
     PQ_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(kTmaThreads) quant_tma_kernel(const QuantArgs 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    pdl_launch_dependents();
+    pdl_wait();                 // set-up above overlaps the previous kernel's tail; no global access before this line
 
     if (threadIdx.x < 32) {
         if (threadIdx.x == 0) {
@@ -183,7 +185,7 @@ void launch_tma_cell(const QuantArgs& a, const LaunchCfg& cfg) {
     int64_t grid = static_cast<int64_t>(cfg.sm_count) * (per_sm > 0 ? per_sm : 1);
     if (n_tiles < grid) grid = n_tiles;
     if (grid < 1) grid = 1;
-    fn<<<static_cast<unsigned>(grid), kTmaThreads, S::SMEM, cfg.stream>>>(a);
+    launch_kernel(fn, static_cast<unsigned>(grid), kTmaThreads, S::SMEM, cfg.stream, a);
     PQ_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(kThreads) requant_stream_kernel(const RequantA
     const char* in = a.in + a.head * ISZ;
     char* out = a.out + a.head * ISZ;
     const int64_t n_tiles = (a.n_items + TILE - 1) / TILE;
+    pdl_launch_dependents();
+    pdl_wait();
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t first = tile * TILE + threadIdx.x;
@@ -107,6 +109,8 @@ __global__ void __launch_bounds__(kThreads) requant_stream_kernel(const RequantA
 // in / out do not share a 32-byte phase: one element per thread
 template <int DT, int STEP, int OP>
 __global__ void __launch_bounds__(kThreads) requant_scalar_kernel(const RequantArgs a, const int32_t qmax) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (int64_t e = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; e < a.numel;
          e += static_cast<int64_t>(gridDim.x) * kThreads)
         requant_scalar<DT, STEP, OP>(a, e, qmax);
@@ -129,7 +133,7 @@ static void launch_cell(RequantArgs a, int32_t qmax, bool vec, const LaunchCfg& 
     int64_t grid = static_cast<int64_t>(cfg.sm_count) * (per_sm > 0 ? per_sm : 1);
     if (blocks_needed < grid) grid = blocks_needed;
     if (grid < 1) grid = 1;
-    fn<<<static_cast<unsigned>(grid), kThreads, 0, cfg.stream>>>(a, qmax);
+    launch_kernel(fn, static_cast<unsigned>(grid), kThreads, 0, cfg.stream, a, qmax);
     PQ_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -103,6 +103,10 @@ def main() -> None:
     # torch copy for calibration of the peak on this very box
     t = time_fn(lambda: acc.copy_(xf), a.reps)
     report("torch copy_ f32 (calibration)", 8, t, 0)
+    t = time_fn(lambda: acc.fill_(1.0), a.reps)
+    report("torch fill_ f32 (write-only calib.)", 4, t, 0)
+    t = time_fn(lambda: torch.cuda.memset if False else acc.zero_(), a.reps)
+    report("torch zero_ f32 (memset calib.)", 4, t, 0)
     out = ROOT / "gpurun_out"
     out.mkdir(exist_ok=True)
     (out / f"cellbench_{n}.json").write_text(json.dumps(rows, indent=1))
