@@ -9,44 +9,9 @@
 // accumulator is read with 2 x LDG.256 first and the sum is formed in registers, so `out` crosses
 // HBM once in each direction.  U = 2 items per thread per tile keeps 128 B of stores (and, for ADD,
 // 128 B of loads) in flight per thread.  Ragged head/tail bytes are handled by the last CTA.
-#include "pq_kernels.h"
+#include "dequantize_common.cuh"
 
 namespace pq {
-
-struct DequantArgs {
-    const uint8_t* in;          // first packed byte
-    char*          out;         // first output element
-    int64_t        numel;
-    int64_t        head_bytes;  // packed input bytes in front of the vectorised region
-    int64_t        n_items;     // full 64-byte output items
-    QuantParams    P;
-};
-
-// All elements of one packed input byte (elements past numel are skipped).
-template <int BITS, int OUT_DT, int OP>
-__device__ __forceinline__ void dequant_one_byte(const DequantArgs& a, int64_t b) {
-    constexpr int PER = 8 / BITS;
-    constexpr uint32_t QMAX = (1u << BITS) - 1u;
-    const uint32_t byte = a.in[b];
-    // reference quirk kept: the 1-3 element tail of the generic u2->f32 kernel always SETs, even
-    // for ADD (src/kernels/dequantize.inl:72-86)
-    const int64_t set_from = (BITS == 2 && OUT_DT == DT_F32) ? a.numel - (a.numel & 3) : a.numel;
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int64_t e = b * PER + k;
-        if (e >= a.numel) break;
-        const uint32_t q = (byte >> (k * BITS)) & QMAX;
-        if constexpr (OUT_DT == DT_F32) {
-            float* o = reinterpret_cast<float*>(a.out) + e;
-            if (OP == OP_ADD && e < set_from) *o = dequant_f32<BITS, OP_ADD>(q, *o, a.P);
-            else *o = dequant_f32<BITS, OP_SET>(q, 0.0f, a.P);
-        } else {
-            uint16_t* o = reinterpret_cast<uint16_t*>(a.out) + e;
-            const float prev = OP == OP_ADD ? bf16_bits_to_f32(*o) : 0.0f;
-            *o = f32_to_bf16_bits(dequant_bf16_pre<BITS, OP>(q, prev, a.P));
-        }
-    }
-}
 
 template <int BITS, int OUT_DT, int OP, bool A32>
 __global__ void __launch_bounds__(kThreads) dequant_stream_kernel(const DequantArgs a) {
@@ -141,6 +106,7 @@ static void launch_cell(const void* in, void* out, int64_t numel, const QuantPar
     a.P = P;
     a.head_bytes = 0;
     a.n_items = 0;
+    set_dequant_fast(a, BITS, OUT_DT);
     const int64_t full_bytes = numel / PER;
     // smallest head (in packed bytes) after which `out` is 32- (else 16-) byte aligned and `in` is
     // aligned for its vector load
@@ -198,9 +164,19 @@ static void launch_in(const void* in, int dt_in, void* out, int64_t numel, const
     }
 }
 
+int launch_dequantize_tma(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int op,
+                          const LaunchCfg& cfg);   // dequantize_tma.cu; returns 0 when alignment rules out bulk copies
+
 int launch_dequantize(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int op,
                       const LaunchCfg& cfg) {
     if (numel <= 0) return 0;
+    // variant 2: the TMA ring kernel whenever both streams can be 16-byte aligned; 1: direct kernels;
+    // 0 (auto): TMA for large tensors (measured crossover, see dequantize_prefers_tma)
+    const int64_t traffic = numel * (dtype_bits(dt_out) / 8) * (op == OP_ADD ? 2 : 1) + numel * dtype_bits(dt_in) / 8;
+    if (cfg.variant == 2 || (cfg.variant == 0 && dequantize_prefers_tma(traffic))) {
+        const int n = launch_dequantize_tma(in, dt_in, out, dt_out, numel, P, op, cfg);
+        if (n) return n;
+    }
     if (dt_out == DT_F32) launch_in<DT_F32>(in, dt_in, out, numel, P, op, cfg);
     else launch_in<DT_BF16>(in, dt_in, out, numel, P, op, cfg);
     return 1;

@@ -113,10 +113,18 @@ int launch_minmax(const void* x, int dt, int64_t numel, const MinMaxScratch& scr
 
 // variant 0 ("auto"): which quantize cells go to the TMA ring kernel; every entry is a measurement
 // on B200 at numel = 1e9 (profiles/cellbench_*.md), not a guess
-inline bool quantize_prefers_tma(int dt_in, int dt_out, int mode) {
-    if (dt_in == DT_F32) return true;                       // 98-99 % (u8, u4), 92 % (u2) of the measured copy peak
-    return dt_out == DT_U8 && mode == 0;                    // bf16: only ->u8 nearest (98.7 %); the rest is ALU-heavier per byte
-                                                            // and runs better with the direct kernel's higher occupancy
+//   * below ~0.5 GB of traffic the direct kernels win everywhere: no mbarrier set-up, no pipeline fill, shorter
+//     tail (27 M elements f32->u8: 22.6 us direct vs 24.2 us TMA; 16 M elements u4->bf16: 7.0 vs 9.2 us);
+//   * above it the TMA ring is equal or better for the f32 quantize cells and bf16->u8 nearest (96-99 % of the
+//     measured copy peak), and 3-6 points better for dequantize (few long bulk stores instead of many 1-2 KiB
+//     warp stores); the ALU-heavier bf16 quantize cells keep the direct kernel's higher occupancy.
+// Differences below ~3 % are inside the run-to-run drift of a power-capped B200 (profiles/r1_placement_probe.txt).
+constexpr int64_t kTmaMinBytes = int64_t(512) << 20;
+inline bool quantize_prefers_tma(int dt_in, int dt_out, int mode, int64_t algorithmic_bytes) {
+    if (algorithmic_bytes < kTmaMinBytes) return false;
+    if (dt_in == DT_F32) return true;
+    return dt_out == DT_U8 && mode == 0;
 }
+inline bool dequantize_prefers_tma(int64_t algorithmic_bytes) { return algorithmic_bytes >= kTmaMinBytes; }
 
 }  // namespace pq

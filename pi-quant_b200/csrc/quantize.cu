@@ -175,7 +175,8 @@ int launch_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t nu
     const bool a16 = a.n_items > 0 && (in_vec & 15u) == 0;      // what cp.async.bulk needs
     const bool a32 = a.n_items > 0 && (in_vec & 31u) == 0;      // what LDG.256 needs
     // variant 0 = per-cell choice from measurements on B200 (profiles/); 1 = direct, 2 = TMA where alignment allows
-    const bool want_tma = cfg.variant == 2 || (cfg.variant == 0 && quantize_prefers_tma(dt_in, dt_out, mode)) || !a32;
+    const int64_t traffic = numel * isz + numel / per;
+    const bool want_tma = cfg.variant == 2 || (cfg.variant == 0 && quantize_prefers_tma(dt_in, dt_out, mode, traffic)) || !a32;
     if (a16 && want_tma) {
         const int n = launch_quantize_tma(in, dt_in, out, dt_out, numel, P, mode, cfg);
         if (n) return n;

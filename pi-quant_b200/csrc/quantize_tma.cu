@@ -11,6 +11,7 @@
 //                                  packed tile (UBLKCP.G.S), double-buffered with bulk-group waits.
 // No thread computes a global address per element and the loads in flight are bounded by shared
 // memory (S x 16 KiB per CTA, several CTAs per SM), not by registers.
+#include "pq_tma.cuh"
 #include "quantize_common.cuh"
 
 namespace pq {
@@ -21,47 +22,6 @@ constexpr int kStages = 4;
 constexpr int kTileVecs = 1024;                 // 16-byte vectors per input tile (16 KiB)
 constexpr int kConsumers = 256;
 constexpr int kTmaThreads = kConsumers + 32;    // warp 0 = producer
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {   // try_wait suspends the thread in hardware for a bounded time; loop until the phase flips
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-// 1-D bulk copy global -> shared, completion signalled on an mbarrier (TMA, no tensor map needed)
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-// 1-D bulk copy shared -> global, tracked by bulk async-groups
-__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
-// order generic-proxy shared-memory writes before async-proxy (TMA) reads of the same bytes
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
 
 template <int IN_DT, int BITS>
 struct TmaShape {
@@ -91,7 +51,7 @@ __global__ void __launch_bounds__(kTmaThreads) quant_tma_kernel(const QuantArgs 
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kConsumers / 32); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     __syncthreads();
     pdl_launch_dependents();
@@ -152,7 +112,7 @@ __global__ void __launch_bounds__(kTmaThreads) quant_tma_kernel(const QuantArgs 
         }
         fence_proxy_async();
         if (t == 0) tma_store_wait_read<0>();           // the previous tile's store has drained its buffer
-        consumer_barrier();
+        consumer_barrier<kConsumers>();
         if (t == 0) {
             tma_store_1d(out + v0 * S::OBV, ob, static_cast<uint32_t>(vecs * S::OBV));
             tma_store_commit();

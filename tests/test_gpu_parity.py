@@ -148,7 +148,7 @@ def test_quantize_matches_reference_golden(gpu):
 # ------------------------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("cell", DEQUANT_CELLS, ids=cell_id)
-def test_dequantize_bit_exact(gpu0, cell):
+def test_dequantize_bit_exact(gpu, cell):
     dt_in, dt_out, op = cell
     rng = np.random.default_rng(2)
     sizes = list(EDGE_SIZES) + [int(rng.integers(3000, 40000)) for _ in range(5)] + [1 << 20, (1 << 20) + 5]
@@ -159,7 +159,7 @@ def test_dequantize_bit_exact(gpu0, cell):
         prev = rng.uniform(-1, 1, n).astype(np.float32)
         prev = prev if dt_out == F32 else f32_to_bf16_bits(prev)
         want = port.dequantize(q, dt_in, n, dt_out, scale, zp, op, out=prev.copy(), semantics=SEM_BODY)
-        got = gpu0.dequantize(q, dt_in, n, dt_out, scale, zp, op, prev=prev)
+        got = gpu.dequantize(q, dt_in, n, dt_out, scale, zp, op, prev=prev)
         if dt_out == F32:
             assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"n={n} scale={scale} zp={zp}"
         else:
@@ -167,7 +167,7 @@ def test_dequantize_bit_exact(gpu0, cell):
 
 
 @pytest.mark.parametrize("cell", DEQUANT_CELLS, ids=cell_id)
-def test_dequantize_any_alignment_and_odd_zero_points(gpu0, cell):
+def test_dequantize_any_alignment_and_odd_zero_points(gpu, cell):
     dt_in, dt_out, op = cell
     rng = np.random.default_rng(3)
     osz = 4 if dt_out == F32 else 2
@@ -179,28 +179,28 @@ def test_dequantize_any_alignment_and_odd_zero_points(gpu0, cell):
         prev = rng.uniform(-1, 1, n).astype(np.float32)
         prev = prev if dt_out == F32 else f32_to_bf16_bits(prev)
         want = port.dequantize(q, dt_in, n, dt_out, scale, zp, op, out=prev.copy(), semantics=SEM_BODY)
-        got = gpu0.dequantize(q, dt_in, n, dt_out, scale, zp, op, prev=prev, in_off=in_off, out_off=out_off)
+        got = gpu.dequantize(q, dt_in, n, dt_out, scale, zp, op, prev=prev, in_off=in_off, out_off=out_off)
         if dt_out == F32:
             assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"in_off={in_off} out_off={out_off} n={n} zp={zp}"
         else:
             assert bf16_equal(got, want), f"in_off={in_off} out_off={out_off} n={n} zp={zp}"
 
 
-def test_dequantize_uint2_f32_add_tail_quirk_is_kept(gpu0):
+def test_dequantize_uint2_f32_add_tail_quirk_is_kept(gpu):
     """The reference's generic u2->f32 kernel SETs its 1-3 element tail even for ADD (dequantize.inl:72-86)."""
     q = np.array([0b11100100, 0b00011011], dtype=np.uint8)
     prev = np.full(7, 100.0, np.float32)
-    got = gpu0.dequantize(q, UINT2, 7, F32, 1.0, 0, ADD, prev=prev)
+    got = gpu.dequantize(q, UINT2, 7, F32, 1.0, 0, ADD, prev=prev)
     assert got.tolist() == [100.0, 101.0, 102.0, 103.0, 3.0, 2.0, 1.0]
 
 
-def test_dequantize_matches_reference_golden(gpu0):
+def test_dequantize_matches_reference_golden(gpu):
     g = np.load(GOLDEN)
     for key in [str(k) for k in g["__keys__"] if str(k).startswith("dequant/")]:
         _, dti, dto, op, n = key.split("/")
         q, prev, out = g[key + "/q"], g[key + "/prev"], g[key + "/out"]
         scale, zp = g[key + "/p"]
-        got = gpu0.dequantize(q, DTN[dti], int(n), DTN[dto], float(scale), int(zp), ADD if op == "add" else SET, prev=prev)
+        got = gpu.dequantize(q, DTN[dti], int(n), DTN[dto], float(scale), int(zp), ADD if op == "add" else SET, prev=prev)
         if dto == "f32":
             assert np.array_equal(got, out), key
         else:
