@@ -37,6 +37,14 @@ def build(ref: bool | None = None, quiet: bool = True) -> None:
         ref = (REFERENCE_SRC / "src" / "piquant.cpp").exists() and not REF_LIB.exists()
     if ref:
         subprocess.check_call(["make", "-C", str(HERE), "ref", f"REF={REFERENCE_SRC}"], stdout=out, stderr=out)
+    # the reference's own gtest suites, compiled unmodified against this repo's piquant.hpp + libpiquant.so
+    # (acceptance test of the drop-in boundary; runs on the GPU box, see tests/test_gpu_reference_gtests.py)
+    lib = HERE.parent / "pi-quant_b200" / "piquant" / "libpiquant.so"
+    if (REFERENCE_SRC / "test" / "quant.cpp").exists() and lib.exists():
+        subprocess.check_call(["make", "-C", str(HERE), "reftests", f"REF={REFERENCE_SRC}"], stdout=out, stderr=out)
+
+
+REF_TESTS = HERE / "_ref" / "piquant_ref_tests_b200"
 
 
 def have_ref() -> bool:

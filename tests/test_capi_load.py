@@ -121,3 +121,32 @@ def test_compute_without_a_gpu_aborts_loudly(lib):
     buf = "b = ctypes.create_string_buffer(64)\n"
     r = run_snippet(buf + "lib.piquant_quantize(ctypes.c_void_p(ctx), b, 0, b, 4, ctypes.c_size_t(8), ctypes.c_float(1.0), ctypes.c_int64(0), 0)")
     assert r.returncode == -6 and "no usable CUDA device" in r.stderr and "survived" not in r.stdout
+
+
+_FACADE_PROGRAM = r"""
+#include <piquant.hpp>
+#include <vector>
+int main() {
+    using namespace piquant;
+    static_assert(dtype_traits<uint4_t>::type_code == dtype::uint4 && dtype_limits<uint4_t>::max == 15);
+    static_assert(dtype_info_of(dtype::uint2).bit_size == 2 && sizeof(bfp16_t) == 2);
+    static_assert(static_cast<float>(bfp16_t{1.0f} + bfp16_t{0.5f}) == 1.5f);
+    static_assert(bfp16_t{3.14159f}.bits == 0x4049);
+    context ctx{4};                               // no CUDA call
+    ctx.set_stochastic_threshold(0.5f);
+    std::vector<float> x; std::vector<uint4_t> q;
+    ctx.quantize_generic<float, uint4_t>(x, q, 1.0f, 0, round_mode::nearest);      // numel == 0: returns before touching CUDA
+    return ctx.native() != nullptr ? 0 : 1;
+}
+"""
+
+
+def test_cxx_facade_compiles_and_links_against_the_library(lib, tmp_path):
+    """include/piquant.hpp mirrors the reference's C++ API (reference include/piquant.hpp:20-339) header-only on the C ABI."""
+    src = tmp_path / "facade.cpp"
+    src.write_text(_FACADE_PROGRAM)
+    exe = tmp_path / "facade"
+    subprocess.run(["g++", "-std=c++20", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(src), f"-L{LIB.parent}", "-lpiquant",
+                    f"-Wl,-rpath,{LIB.parent}", "-o", str(exe)], check=True, capture_output=True, text=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
