@@ -73,6 +73,41 @@ PIQUANT_EXPORT void piquant_cuda_comm_init_rank(piquant_context_t* ctx, const vo
 /* Leave the communicator; compute_quant_params is local again. */
 PIQUANT_EXPORT void piquant_cuda_comm_destroy(piquant_context_t* ctx);
 
+/* ---- device-resident parameters: no host round trip between min/max, (scale, zero_point) and quantize ----
+ * The reference's callers do  params = compute_quant_params(x); q = quantize(x, params)  with a join after
+ * each step (reference python/benchmark/throughput_avg.py:18-21).  Here the parameters can stay on the GPU:
+ * a one-thread kernel evaluates the reference's double-precision formula (bit-identical to the host version)
+ * into a 64-byte block that the quantize / dequantize kernels read, so the three launches queue back to back
+ * and a tensor smaller than the 126 MB L2 is read from HBM only once. */
+
+/* 64 bytes of DEVICE memory (8-byte aligned).  The first 16 bytes are the public result; the rest is what the
+ * kernels need (1/scale, bias, range flags) and is opaque.  error != 0: the reference would have aborted
+ * ("scale must be positive"). */
+typedef struct piquant_cuda_meta_t {
+    float   scale;
+    int32_t error;
+    int64_t zero_point;
+    unsigned char opaque[48];
+} piquant_cuda_meta_t;
+
+/* Asynchronous: d_meta <- quantization parameters of x (F32 / BF16 device tensor, n elements; whole-tensor
+ * parameters if the context has a communicator) for the quantized dtype target_quant_dtype. */
+PIQUANT_EXPORT void piquant_cuda_compute_meta_async(piquant_context_t* ctx, const void* x, piquant_dtype_t dtype, size_t n,
+                                                    piquant_dtype_t target_quant_dtype, piquant_cuda_meta_t* d_meta);
+/* Asynchronous: like piquant_quantize / piquant_dequantize on device pointers, with (scale, zero_point) read
+ * from d_meta by the kernel instead of passed by value. */
+PIQUANT_EXPORT void piquant_cuda_quantize_meta_async(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                                     piquant_dtype_t dtype_out, size_t numel, piquant_round_mode_t mode,
+                                                     const piquant_cuda_meta_t* d_meta);
+PIQUANT_EXPORT void piquant_cuda_dequantize_meta_async(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                                       piquant_dtype_t dtype_out, size_t numel, piquant_reduce_op_t op,
+                                                       const piquant_cuda_meta_t* d_meta);
+/* One call = compute_quant_params + quantize: min/max kernel, parameter kernel, quantize kernel, ONE stream
+ * synchronisation; returns the parameters it used.  Results are bit-identical to the two separate calls. */
+PIQUANT_EXPORT void piquant_cuda_quantize_auto(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                               piquant_dtype_t dtype_out, size_t numel, piquant_round_mode_t mode,
+                                               float* out_scale, int64_t* out_zero_point);
+
 #ifdef __cplusplus
 }
 #endif

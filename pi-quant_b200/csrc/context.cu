@@ -109,6 +109,9 @@ struct DeviceState {
     float*        d_result = nullptr;        // 4 floats
     float*        h_result = nullptr;        // pinned + mapped, 4 floats
     float*        h_result_dev = nullptr;    // device view of h_result
+    DeviceMeta*   d_meta = nullptr;          // parameters produced on the device (one-shot quantize)
+    DeviceMeta*   h_meta = nullptr;          // pinned + mapped copy the host reads after the sync
+    DeviceMeta*   h_meta_dev = nullptr;
     // host-pointer pipeline (lazily created)
     cudaStream_t  s_h2d = nullptr, s_run = nullptr, s_d2h = nullptr;
     cudaEvent_t   ev_h2d[kRing]{}, ev_run[kRing]{}, ev_d2h[kRing]{};
@@ -151,6 +154,8 @@ struct Context {
             cudaFree(d.scratch.ticket);
             cudaFree(d.d_result);
             cudaFreeHost(d.h_result);
+            cudaFree(d.d_meta);
+            cudaFreeHost(d.h_meta);
             if (d.pipe_ready) {
                 for (int i = 0; i < kRing; ++i) {
                     cudaFree(d.d_in[i]);
@@ -191,6 +196,9 @@ struct Context {
         PQ_CUDA_CHECK(cudaMalloc(&d.d_result, 4 * sizeof(float)));
         PQ_CUDA_CHECK(cudaHostAlloc(&d.h_result, 4 * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
         PQ_CUDA_CHECK(cudaHostGetDevicePointer(&d.h_result_dev, d.h_result, 0));
+        PQ_CUDA_CHECK(cudaMalloc(&d.d_meta, sizeof(DeviceMeta)));
+        PQ_CUDA_CHECK(cudaHostAlloc(&d.h_meta, sizeof(DeviceMeta), cudaHostAllocMapped | cudaHostAllocPortable));
+        PQ_CUDA_CHECK(cudaHostGetDevicePointer(&d.h_meta_dev, d.h_meta, 0));
         PQ_CUDA_CHECK(cudaDeviceSynchronize());
         return devs.emplace(device, d).first->second;
     }
@@ -279,6 +287,7 @@ struct Job {
     QuantParams P;
     int         mode;
     int         op;
+    const QuantParams* dP = nullptr;   // parameters that live in device memory (produced by params_kernel)
 };
 
 // bytes of the `in` / `out` buffers for a range of `n` elements
@@ -287,9 +296,9 @@ size_t job_out_bytes(const Job& j, size_t n) { return j.cmd == Cmd::Requant ? st
 
 int launch_job(const Job& j, const void* in, void* out, size_t n, const LaunchCfg& cfg) {
     switch (j.cmd) {
-        case Cmd::Quant: return launch_quantize(in, j.dt_in, out, j.dt_out, static_cast<int64_t>(n), j.P, j.mode, cfg);
-        case Cmd::Dequant: return launch_dequantize(in, j.dt_in, out, j.dt_out, static_cast<int64_t>(n), j.P, j.op, cfg);
-        default: return launch_requantize(in, j.dt_in, out, j.dt_out, static_cast<int64_t>(n), j.P, j.mode, j.op, cfg);
+        case Cmd::Quant: return launch_quantize(in, j.dt_in, out, j.dt_out, static_cast<int64_t>(n), j.P, j.mode, cfg, j.dP);
+        case Cmd::Dequant: return launch_dequantize(in, j.dt_in, out, j.dt_out, static_cast<int64_t>(n), j.P, j.op, cfg, j.dP);
+        default: return launch_requantize(in, j.dt_in, out, j.dt_out, static_cast<int64_t>(n), j.P, j.mode, j.op, cfg, j.dP);
     }
 }
 
@@ -651,4 +660,128 @@ extern "C" void piquant_cuda_comm_destroy(piquant_context_t* ctx) {
         PQ_NCCL_CHECK(Nccl::get().CommDestroy(c->comm));
         c->comm = nullptr;
     }
+}
+
+// -------------------------------------------------------------------------------------------------
+// device-resident parameters: min/max -> (scale, zero_point) -> quantize without a host round trip
+// -------------------------------------------------------------------------------------------------
+
+namespace pq {
+namespace {
+
+static_assert(sizeof(piquant_cuda_meta_t) == sizeof(DeviceMeta), "public meta block == kernel-side meta block");
+
+struct DeviceCall {          // common prologue of the *_async entry points: everything must be device memory on ONE device
+    int cur;
+    int device;
+};
+
+DeviceCall require_device_ptrs(const void* a, const void* b, const void* c, const char* who) {
+    const int cur = require_device();
+    int device = -1;
+    for (const void* p : {a, b, c}) {
+        if (!p) continue;
+        const PtrInfo pi = classify(p);
+        pq_assert(pi.where == Where::Device, "%s needs CUDA device pointers", who);
+        pq_assert(device < 0 || device == pi.device, "%s: buffers live on different devices (%d and %d)", who, device, pi.device);
+        device = pi.device;
+    }
+    return {cur, device};
+}
+
+// min/max of x -> {-min, max} (all-reduced over the communicator, if any) -> DeviceMeta at d_meta; asynchronous.
+// small_tensor_bytes: > 0 asks the min/max pass to leave x in L2 for the pass that follows.
+void compute_meta_async(Context& c, DeviceState& d, const void* x, int dt_in, size_t n, int dt_quant, DeviceMeta* d_meta,
+                        DeviceMeta* mapped, bool keep_in_l2) {
+    LaunchCfg cfg{c.stream, d.sm_count, c.variant};
+    if (n > 0) {
+        c.launches += launch_minmax(x, dt_in, static_cast<int64_t>(n), d.scratch, d.d_result, nullptr, cfg, keep_in_l2);
+    } else {
+        const float fmax = std::numeric_limits<float>::max();
+        const float r[4] = {fmax, -fmax, -fmax, -fmax};          // an empty shard is the identity of the reduction
+        PQ_CUDA_CHECK(cudaMemcpyAsync(d.d_result, r, sizeof(r), cudaMemcpyHostToDevice, c.stream));
+    }
+    if (c.comm) PQ_NCCL_CHECK(Nccl::get().AllReduce(d.d_result + 2, d.d_result + 2, 2, kNcclFloat32, kNcclMax, c.comm, c.stream));
+    c.launches += launch_params(d.d_result, dt_quant, d_meta, mapped, cfg);
+}
+
+}  // namespace
+}  // namespace pq
+
+extern "C" void piquant_cuda_compute_meta_async(piquant_context_t* ctx, const void* x, piquant_dtype_t dtype, size_t n,
+                                                piquant_dtype_t target_quant_dtype, piquant_cuda_meta_t* d_meta) {
+    Context* c = as_ctx(ctx);
+    pq_assert(dtype_is_float(dtype), "input dtype (%s) must be a dequantized type", dtype_name(dtype));
+    pq_assert(dtype_is_quant(target_quant_dtype), "type %s is not a quantization type", dtype_name(target_quant_dtype));
+    std::lock_guard<std::mutex> lock(c->mu);
+    const DeviceCall dc = require_device_ptrs(n ? x : nullptr, d_meta, nullptr, "piquant_cuda_compute_meta_async");
+    DeviceGuard guard(dc.cur, dc.device);
+    DeviceState& d = c->dev_state(dc.device);
+    compute_meta_async(*c, d, x, dtype, n, target_quant_dtype, reinterpret_cast<DeviceMeta*>(d_meta), nullptr,
+                       n * static_cast<size_t>(dtype_bits(dtype) / 8) <= (size_t(96) << 20));
+}
+
+extern "C" void piquant_cuda_quantize_meta_async(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                                 piquant_dtype_t dtype_out, size_t numel, piquant_round_mode_t mode,
+                                                 const piquant_cuda_meta_t* d_meta) {
+    Context* c = as_ctx(ctx);
+    pq_assert(dtype_is_float(dtype_in), "input dtype (%s) must be a dequantized type", dtype_name(dtype_in));
+    pq_assert(dtype_is_quant(dtype_out), "output dtype (%s) must be a quantized type", dtype_name(dtype_out));
+    if (numel == 0) return;
+    std::lock_guard<std::mutex> lock(c->mu);
+    const DeviceCall dc = require_device_ptrs(in, out, d_meta, "piquant_cuda_quantize_meta_async");
+    DeviceGuard guard(dc.cur, dc.device);
+    DeviceState& d = c->dev_state(dc.device);
+    const float xi = mode == PIQUANT_STOCHASTIC ? c->draw_xi() : 0.0f;
+    LaunchCfg cfg{c->stream, d.sm_count, c->variant};
+    c->launches += launch_quantize(in, dtype_in, out, dtype_out, static_cast<int64_t>(numel), make_params(1.0f, 0, xi), static_cast<int>(mode),
+                                   cfg, &reinterpret_cast<const DeviceMeta*>(d_meta)->P);
+}
+
+extern "C" void piquant_cuda_dequantize_meta_async(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                                   piquant_dtype_t dtype_out, size_t numel, piquant_reduce_op_t op,
+                                                   const piquant_cuda_meta_t* d_meta) {
+    Context* c = as_ctx(ctx);
+    pq_assert(dtype_is_quant(dtype_in), "input dtype (%s) must be a quantized type", dtype_name(dtype_in));
+    pq_assert(dtype_is_float(dtype_out), "output dtype (%s) must be a dequantized type", dtype_name(dtype_out));
+    if (numel == 0) return;
+    std::lock_guard<std::mutex> lock(c->mu);
+    const DeviceCall dc = require_device_ptrs(in, out, d_meta, "piquant_cuda_dequantize_meta_async");
+    DeviceGuard guard(dc.cur, dc.device);
+    DeviceState& d = c->dev_state(dc.device);
+    LaunchCfg cfg{c->stream, d.sm_count, c->variant};
+    c->launches += launch_dequantize(in, dtype_in, out, dtype_out, static_cast<int64_t>(numel), make_params(1.0f, 0, 0.0f), static_cast<int>(op),
+                                     cfg, &reinterpret_cast<const DeviceMeta*>(d_meta)->P);
+}
+
+extern "C" void piquant_cuda_quantize_auto(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                           piquant_dtype_t dtype_out, size_t numel, piquant_round_mode_t mode, float* out_scale,
+                                           int64_t* out_zero_point) {
+    Context* c = as_ctx(ctx);
+    pq_assert(dtype_is_float(dtype_in), "input dtype (%s) must be a dequantized type", dtype_name(dtype_in));
+    pq_assert(dtype_is_quant(dtype_out), "output dtype (%s) must be a quantized type", dtype_name(dtype_out));
+    pq_assert(numel > 0, "scale must be positive");          // the reference aborts on an empty tensor (src/piquant.cpp:373)
+    {
+        const PtrInfo pi = (require_device(), classify(in)), po = classify(out);
+        if (pi.where != Where::Device || po.where != Where::Device) {   // host tensors: the two-step path
+            if (dtype_in == PIQUANT_DTYPE_F32) piquant_compute_quant_params_float32(ctx, static_cast<const float*>(in), numel, dtype_out, out_scale, out_zero_point);
+            else piquant_compute_quant_params_bfloat16(ctx, static_cast<const uint16_t*>(in), numel, dtype_out, out_scale, out_zero_point);
+            piquant_quantize(ctx, in, dtype_in, out, dtype_out, numel, *out_scale, *out_zero_point, mode);
+            return;
+        }
+    }
+    std::lock_guard<std::mutex> lock(c->mu);
+    const DeviceCall dc = require_device_ptrs(in, out, nullptr, "piquant_cuda_quantize_auto");
+    DeviceGuard guard(dc.cur, dc.device);
+    DeviceState& d = c->dev_state(dc.device);
+    const size_t in_bytes = numel * static_cast<size_t>(dtype_bits(dtype_in) / 8);
+    compute_meta_async(*c, d, in, dtype_in, numel, dtype_out, d.d_meta, d.h_meta_dev, in_bytes <= (size_t(96) << 20));
+    const float xi = mode == PIQUANT_STOCHASTIC ? c->draw_xi() : 0.0f;
+    LaunchCfg cfg{c->stream, d.sm_count, c->variant};
+    c->launches += launch_quantize(in, dtype_in, out, dtype_out, static_cast<int64_t>(numel), make_params(1.0f, 0, xi), static_cast<int>(mode),
+                                   cfg, &d.d_meta->P);
+    PQ_CUDA_CHECK(cudaStreamSynchronize(c->stream));         // the ONE host sync of the whole sequence
+    pq_assert(d.h_meta->error == 0, "scale must be positive");
+    *out_scale = d.h_meta->scale;
+    *out_zero_point = d.h_meta->zero_point;
 }

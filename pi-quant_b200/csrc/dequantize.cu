@@ -14,7 +14,8 @@
 namespace pq {
 
 template <int BITS, int OUT_DT, int OP, bool A32>
-__global__ void __launch_bounds__(kThreads) dequant_stream_kernel(const DequantArgs a) {
+__global__ void __launch_bounds__(kThreads) dequant_stream_kernel(const DequantArgs a_in) {
+    DequantArgs a = a_in;
     constexpr int PER = 8 / BITS;
     constexpr int V = OUT_DT == DT_F32 ? 16 : 32;       // elements per item (64 output bytes)
     constexpr int OSZ = OUT_DT == DT_F32 ? 4 : 2;
@@ -30,6 +31,7 @@ __global__ void __launch_bounds__(kThreads) dequant_stream_kernel(const DequantA
     const int64_t n_tiles = (a.n_items + TILE - 1) / TILE;
     pdl_launch_dependents();
     pdl_wait();
+    load_device_params<BITS, OUT_DT>(a);
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t first = tile * TILE + threadIdx.x;
@@ -77,11 +79,13 @@ __global__ void __launch_bounds__(kThreads) dequant_stream_kernel(const DequantA
 
 // Any alignment: one thread per packed input byte.
 template <int BITS, int OUT_DT, int OP>
-__global__ void __launch_bounds__(kThreads) dequant_bytes_kernel(const DequantArgs a) {
+__global__ void __launch_bounds__(kThreads) dequant_bytes_kernel(const DequantArgs a_in) {
+    DequantArgs a = a_in;
     constexpr int PER = 8 / BITS;
     const int64_t total = (a.numel + PER - 1) / PER;
     pdl_launch_dependents();
     pdl_wait();
+    load_device_params<BITS, OUT_DT>(a);
     for (int64_t b = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; b < total;
          b += static_cast<int64_t>(gridDim.x) * kThreads)
         dequant_one_byte<BITS, OUT_DT, OP>(a, b);
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(kThreads) dequant_bytes_kernel(const DequantAr
 using DequantKernel = void (*)(const DequantArgs);
 
 template <int BITS, int OUT_DT, int OP>
-static void launch_cell(const void* in, void* out, int64_t numel, const QuantParams& P, const LaunchCfg& cfg) {
+static void launch_cell(const void* in, void* out, int64_t numel, const QuantParams& P, const LaunchCfg& cfg, const QuantParams* dP) {
     constexpr int PER = 8 / BITS;
     constexpr int V = OUT_DT == DT_F32 ? 16 : 32;
     constexpr int OSZ = OUT_DT == DT_F32 ? 4 : 2;
@@ -104,6 +108,7 @@ static void launch_cell(const void* in, void* out, int64_t numel, const QuantPar
     a.out = static_cast<char*>(out);
     a.numel = numel;
     a.P = P;
+    a.dP = dP;
     a.head_bytes = 0;
     a.n_items = 0;
     set_dequant_fast(a, BITS, OUT_DT);
@@ -150,35 +155,35 @@ static void launch_cell(const void* in, void* out, int64_t numel, const QuantPar
 }
 
 template <int BITS, int OUT_DT>
-static void launch_op(const void* in, void* out, int64_t numel, const QuantParams& P, int op, const LaunchCfg& cfg) {
-    if (op == OP_ADD) launch_cell<BITS, OUT_DT, OP_ADD>(in, out, numel, P, cfg);
-    else launch_cell<BITS, OUT_DT, OP_SET>(in, out, numel, P, cfg);
+static void launch_op(const void* in, void* out, int64_t numel, const QuantParams& P, int op, const LaunchCfg& cfg, const QuantParams* dP) {
+    if (op == OP_ADD) launch_cell<BITS, OUT_DT, OP_ADD>(in, out, numel, P, cfg, dP);
+    else launch_cell<BITS, OUT_DT, OP_SET>(in, out, numel, P, cfg, dP);
 }
 
 template <int OUT_DT>
-static void launch_in(const void* in, int dt_in, void* out, int64_t numel, const QuantParams& P, int op, const LaunchCfg& cfg) {
+static void launch_in(const void* in, int dt_in, void* out, int64_t numel, const QuantParams& P, int op, const LaunchCfg& cfg, const QuantParams* dP) {
     switch (dt_in) {
-        case DT_U8: launch_op<8, OUT_DT>(in, out, numel, P, op, cfg); break;
-        case DT_U4: launch_op<4, OUT_DT>(in, out, numel, P, op, cfg); break;
-        default:    launch_op<2, OUT_DT>(in, out, numel, P, op, cfg); break;
+        case DT_U8: launch_op<8, OUT_DT>(in, out, numel, P, op, cfg, dP); break;
+        case DT_U4: launch_op<4, OUT_DT>(in, out, numel, P, op, cfg, dP); break;
+        default:    launch_op<2, OUT_DT>(in, out, numel, P, op, cfg, dP); break;
     }
 }
 
 int launch_dequantize_tma(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int op,
-                          const LaunchCfg& cfg);   // dequantize_tma.cu; returns 0 when alignment rules out bulk copies
+                          const LaunchCfg& cfg, const QuantParams* dP);   // dequantize_tma.cu; returns 0 when alignment rules out bulk copies
 
 int launch_dequantize(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int op,
-                      const LaunchCfg& cfg) {
+                      const LaunchCfg& cfg, const QuantParams* dP) {
     if (numel <= 0) return 0;
     // variant 2: the TMA ring kernel whenever both streams can be 16-byte aligned; 1: direct kernels;
     // 0 (auto): TMA for large tensors (measured crossover, see dequantize_prefers_tma)
     const int64_t traffic = numel * (dtype_bits(dt_out) / 8) * (op == OP_ADD ? 2 : 1) + numel * dtype_bits(dt_in) / 8;
     if (cfg.variant == 2 || (cfg.variant == 0 && dequantize_prefers_tma(traffic))) {
-        const int n = launch_dequantize_tma(in, dt_in, out, dt_out, numel, P, op, cfg);
+        const int n = launch_dequantize_tma(in, dt_in, out, dt_out, numel, P, op, cfg, dP);
         if (n) return n;
     }
-    if (dt_out == DT_F32) launch_in<DT_F32>(in, dt_in, out, numel, P, op, cfg);
-    else launch_in<DT_BF16>(in, dt_in, out, numel, P, op, cfg);
+    if (dt_out == DT_F32) launch_in<DT_F32>(in, dt_in, out, numel, P, op, cfg, dP);
+    else launch_in<DT_BF16>(in, dt_in, out, numel, P, op, cfg, dP);
     return 1;
 }
 

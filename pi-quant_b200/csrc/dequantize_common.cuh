@@ -14,12 +14,22 @@ struct DequantArgs {
     QuantParams    P;
     float          magic_zp;    // 2^23 + zp32 (exact) when fast != 0
     int32_t        fast;        // |zp| <= 2^22: the byte-permute conversion below is exact
+    const QuantParams* dP;      // not null: parameters produced on the device (params_kernel), read from there
 };
 
-inline void set_dequant_fast(DequantArgs& a, int bits, int out_dt) {
+__host__ __device__ inline void set_dequant_fast(DequantArgs& a, int bits, int out_dt) {
     const QuantParams& P = a.P;
     a.fast = (P.zp32 <= (1 << 22) && P.zp32 >= -(1 << 22) && !(bits == 2 && out_dt == DT_F32 && P.bigzp)) ? 1 : 0;
     a.magic_zp = 8388608.0f + static_cast<float>(a.fast ? P.zp32 : 0);
+}
+
+// Parameters computed by an earlier kernel on the stream replace the by-value ones.  Call after pdl_wait().
+template <int BITS, int OUT_DT>
+__device__ __forceinline__ void load_device_params(DequantArgs& a) {
+    if (a.dP) {
+        a.P = *a.dP;
+        set_dequant_fast(a, BITS, OUT_DT);
+    }
 }
 
 // All elements of one packed input byte (elements past numel are skipped).

@@ -52,7 +52,8 @@ __device__ __forceinline__ uint32_t lds_packed(const unsigned char* p, uint32_t 
 }
 
 template <int BITS, int OUT_DT, int OP>
-__global__ void __launch_bounds__(kDqThreads) dequant_tma_kernel(const DequantArgs a) {
+__global__ void __launch_bounds__(kDqThreads) dequant_tma_kernel(const DequantArgs a_in) {
+    DequantArgs a = a_in;
     using S = DqShape<BITS, OUT_DT>;
     constexpr int PER = 8 / BITS;
     constexpr int NWI = (S::IBV + 3) / 4;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(kDqThreads) dequant_tma_kernel(const DequantAr
     __syncthreads();
     pdl_launch_dependents();
     pdl_wait();
+    load_device_params<BITS, OUT_DT>(a);
 
     if (threadIdx.x < 32) {
         if (threadIdx.x == 0) {
@@ -182,7 +184,7 @@ void launch_tma_in(const DequantArgs& a, int dt_in, int op, const LaunchCfg& cfg
 
 // returns 0 when the alignment of the buffers rules out bulk copies (the direct kernels run then)
 int launch_dequantize_tma(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int op,
-                          const LaunchCfg& cfg) {
+                          const LaunchCfg& cfg, const QuantParams* dP) {
     const int per = 8 / dtype_bits(dt_in);
     const int osz = dtype_bits(dt_out) / 8;
     DequantArgs a;
@@ -190,6 +192,7 @@ int launch_dequantize_tma(const void* in, int dt_in, void* out, int dt_out, int6
     a.out = static_cast<char*>(out);
     a.numel = numel;
     a.P = P;
+    a.dP = dP;
     a.head_bytes = 0;
     a.n_items = 0;
     const int64_t full_bytes = numel / per;

@@ -39,7 +39,7 @@ struct MinMaxArgs {
     float*      mapped_result;  // device-mapped pinned host copy of the same, or nullptr
 };
 
-template <int IN_DT>
+template <int IN_DT, bool KEEP>
 __global__ void __launch_bounds__(kThreads) minmax_kernel(const MinMaxArgs a) {
     constexpr int ISZ = IN_DT == DT_F32 ? 4 : 2;
     constexpr int EPI = 32 / ISZ;     // elements per 32-byte item
@@ -58,12 +58,15 @@ __global__ void __launch_bounds__(kThreads) minmax_kernel(const MinMaxArgs a) {
         uint32_t w[U][8];
         if (tile * TILE + TILE <= a.n_items) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) ldg_stream(base + (first + static_cast<int64_t>(u) * kThreads) * 32, w[u]);
+            for (int u = 0; u < U; ++u) {
+                if constexpr (KEEP) ldg_keep(base + (first + static_cast<int64_t>(u) * kThreads) * 32, w[u]);
+                else ldg_stream(base + (first + static_cast<int64_t>(u) * kThreads) * 32, w[u]);
+            }
         } else {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int64_t item = first + static_cast<int64_t>(u) * kThreads;
-                if (item < a.n_items) ldg_stream(base + item * 32, w[u]);
+                if (item < a.n_items) { if constexpr (KEEP) ldg_keep(base + item * 32, w[u]); else ldg_stream(base + item * 32, w[u]); }
                 else {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) w[u][k] = IN_DT == DT_F32 ? 0x7fc00000u : 0x7fc07fc0u;   // NaN: never wins
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(kThreads) minmax_kernel(const MinMaxArgs a) {
 }
 
 int launch_minmax(const void* x, int dt, int64_t numel, const MinMaxScratch& scratch, float* result,
-                  float* mapped_result, const LaunchCfg& cfg) {
+                  float* mapped_result, const LaunchCfg& cfg, bool keep_in_l2) {
     const int isz = dt == DT_F32 ? 4 : 2;
     const int epi = 32 / isz;
     MinMaxArgs a;
@@ -162,7 +165,8 @@ int launch_minmax(const void* x, int dt, int64_t numel, const MinMaxScratch& scr
     if (head > numel) head = numel;
     a.head = head;
     a.n_items = (numel - head) / epi;
-    auto fn = dt == DT_F32 ? minmax_kernel<DT_F32> : minmax_kernel<DT_BF16>;
+    auto fn = dt == DT_F32 ? (keep_in_l2 ? minmax_kernel<DT_F32, true> : minmax_kernel<DT_F32, false>)
+                           : (keep_in_l2 ? minmax_kernel<DT_BF16, true> : minmax_kernel<DT_BF16, false>);
     int per_sm = 0;
     PQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
     const int64_t tile = static_cast<int64_t>(kThreads) * 4;
@@ -172,6 +176,59 @@ int launch_minmax(const void* x, int dt, int64_t numel, const MinMaxScratch& scr
     if (blocks_needed < grid) grid = blocks_needed;
     if (grid < 1) grid = 1;
     launch_kernel(fn, static_cast<unsigned>(grid), kThreads, 0, cfg.stream, a);
+    PQ_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// (scale, zero_point) on the device
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ long long dev_cvttsd_i64(double a) {     // x86 cvttsd2si: out of range / NaN -> INT64_MIN
+    return (a >= -9223372036854775808.0 && a < 9223372036854775808.0) ? __double2ll_rz(a) : LLONG_MIN;
+}
+
+__global__ void params_kernel(const float* minmax4, int bits, DeviceMeta* out, DeviceMeta* mapped_out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    // same expressions, same order, same IEEE double operations as params_from_minmax() in context.cu
+    const double r_min = -static_cast<double>(minmax4[2]), r_max = static_cast<double>(minmax4[3]);
+    const unsigned long long type_max = (1ull << bits) - 1;
+    float s;
+    long long z;
+    if (r_max == r_min) {
+        s = 1.0f;
+        z = static_cast<long long>(type_max >> 1);
+    } else {
+        const double q_min = 0.0, q_max = static_cast<double>(type_max);
+        const double sd = __ddiv_rn(__dsub_rn(r_max, r_min), __dsub_rn(q_max, q_min));
+        double zp = __dsub_rn(q_min, __ddiv_rn(r_min, sd));
+        zp = fmax(fmin(static_cast<double>(dev_cvttsd_i64(round(zp))), q_max), q_min);
+        s = __double2float_rn(sd);
+        z = dev_cvttsd_i64(zp);
+    }
+    DeviceMeta m;
+    m.scale = s;
+    m.error = (isnan(s) || !(s >= 0.0f)) ? 1 : 0;
+    m.zero_point = z;
+    m.P.scale = s;
+    m.P.inv_scale = __fdiv_rn(1.0f, s);
+    m.P.xi = 0.0f;
+    m.P.zp64 = z;
+    m.P.zp32 = static_cast<int32_t>(static_cast<uint32_t>(static_cast<unsigned long long>(z)));
+    m.P.bias = __fmul_rn(-static_cast<float>(m.P.zp32), s);
+    m.P.bigzp = (z > (1ll << 29) || z < -(1ll << 29)) ? 1 : 0;
+    m.P.spec_ok32 = (m.P.zp32 <= (1 << 29) && m.P.zp32 >= -(1 << 29)) ? 1 : 0;
+    for (int i = 0; i < static_cast<int>(sizeof(m.pad)); ++i) m.pad[i] = 0;
+    *out = m;
+    if (mapped_out) {
+        *mapped_out = m;
+        __threadfence_system();
+    }
+}
+
+int launch_params(const float* minmax4, int dt_quant, DeviceMeta* out, DeviceMeta* mapped_out, const LaunchCfg& cfg) {
+    launch_kernel(params_kernel, 1u, 1u, 0, cfg.stream, minmax4, dtype_bits(dt_quant), out, mapped_out);
     PQ_CUDA_CHECK(cudaGetLastError());
     return 1;
 }

@@ -70,6 +70,13 @@ __device__ __forceinline__ void ldg_stream(const void* p, uint32_t (&r)[1]) {
     asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r[0]) : "l"(p));
 }
 
+// read-only load that asks L2 to KEEP the line (a following pass will read it again)
+__device__ __forceinline__ void ldg_keep(const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+
 // coherent load of data this kernel will overwrite (the accumulator of dequantize-ADD)
 __device__ __forceinline__ void ldg_rmw(const void* p, uint32_t (&r)[8]) {
     asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

@@ -92,12 +92,12 @@ QuantParams make_params(float scale, int64_t zero_point, float xi);
 // Device pointers (or device-accessible mapped host pointers) only.  All launches are asynchronous
 // on cfg.stream.  `mode`: 0 nearest, 1 stochastic (P.xi).  Returns the number of kernels launched.
 int launch_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int mode,
-                    const LaunchCfg& cfg);
+                    const LaunchCfg& cfg, const QuantParams* device_params = nullptr);
 int launch_dequantize(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int op,
-                      const LaunchCfg& cfg);
+                      const LaunchCfg& cfg, const QuantParams* device_params = nullptr);
 // fused quantize -> dequantize, unpacked (reference src/kernels/kernels.inl:30-52)
 int launch_requantize(const void* in, int dt_inout, void* out, int dt_quant, int64_t numel, const QuantParams& P,
-                      int mode, int op, const LaunchCfg& cfg);
+                      int mode, int op, const LaunchCfg& cfg, const QuantParams* device_params = nullptr);
 
 // Scratch owned by the context, one set per device.
 struct MinMaxScratch {
@@ -108,8 +108,26 @@ struct MinMaxScratch {
 // Writes result[0..3] = {min, max, -min, max} (device memory) and, if `mapped_result` is not null,
 // the same four floats to that device-mapped pinned host address.  min/max start from +-FLT_MAX and
 // NaNs never win, like the reference (src/kernels/kernels_specialized.inl:1418-1607).
+// keep_in_l2: read with the default cache policy instead of evict-first, so that a tensor smaller than the
+// 126 MB L2 is still resident when the quantize pass that follows reads it again.
 int launch_minmax(const void* x, int dt, int64_t numel, const MinMaxScratch& scratch, float* result,
-                  float* mapped_result, const LaunchCfg& cfg);
+                  float* mapped_result, const LaunchCfg& cfg, bool keep_in_l2 = false);
+
+// Parameters of one quantized tensor, produced and consumed on the device (include/piquant_cuda.h:
+// piquant_cuda_meta_t has the same 64-byte layout: 16 public bytes, then the kernel-side parameters).
+struct DeviceMeta {
+    float       scale;
+    int32_t     error;        // 1: the reference would have aborted (scale NaN or negative)
+    int64_t     zero_point;
+    QuantParams P;
+    char        pad[64 - 16 - sizeof(QuantParams)];
+};
+static_assert(sizeof(DeviceMeta) == 64 && offsetof(DeviceMeta, P) == 16, "piquant_cuda_meta_t layout");
+
+// One-thread kernel: the double-precision scale / zero-point arithmetic of the reference
+// (src/piquant.cpp:245-258) on the {-min, max} pair at minmax4[2..3], bit-identical to the host version,
+// plus everything the kernels derive from it (1/scale, bias, range flags).  Asynchronous on cfg.stream.
+int launch_params(const float* minmax4, int dt_quant, DeviceMeta* out, DeviceMeta* mapped_out, const LaunchCfg& cfg);
 
 // variant 0 ("auto"): which quantize cells go to the TMA ring kernel; every entry is a measurement
 // on B200 at numel = 1e9 (profiles/cellbench_*.md), not a guess

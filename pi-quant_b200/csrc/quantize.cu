@@ -43,7 +43,8 @@ __device__ __forceinline__ void store_packed(uint8_t* p, const uint32_t* o) {
 }  // namespace
 
 template <int IN_DT, int BITS, int STEP>
-__global__ void __launch_bounds__(kThreads) quant_stream_kernel(const QuantArgs a) {
+__global__ void __launch_bounds__(kThreads) quant_stream_kernel(const QuantArgs a_in) {
+    QuantArgs a = a_in;
     constexpr int PER = 8 / BITS;                       // elements per packed byte
     constexpr int ISZ = IN_DT == DT_F32 ? 4 : 2;
     constexpr int EV = 32 / ISZ;                        // elements per 32-byte vector
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(kThreads) quant_stream_kernel(const QuantArgs 
     const int64_t n_tiles = (n_vecs + TILE - 1) / TILE;
     pdl_launch_dependents();
     pdl_wait();
+    load_device_params(a);
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t first = tile * TILE + threadIdx.x;
@@ -94,11 +96,13 @@ __global__ void __launch_bounds__(kThreads) quant_stream_kernel(const QuantArgs 
 
 // Any alignment: one thread per packed output byte (loads stay sector-coalesced through L1).
 template <int IN_DT, int BITS, int STEP>
-__global__ void __launch_bounds__(kThreads) quant_bytes_kernel(const QuantArgs a) {
+__global__ void __launch_bounds__(kThreads) quant_bytes_kernel(const QuantArgs a_in) {
+    QuantArgs a = a_in;
     constexpr int PER = 8 / BITS;
     const int64_t total = (a.numel + PER - 1) / PER;
     pdl_launch_dependents();
     pdl_wait();
+    load_device_params(a);
     for (int64_t b = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; b < total;
          b += static_cast<int64_t>(gridDim.x) * kThreads)
         quant_one_byte<IN_DT, BITS, STEP>(a, b);
@@ -154,10 +158,10 @@ static void launch_out(const QuantArgs& a, int dt_out, int mode, bool vec, const
 }
 
 int launch_quantize_tma(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int mode,
-                        const LaunchCfg& cfg);   // quantize_tma.cu; returns 0 when the cell / alignment is not covered
+                        const LaunchCfg& cfg, const QuantParams* dP);   // quantize_tma.cu; returns 0 when the cell / alignment is not covered
 
 int launch_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int mode,
-                    const LaunchCfg& cfg) {
+                    const LaunchCfg& cfg, const QuantParams* dP) {
     if (numel <= 0) return 0;
     const int per = 8 / dtype_bits(dt_out);
     const int isz = dtype_bits(dt_in) / 8;
@@ -166,6 +170,7 @@ int launch_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t nu
     a.out = static_cast<uint8_t*>(out);
     a.numel = numel;
     a.P = P;
+    a.dP = dP;
     const int64_t full_bytes = numel / per;                      // bytes whose elements all exist
     int64_t head = static_cast<int64_t>((16 - (reinterpret_cast<uintptr_t>(out) & 15u)) & 15u);
     if (head > full_bytes) head = full_bytes;
@@ -178,7 +183,7 @@ int launch_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t nu
     const int64_t traffic = numel * isz + numel / per;
     const bool want_tma = cfg.variant == 2 || (cfg.variant == 0 && quantize_prefers_tma(dt_in, dt_out, mode, traffic)) || !a32;
     if (a16 && want_tma) {
-        const int n = launch_quantize_tma(in, dt_in, out, dt_out, numel, P, mode, cfg);
+        const int n = launch_quantize_tma(in, dt_in, out, dt_out, numel, P, mode, cfg, dP);
         if (n) return n;
     }
     if (dt_in == DT_F32) launch_out<DT_F32>(a, dt_out, mode, a32, cfg);

@@ -12,7 +12,18 @@ struct QuantArgs {
     int64_t     head_bytes;  // output bytes in front of the vectorised region
     int64_t     n_items;     // full 16-byte output items in the vectorised region
     QuantParams P;
+    const QuantParams* dP;   // not null: the parameters were produced on the device (params_kernel) and are read from there
 };
+
+// Parameters computed by an earlier kernel on the stream replace the by-value ones (the per-call stochastic
+// threshold always comes from the host).  Call after pdl_wait().
+__device__ __forceinline__ void load_device_params(QuantArgs& a) {
+    if (a.dP) {
+        const float xi = a.P.xi;
+        a.P = *a.dP;
+        a.P.xi = xi;
+    }
+}
 
 template <int IN_DT>
 __device__ __forceinline__ float load_elem(const char* in, int64_t e) {

@@ -34,7 +34,8 @@ struct TmaShape {
 };
 
 template <int IN_DT, int BITS, int STEP>
-__global__ void __launch_bounds__(kTmaThreads) quant_tma_kernel(const QuantArgs a) {
+__global__ void __launch_bounds__(kTmaThreads) quant_tma_kernel(const QuantArgs a_in) {
+    QuantArgs a = a_in;
     using S = TmaShape<IN_DT, BITS>;
     constexpr int PER = 8 / BITS;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(kTmaThreads) quant_tma_kernel(const QuantArgs 
     __syncthreads();
     pdl_launch_dependents();
     pdl_wait();                 // set-up above overlaps the previous kernel's tail; no global access before this line
+    load_device_params(a);
 
     if (threadIdx.x < 32) {
         if (threadIdx.x == 0) {
@@ -159,7 +161,7 @@ void launch_tma_mode(const QuantArgs& a, int mode, const LaunchCfg& cfg) {
 }  // namespace
 
 int launch_quantize_tma(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int mode,
-                        const LaunchCfg& cfg) {
+                        const LaunchCfg& cfg, const QuantParams* dP) {
     const int per = 8 / dtype_bits(dt_out);
     const int isz = dtype_bits(dt_in) / 8;
     QuantArgs a;
@@ -167,6 +169,7 @@ int launch_quantize_tma(const void* in, int dt_in, void* out, int dt_out, int64_
     a.out = static_cast<uint8_t*>(out);
     a.numel = numel;
     a.P = P;
+    a.dP = dP;
     const int64_t full_bytes = numel / per;
     int64_t head = static_cast<int64_t>((16 - (reinterpret_cast<uintptr_t>(out) & 15u)) & 15u);
     if (head > full_bytes) head = full_bytes;

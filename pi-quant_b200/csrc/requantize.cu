@@ -24,7 +24,17 @@ struct RequantArgs {
     int64_t     n_items;   // 32-byte items
     QuantParams P;
     float       scale_bf16;   // scale rounded to bf16 and widened again
+    const QuantParams* dP;    // not null: parameters produced on the device (params_kernel), read from there
 };
+
+__device__ __forceinline__ void load_device_params(RequantArgs& a) {
+    if (a.dP) {
+        const float xi = a.P.xi;
+        a.P = *a.dP;
+        a.P.xi = xi;
+        a.scale_bf16 = bf16_bits_to_f32(f32_to_bf16_bits(a.P.scale));
+    }
+}
 
 template <int DT, int STEP, int OP>
 __device__ __forceinline__ uint32_t requant_elem(float x, uint32_t prev_bits, const RequantArgs& a, int32_t qmax) {
@@ -57,7 +67,8 @@ __device__ __forceinline__ void requant_scalar(const RequantArgs& a, int64_t e, 
 }
 
 template <int DT, int STEP, int OP>
-__global__ void __launch_bounds__(kThreads) requant_stream_kernel(const RequantArgs a, const int32_t qmax) {
+__global__ void __launch_bounds__(kThreads) requant_stream_kernel(const RequantArgs a_in, const int32_t qmax) {
+    RequantArgs a = a_in;
     constexpr int ISZ = DT == DT_F32 ? 4 : 2;
     constexpr int EPI = 32 / ISZ;
     constexpr int U = 4;
@@ -67,6 +78,7 @@ __global__ void __launch_bounds__(kThreads) requant_stream_kernel(const RequantA
     const int64_t n_tiles = (a.n_items + TILE - 1) / TILE;
     pdl_launch_dependents();
     pdl_wait();
+    load_device_params(a);
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t first = tile * TILE + threadIdx.x;
@@ -108,9 +120,11 @@ __global__ void __launch_bounds__(kThreads) requant_stream_kernel(const RequantA
 
 // in / out do not share a 32-byte phase: one element per thread
 template <int DT, int STEP, int OP>
-__global__ void __launch_bounds__(kThreads) requant_scalar_kernel(const RequantArgs a, const int32_t qmax) {
+__global__ void __launch_bounds__(kThreads) requant_scalar_kernel(const RequantArgs a_in, const int32_t qmax) {
+    RequantArgs a = a_in;
     pdl_launch_dependents();
     pdl_wait();
+    load_device_params(a);
     for (int64_t e = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; e < a.numel;
          e += static_cast<int64_t>(gridDim.x) * kThreads)
         requant_scalar<DT, STEP, OP>(a, e, qmax);
@@ -159,7 +173,7 @@ static float round_to_bf16(float x) {   // include/piquant.hpp:86-90
 }
 
 int launch_requantize(const void* in, int dt_inout, void* out, int dt_quant, int64_t numel, const QuantParams& P,
-                      int mode, int op, const LaunchCfg& cfg) {
+                      int mode, int op, const LaunchCfg& cfg, const QuantParams* dP) {
     if (numel <= 0) return 0;
     const int isz = dtype_bits(dt_inout) / 8;
     RequantArgs a;
@@ -167,6 +181,7 @@ int launch_requantize(const void* in, int dt_inout, void* out, int dt_quant, int
     a.out = static_cast<char*>(out);
     a.numel = numel;
     a.P = P;
+    a.dP = dP;
     a.scale_bf16 = round_to_bf16(P.scale);
     const uintptr_t ia = reinterpret_cast<uintptr_t>(in), oa = reinterpret_cast<uintptr_t>(out);
     int64_t head = static_cast<int64_t>(((32 - (ia & 31u)) & 31u) / isz);

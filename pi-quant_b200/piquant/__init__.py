@@ -186,6 +186,36 @@ class Context:
     def comm_destroy(self) -> None:
         C.piquant_cuda_comm_destroy(self._ctx)
 
+    # ---- device-resident parameters (include/piquant_cuda.h: piquant_cuda_meta_t, 64 bytes of device memory) ----
+
+    META_BYTES = 64
+
+    def compute_meta_async_ptr(self, ptr: int, dtype: DataType, numel: int, target_quant_dtype: DataType, ptr_meta: int) -> None:
+        assert dtype.is_dequantized and target_quant_dtype.is_quantized and ptr_meta != 0
+        C.piquant_cuda_compute_meta_async(self._ctx, ffi.cast("const void*", ptr), dtype.value, numel, target_quant_dtype.value,
+                                          ffi.cast("piquant_cuda_meta_t*", ptr_meta))
+
+    def quantize_meta_async_ptr(self, ptr_in: int, dtype_in: DataType, ptr_out: int, dtype_out: DataType, numel: int,
+                                round_mode: RoundMode, ptr_meta: int) -> None:
+        assert dtype_in.is_dequantized and dtype_out.is_quantized and ptr_meta != 0
+        C.piquant_cuda_quantize_meta_async(self._ctx, ffi.cast("const void*", ptr_in), dtype_in.value, ffi.cast("void*", ptr_out),
+                                           dtype_out.value, numel, round_mode.value, ffi.cast("const piquant_cuda_meta_t*", ptr_meta))
+
+    def dequantize_meta_async_ptr(self, ptr_in: int, dtype_in: DataType, ptr_out: int, dtype_out: DataType, numel: int,
+                                  reduce_op: ReduceOp, ptr_meta: int) -> None:
+        assert dtype_in.is_quantized and dtype_out.is_dequantized and ptr_meta != 0
+        C.piquant_cuda_dequantize_meta_async(self._ctx, ffi.cast("const void*", ptr_in), dtype_in.value, ffi.cast("void*", ptr_out),
+                                             dtype_out.value, numel, reduce_op.value, ffi.cast("const piquant_cuda_meta_t*", ptr_meta))
+
+    def quantize_auto_ptr(self, ptr_in: int, dtype_in: DataType, ptr_out: int, dtype_out: DataType, numel: int,
+                          round_mode: RoundMode = RoundMode.NEAREST) -> Tuple[float, int]:
+        """compute_quant_params + quantize in one call with a single synchronisation; returns (scale, zero_point)."""
+        assert dtype_in.is_dequantized and dtype_out.is_quantized and ptr_in != 0 and ptr_out != 0
+        scale, zero_point = ffi.new("float*"), ffi.new("int64_t*")
+        C.piquant_cuda_quantize_auto(self._ctx, ffi.cast("const void*", ptr_in), dtype_in.value, ffi.cast("void*", ptr_out),
+                                     dtype_out.value, numel, round_mode.value, scale, zero_point)
+        return scale[0], zero_point[0]
+
 
 def cuda_device_count() -> int:
     return int(C.piquant_cuda_device_count())

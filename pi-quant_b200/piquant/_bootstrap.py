@@ -56,6 +56,19 @@ void  piquant_cuda_params_from_minmax(float min, float max, piquant_dtype_t targ
 int   piquant_cuda_nccl_unique_id(void* out128);
 void  piquant_cuda_comm_init_rank(piquant_context_t* ctx, const void* unique_id128, int nranks, int rank);
 void  piquant_cuda_comm_destroy(piquant_context_t* ctx);
+
+typedef struct piquant_cuda_meta_t { float scale; int32_t error; int64_t zero_point; unsigned char opaque[48]; } piquant_cuda_meta_t;
+void  piquant_cuda_compute_meta_async(piquant_context_t* ctx, const void* x, piquant_dtype_t dtype, size_t n,
+                                      piquant_dtype_t target_quant_dtype, piquant_cuda_meta_t* d_meta);
+void  piquant_cuda_quantize_meta_async(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                       piquant_dtype_t dtype_out, size_t numel, piquant_round_mode_t mode,
+                                       const piquant_cuda_meta_t* d_meta);
+void  piquant_cuda_dequantize_meta_async(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                         piquant_dtype_t dtype_out, size_t numel, piquant_reduce_op_t op,
+                                         const piquant_cuda_meta_t* d_meta);
+void  piquant_cuda_quantize_auto(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                 piquant_dtype_t dtype_out, size_t numel, piquant_round_mode_t mode,
+                                 float* out_scale, int64_t* out_zero_point);
 """
 
 

@@ -123,3 +123,36 @@ def requantize(tensor: torch.Tensor, *, scale: float, zero_point: int, dtype: to
     ctx.requantize_ptr(tensor.data_ptr(), torch_to_piquant_dtype(tensor.dtype), out.data_ptr(), torch_to_piquant_dtype(dtype),
                        tensor.numel(), scale, zero_point, _ROUND_MODES[round_mode], _REDUCE_OPS[reduce_op])
     return out
+
+
+def quantize_auto(tensor: torch.Tensor, *, dtype: torch.dtype, round_mode: str = "nearest", ctx: Context = Context.get(),
+                  out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, float, int]:
+    """``compute_quant_params`` followed by ``quantize`` without a host round trip in between: min/max kernel,
+    parameter kernel and quantize kernel queue back to back (tensors that fit the 126 MB L2 are read from HBM
+    once) and there is ONE synchronisation.  Returns ``(quantized, scale, zero_point)``; bit-identical to the
+    two separate calls."""
+    assert dtype in _QUANT_TYPES, f"Unsupported quantized dtype: {dtype}. Must be one of {list(_QUANT_TYPES)}"
+    tensor = _contiguous(tensor)
+    if out is None:
+        out = torch.empty(tensor.shape, dtype=dtype, device=tensor.device)
+    else:
+        assert out.dtype == dtype and out.shape == tensor.shape and out.device == tensor.device and out.is_contiguous()
+    _bind_stream(ctx, tensor)
+    scale, zero_point = ctx.quantize_auto_ptr(tensor.data_ptr(), torch_to_piquant_dtype(tensor.dtype), out.data_ptr(),
+                                              torch_to_piquant_dtype(dtype), tensor.numel(), _ROUND_MODES[round_mode])
+    return out, scale, zero_point
+
+
+def new_meta(device: torch.device) -> torch.Tensor:
+    """A 64-byte device block for parameters that never leave the GPU (``piquant_cuda_meta_t``)."""
+    return torch.zeros(Context.META_BYTES, dtype=torch.uint8, device=device)
+
+
+def meta_to_host(meta: torch.Tensor) -> Tuple[float, int]:
+    """(scale, zero_point) of a meta block (synchronises)."""
+    raw = meta.cpu().numpy().tobytes()
+    import struct
+    scale, error, zero_point = struct.unpack_from("<fiq", raw, 0)
+    if error:
+        raise ValueError("scale must be positive")
+    return scale, zero_point

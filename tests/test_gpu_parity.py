@@ -297,3 +297,63 @@ def test_known_answers(gpu0):
     q = gpu0.quantize(c, UINT8, s, z)
     y = gpu0.dequantize(q, UINT8, c.size, F32, s, z, ADD, prev=np.zeros_like(c))
     assert np.abs(y - 42.0).max() <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# device-resident parameters (one-shot quantize): bit-identical to the two-step host-parameter path
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("cell", QUANT_CELLS, ids=cell_id)
+def test_quantize_auto_equals_params_then_quantize(gpu, cell):
+    import torch
+    from gpu_util import DT, to_dev, to_host
+    from piquant import RoundMode
+
+    dt_in, dt_out = cell
+    rng = np.random.default_rng(21)
+    for n, lo, hi in ((1, -1, 1), (7, 0, 1), (4099, -3, 5), (250_001, -1e-3, 1e3), (3_000_000, -1, 1), (30_000_000, -2, 2)):
+        x = make_input(rng, n, dt_in, lo, hi)
+        want_params = port.compute_quant_params(x, dt_out)
+        want_q = port.quantize(x, dt_out, *want_params, NEAREST, semantics=SEM_BODY)
+        d_in = to_dev(x)
+        d_out = to_dev(np.zeros(packed_bytes(dt_out, n), np.uint8))
+        got_params = gpu.ctx.quantize_auto_ptr(d_in.data_ptr(), DT[dt_in], d_out.data_ptr(), DT[dt_out], n, RoundMode.NEAREST)
+        assert np.float32(got_params[0]).tobytes() == np.float32(want_params[0]).tobytes() and got_params[1] == want_params[1], f"n={n}"
+        assert np.array_equal(to_host(d_out, np.uint8), want_q), f"n={n}"
+        # the same through the asynchronous pieces + dequantize from the device-resident parameters
+        meta = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        d_out2 = to_dev(np.zeros(packed_bytes(dt_out, n), np.uint8))
+        gpu.ctx.compute_meta_async_ptr(d_in.data_ptr(), DT[dt_in], n, DT[dt_out], meta.data_ptr())
+        gpu.ctx.quantize_meta_async_ptr(d_in.data_ptr(), DT[dt_in], d_out2.data_ptr(), DT[dt_out], n, RoundMode.NEAREST, meta.data_ptr())
+        prev = rng.uniform(-1, 1, n).astype(np.float32)
+        prev = prev if dt_in == F32 else f32_to_bf16_bits(prev)
+        d_acc = to_dev(prev)
+        from piquant import ReduceOp
+        gpu.ctx.dequantize_meta_async_ptr(d_out2.data_ptr(), DT[dt_out], d_acc.data_ptr(), DT[dt_in], n, ReduceOp.ADD, meta.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(to_host(d_out2, np.uint8), want_q), f"n={n}"
+        want_acc = port.dequantize(want_q, dt_out, n, dt_in, *want_params, ADD, out=prev.copy(), semantics=SEM_BODY)
+        got_acc = to_host(d_acc, prev.dtype)
+        assert (np.array_equal(got_acc.view(np.uint32), want_acc.view(np.uint32)) if dt_in == F32 else bf16_equal(got_acc, want_acc)), f"n={n}"
+        import piquant.torch as pt
+        assert pt.meta_to_host(meta) == (pytest.approx(want_params[0], abs=0), want_params[1])
+
+
+def test_device_params_kernel_matches_host_arithmetic(gpu0):
+    """The one-thread parameter kernel evaluates the reference's double-precision formula exactly like the host."""
+    import torch
+    import piquant.torch as pt
+    from gpu_util import DT, to_dev
+
+    rng = np.random.default_rng(22)
+    cases = [np.array(v, np.float32) for v in ([-1, 1], [0, 1], [1, 2], [-5, -1], [42, 42], [-3, 5, 1], [-3e38, 3e38], [1e-30, 2e-30],
+                                               [0, 0], [-0.0, 0.0], [1e-45, 2e-45], [-7.5, -7.5])]
+    cases += [rng.uniform(-10 ** rng.uniform(-6, 6), 10 ** rng.uniform(-6, 6), int(rng.integers(2, 2000))).astype(np.float32) for _ in range(60)]
+    for x in cases:
+        for dq in (UINT2, UINT4, UINT8):
+            meta = torch.zeros(64, dtype=torch.uint8, device="cuda")
+            d = to_dev(x)
+            gpu0.ctx.compute_meta_async_ptr(d.data_ptr(), DT[F32], x.size, DT[dq], meta.data_ptr())
+            s, z = pt.meta_to_host(meta)
+            ws, wz = port.compute_quant_params(x, dq)
+            assert np.float32(s).tobytes() == np.float32(ws).tobytes() and z == wz, (x[:4], dq, (s, z), (ws, wz))

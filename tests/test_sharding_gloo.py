@@ -100,3 +100,30 @@ def test_shard_bounds_properties():
             assert prev_end == numel
     # BASELINE config 5: 1e9 over 8 GPUs = 8 shards of 125 M elements
     assert [shard_bounds(10**9, 8, r) for r in (0, 7)] == [(0, 125_000_000), (875_000_000, 10**9)]
+
+
+def test_ring_schedule_is_an_all_reduce():
+    """quantized_all_reduce_'s chunk schedule, simulated for W ranks with exact arithmetic: what a rank sends
+    at step s is what its successor expects, reduce-scatter leaves chunk (r+1)%W complete on rank r, and the
+    all-gather spreads every reduced chunk to every rank."""
+    for p in (str(ROOT), str(ROOT / "pi-quant_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from piquant.distributed import ring_schedule
+
+    for world in (2, 3, 4, 8):
+        data = [np.arange(world * 3, dtype=np.float64).reshape(world, 3) * (r + 1) for r in range(world)]
+        want = sum(data)
+        sched = [ring_schedule(world, r) for r in range(world)]
+        for phase, combine in ((0, np.add), (1, lambda old, new: new)):
+            for s in range(world - 1):
+                msgs = [data[r][sched[r][phase][s][0]].copy() for r in range(world)]
+                for r in range(world):
+                    src = (r - 1) % world
+                    assert sched[src][phase][s][0] == sched[r][phase][s][1]
+                    data[r][sched[r][phase][s][1]] = combine(data[r][sched[r][phase][s][1]], msgs[src])
+            if phase == 0:
+                for r in range(world):
+                    assert np.array_equal(data[r][(r + 1) % world], want[(r + 1) % world])
+        for r in range(world):
+            assert np.array_equal(data[r], want)
