@@ -100,6 +100,7 @@ constexpr int kNcclFloat32 = 7, kNcclMax = 2;   // nccl.h: ncclFloat32, ncclMax
 
 // ---- per-device resources ------------------------------------------------------------------------
 constexpr int kRing = 3;                         // host-pointer pipeline depth
+constexpr int kSchedSlots = 16;                  // distinct streams one context can drive concurrently
 constexpr size_t kChunkElems = size_t(8) << 20;  // elements per pipeline chunk (f32: 32 MiB in flight per slot)
 
 struct DeviceState {
@@ -112,6 +113,10 @@ struct DeviceState {
     DeviceMeta*   d_meta = nullptr;          // parameters produced on the device (one-shot quantize)
     DeviceMeta*   h_meta = nullptr;          // pinned + mapped copy the host reads after the sync
     DeviceMeta*   h_meta_dev = nullptr;
+    // work counters of the persistent TMA kernels: one {next tile, finished CTAs} pair per stream in use
+    unsigned long long* d_sched = nullptr;
+    cudaStream_t  sched_stream[kSchedSlots]{};
+    int           sched_used = 0;
     // host-pointer pipeline (lazily created)
     cudaStream_t  s_h2d = nullptr, s_run = nullptr, s_d2h = nullptr;
     cudaEvent_t   ev_h2d[kRing]{}, ev_run[kRing]{}, ev_d2h[kRing]{};
@@ -155,6 +160,7 @@ struct Context {
             cudaFree(d.d_result);
             cudaFreeHost(d.h_result);
             cudaFree(d.d_meta);
+            cudaFree(d.d_sched);
             cudaFreeHost(d.h_meta);
             if (d.pipe_ready) {
                 for (int i = 0; i < kRing; ++i) {
@@ -189,7 +195,7 @@ struct Context {
             panic("device %d (%s) has compute capability %d.%d; this library contains sm_100a code only", device, prop.name,
                   prop.major, prop.minor);
         d.sm_count = prop.multiProcessorCount;
-        d.scratch.max_blocks = d.sm_count * 16;
+        d.scratch.max_blocks = 16384;
         PQ_CUDA_CHECK(cudaMalloc(&d.scratch.partials, sizeof(float2) * d.scratch.max_blocks));
         PQ_CUDA_CHECK(cudaMalloc(&d.scratch.ticket, sizeof(unsigned)));
         PQ_CUDA_CHECK(cudaMemset(d.scratch.ticket, 0, sizeof(unsigned)));
@@ -197,6 +203,8 @@ struct Context {
         PQ_CUDA_CHECK(cudaHostAlloc(&d.h_result, 4 * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
         PQ_CUDA_CHECK(cudaHostGetDevicePointer(&d.h_result_dev, d.h_result, 0));
         PQ_CUDA_CHECK(cudaMalloc(&d.d_meta, sizeof(DeviceMeta)));
+        PQ_CUDA_CHECK(cudaMalloc(&d.d_sched, sizeof(unsigned long long) * 2 * kSchedSlots));
+        PQ_CUDA_CHECK(cudaMemset(d.d_sched, 0, sizeof(unsigned long long) * 2 * kSchedSlots));
         PQ_CUDA_CHECK(cudaHostAlloc(&d.h_meta, sizeof(DeviceMeta), cudaHostAllocMapped | cudaHostAllocPortable));
         PQ_CUDA_CHECK(cudaHostGetDevicePointer(&d.h_meta_dev, d.h_meta, 0));
         PQ_CUDA_CHECK(cudaDeviceSynchronize());
@@ -233,6 +241,23 @@ struct Context {
 };
 
 namespace {
+
+// Launch configuration for `stream`: kernels of one stream run one after the other, so each stream owns one
+// self-resetting work-counter pair; two streams never share one.
+LaunchCfg make_cfg(Context& c, DeviceState& d, cudaStream_t stream) {
+    int slot = -1;
+    for (int i = 0; i < d.sched_used; ++i)
+        if (d.sched_stream[i] == stream) slot = i;
+    if (slot < 0) {
+        if (d.sched_used == kSchedSlots) {          // table full: quiesce the device, every pair is zero again
+            PQ_CUDA_CHECK(cudaDeviceSynchronize());
+            d.sched_used = 0;
+        }
+        slot = d.sched_used++;
+        d.sched_stream[slot] = stream;
+    }
+    return LaunchCfg{stream, d.sm_count, c.variant, d.d_sched + 2 * slot};
+}
 
 int require_device() {
     int n = 0;
@@ -313,7 +338,7 @@ void run_staged(Context& c, DeviceState& d, const Job& j, bool in_host, bool out
     PQ_CUDA_CHECK(cudaEventRecord(gate, c.stream));
     PQ_CUDA_CHECK(cudaStreamWaitEvent(d.s_h2d, gate, 0));
     PQ_CUDA_CHECK(cudaStreamWaitEvent(d.s_run, gate, 0));
-    LaunchCfg cfg{d.s_run, d.sm_count, c.variant};
+    const LaunchCfg cfg = make_cfg(c, d, d.s_run);
     size_t i = 0;
     for (size_t e0 = 0; e0 < j.numel; e0 += chunk, ++i) {
         const size_t n = (j.numel - e0 < chunk) ? j.numel - e0 : chunk;
@@ -370,7 +395,7 @@ void run_job(Context& c, const Job& j) {
         void* out = j.out;
         if (pi.where == Where::HostPinned) PQ_CUDA_CHECK(cudaHostGetDevicePointer(const_cast<void**>(&in), const_cast<void*>(j.in), 0));
         if (po.where == Where::HostPinned) PQ_CUDA_CHECK(cudaHostGetDevicePointer(&out, j.out, 0));
-        LaunchCfg cfg{c.stream, d.sm_count, c.variant};
+        const LaunchCfg cfg = make_cfg(c, d, c.stream);
         c.launches += launch_job(j, in, out, j.numel, cfg);
         // pinned host operands: keep the reference's synchronous contract
         if (pi.where == Where::HostPinned || po.where == Where::HostPinned) PQ_CUDA_CHECK(cudaStreamSynchronize(c.stream));
@@ -421,14 +446,14 @@ void compute_params(Context& c, const void* x, int dt_in, size_t n, int dt_quant
         if (pi.where == Where::Device || (pi.where == Where::HostPinned && c.host_mode == 1)) {
             const void* xp = x;
             if (pi.where == Where::HostPinned) PQ_CUDA_CHECK(cudaHostGetDevicePointer(const_cast<void**>(&xp), const_cast<void*>(x), 0));
-            LaunchCfg cfg{c.stream, d.sm_count, c.variant};
+            const LaunchCfg cfg = make_cfg(c, d, c.stream);
             c.launches += launch_minmax(xp, dt_in, static_cast<int64_t>(n), d.scratch, d.d_result, c.comm ? nullptr : d.h_result_dev, cfg);
         } else {
             // host tensor: chunks through the ring, partial results folded on the host
             const size_t chunk = kChunkElems * 2;
             const size_t isz = static_cast<size_t>(dtype_bits(dt_in) / 8);
             c.ensure_pipe(d, chunk * isz, 0);
-            LaunchCfg cfg{d.s_run, d.sm_count, c.variant};
+            const LaunchCfg cfg = make_cfg(c, d, d.s_run);
             float* h_parts = nullptr;
             const size_t n_chunks = (n + chunk - 1) / chunk;
             PQ_CUDA_CHECK(cudaHostAlloc(&h_parts, n_chunks * 4 * sizeof(float), cudaHostAllocMapped));
@@ -625,7 +650,7 @@ extern "C" void piquant_cuda_minmax_async(piquant_context_t* ctx, const void* x,
     pq_assert(pi.where == Where::Device && po.where == Where::Device, "piquant_cuda_minmax_async needs device pointers");
     DeviceGuard guard(cur, pi.device);
     DeviceState& d = c->dev_state(pi.device);
-    LaunchCfg cfg{c->stream, d.sm_count, c->variant};
+    const LaunchCfg cfg = make_cfg(*c, d, c->stream);
     c->launches += launch_minmax(x, dtype, static_cast<int64_t>(n), d.scratch, out4, nullptr, cfg);
 }
 
@@ -693,7 +718,7 @@ DeviceCall require_device_ptrs(const void* a, const void* b, const void* c, cons
 // small_tensor_bytes: > 0 asks the min/max pass to leave x in L2 for the pass that follows.
 void compute_meta_async(Context& c, DeviceState& d, const void* x, int dt_in, size_t n, int dt_quant, DeviceMeta* d_meta,
                         DeviceMeta* mapped, bool keep_in_l2) {
-    LaunchCfg cfg{c.stream, d.sm_count, c.variant};
+    const LaunchCfg cfg = make_cfg(c, d, c.stream);
     if (n > 0) {
         c.launches += launch_minmax(x, dt_in, static_cast<int64_t>(n), d.scratch, d.d_result, nullptr, cfg, keep_in_l2);
     } else {
@@ -733,7 +758,7 @@ extern "C" void piquant_cuda_quantize_meta_async(piquant_context_t* ctx, const v
     DeviceGuard guard(dc.cur, dc.device);
     DeviceState& d = c->dev_state(dc.device);
     const float xi = mode == PIQUANT_STOCHASTIC ? c->draw_xi() : 0.0f;
-    LaunchCfg cfg{c->stream, d.sm_count, c->variant};
+    const LaunchCfg cfg = make_cfg(*c, d, c->stream);
     c->launches += launch_quantize(in, dtype_in, out, dtype_out, static_cast<int64_t>(numel), make_params(1.0f, 0, xi), static_cast<int>(mode),
                                    cfg, &reinterpret_cast<const DeviceMeta*>(d_meta)->P);
 }
@@ -749,7 +774,7 @@ extern "C" void piquant_cuda_dequantize_meta_async(piquant_context_t* ctx, const
     const DeviceCall dc = require_device_ptrs(in, out, d_meta, "piquant_cuda_dequantize_meta_async");
     DeviceGuard guard(dc.cur, dc.device);
     DeviceState& d = c->dev_state(dc.device);
-    LaunchCfg cfg{c->stream, d.sm_count, c->variant};
+    const LaunchCfg cfg = make_cfg(*c, d, c->stream);
     c->launches += launch_dequantize(in, dtype_in, out, dtype_out, static_cast<int64_t>(numel), make_params(1.0f, 0, 0.0f), static_cast<int>(op),
                                      cfg, &reinterpret_cast<const DeviceMeta*>(d_meta)->P);
 }
@@ -777,7 +802,7 @@ extern "C" void piquant_cuda_quantize_auto(piquant_context_t* ctx, const void* i
     const size_t in_bytes = numel * static_cast<size_t>(dtype_bits(dtype_in) / 8);
     compute_meta_async(*c, d, in, dtype_in, numel, dtype_out, d.d_meta, d.h_meta_dev, in_bytes <= (size_t(96) << 20));
     const float xi = mode == PIQUANT_STOCHASTIC ? c->draw_xi() : 0.0f;
-    LaunchCfg cfg{c->stream, d.sm_count, c->variant};
+    const LaunchCfg cfg = make_cfg(*c, d, c->stream);
     c->launches += launch_quantize(in, dtype_in, out, dtype_out, static_cast<int64_t>(numel), make_params(1.0f, 0, xi), static_cast<int>(mode),
                                    cfg, &d.d_meta->P);
     PQ_CUDA_CHECK(cudaStreamSynchronize(c->stream));         // the ONE host sync of the whole sequence

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(kThreads) dequant_stream_kernel(const DequantA
     pdl_wait();
     load_device_params<BITS, OUT_DT>(a);
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (const int64_t tile = blockIdx.x; tile < n_tiles) {      // one tile per CTA, hardware-scheduled (see quantize.cu)
         const int64_t first = tile * TILE + threadIdx.x;
         uint32_t wi[U][NWI];
         uint32_t wp[U][OP == OP_ADD ? NWO : 1];
@@ -145,10 +145,13 @@ static void launch_cell(const void* in, void* out, int64_t numel, const QuantPar
         const int64_t total = (numel + PER - 1) / PER;
         blocks_needed = (total + kThreads - 1) / kThreads;
     }
-    int per_sm = 0;
-    PQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
-    int64_t grid = static_cast<int64_t>(cfg.sm_count) * (per_sm > 0 ? per_sm : 1);
-    if (blocks_needed < grid) grid = blocks_needed;
+    int64_t grid = blocks_needed;                      // vector kernel: one tile per CTA
+    if (!vec) {                                        // byte kernel: grid-stride over a resident grid
+        int per_sm = 0;
+        PQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
+        const int64_t resident = static_cast<int64_t>(cfg.sm_count) * (per_sm > 0 ? per_sm : 1);
+        if (resident < grid) grid = resident;
+    }
     if (grid < 1) grid = 1;
     launch_kernel(fn, static_cast<unsigned>(grid), kThreads, 0, cfg.stream, a);
     PQ_CUDA_CHECK(cudaGetLastError());

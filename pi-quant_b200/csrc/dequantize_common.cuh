@@ -15,6 +15,7 @@ struct DequantArgs {
     float          magic_zp;    // 2^23 + zp32 (exact) when fast != 0
     int32_t        fast;        // |zp| <= 2^22: the byte-permute conversion below is exact
     const QuantParams* dP;      // not null: parameters produced on the device (params_kernel), read from there
+    unsigned long long* sched;  // TMA kernels: {next tile, finished CTAs} (LaunchCfg::sched)
 };
 
 __host__ __device__ inline void set_dequant_fast(DequantArgs& a, int bits, int out_dt) {

@@ -32,7 +32,7 @@ struct DqShape {
     static constexpr int IBV = EV * BITS / 8;               // packed input bytes per output vector: 1..8
     static constexpr int IN_TILE = kOutVecs * IBV;          // 1..8 KiB
     static constexpr int STAGE = kOutTile + IN_TILE;
-    static constexpr int SMEM = kDqStages * STAGE + 2 * kDqStages * 8;
+    static constexpr int SMEM = kDqStages * STAGE + 3 * kDqStages * 8;      // + full, empty, tile index per stage
 };
 
 template <int NB>
@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(kDqThreads) dequant_tma_kernel(const DequantAr
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kDqStages * S::STAGE);
     uint64_t* empty = full + kDqStages;
+    long long* s_tile = reinterpret_cast<long long*>(empty + kDqStages);   // tile index of each stage, -1 = no more work
 
     const uint8_t* in = a.in + a.head_bytes;
     char* out = a.out + a.head_bytes * PER * S::OSZ;
@@ -78,10 +79,17 @@ __global__ void __launch_bounds__(kDqThreads) dequant_tma_kernel(const DequantAr
 
     if (threadIdx.x < 32) {
         if (threadIdx.x == 0) {
-            int i = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+            long long tile = sched_next_chunk(a.sched), chunk_end = tile + kSchedChunk;
+            long long next_chunk = sched_next_chunk(a.sched);     // requested one chunk ahead: its latency is never waited for
+            for (int i = 0;; ++i) {
                 const int s = i % kDqStages;
                 mbar_wait(empty + s, ((i / kDqStages) & 1) ^ 1);
+                if (tile >= n_tiles) {                          // tell the consumers and stop
+                    s_tile[s] = -1;
+                    mbar_arrive(full + s);
+                    break;
+                }
+                s_tile[s] = tile;
                 const int64_t v0 = tile * kOutVecs;
                 const int64_t rem = n_vecs - v0;
                 const uint32_t vecs = static_cast<uint32_t>(rem < kOutVecs ? rem : kOutVecs);
@@ -89,22 +97,29 @@ __global__ void __launch_bounds__(kDqThreads) dequant_tma_kernel(const DequantAr
                 mbar_expect_tx(full + s, vecs * S::IBV + (OP == OP_ADD ? vecs * 16 : 0));
                 tma_load_1d(st + kOutTile, in + v0 * S::IBV, vecs * S::IBV, full + s);
                 if constexpr (OP == OP_ADD) tma_load_1d(st, out + v0 * 16, vecs * 16, full + s);
+                if (++tile == chunk_end) {
+                    tile = next_chunk;
+                    chunk_end = tile + kSchedChunk;
+                    next_chunk = sched_next_chunk(a.sched);
+                }
             }
+            sched_cta_done(a.sched);
         }
         return;
     }
 
     const int t = threadIdx.x - 32;
-    int i = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+    for (int i = 0;; ++i) {
         const int s = i % kDqStages;
+        mbar_wait(full + s, (i / kDqStages) & 1);
+        const long long tile = s_tile[s];
+        if (tile < 0) break;
         const int64_t v0 = tile * kOutVecs;
         const int64_t rem = n_vecs - v0;
         const int vecs = static_cast<int>(rem < kOutVecs ? rem : kOutVecs);
         unsigned char* st = smem + s * S::STAGE;
         uint4* ot = reinterpret_cast<uint4*>(st);
         const unsigned char* it = st + kOutTile;
-        mbar_wait(full + s, (i / kDqStages) & 1);
         constexpr int NV = kOutVecs / kDqConsumers;      // 16-byte output vectors per thread per tile
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
@@ -193,6 +208,7 @@ int launch_dequantize_tma(const void* in, int dt_in, void* out, int dt_out, int6
     a.numel = numel;
     a.P = P;
     a.dP = dP;
+    a.sched = cfg.sched;
     a.head_bytes = 0;
     a.n_items = 0;
     const int64_t full_bytes = numel / per;

@@ -37,6 +37,7 @@ struct MinMaxArgs {
     unsigned*   ticket;
     float*      result;         // device: {min, max, -min, max}
     float*      mapped_result;  // device-mapped pinned host copy of the same, or nullptr
+    int64_t     tiles_per_cta;  // each CTA folds this many consecutive tiles
 };
 
 template <int IN_DT, bool KEEP>
@@ -53,7 +54,11 @@ __global__ void __launch_bounds__(kThreads) minmax_kernel(const MinMaxArgs a) {
     pdl_launch_dependents();
     pdl_wait();                                          // also orders this launch after the previous one's use of the scratch
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // CTA b owns tiles [b*C, (b+1)*C): many more CTAs than SMs, dealt by the hardware scheduler, so no SM waits for
+    // a slower one (static round-robin over a persistent grid measured ~4 % lower on reads)
+    const int64_t tile_begin = static_cast<int64_t>(blockIdx.x) * a.tiles_per_cta;
+    const int64_t tile_end = tile_begin + a.tiles_per_cta < n_tiles ? tile_begin + a.tiles_per_cta : n_tiles;
+    for (int64_t tile = tile_begin; tile < tile_end; ++tile) {
         const int64_t first = tile * TILE + threadIdx.x;
         uint32_t w[U][8];
         if (tile * TILE + TILE <= a.n_items) {
@@ -167,13 +172,11 @@ int launch_minmax(const void* x, int dt, int64_t numel, const MinMaxScratch& scr
     a.n_items = (numel - head) / epi;
     auto fn = dt == DT_F32 ? (keep_in_l2 ? minmax_kernel<DT_F32, true> : minmax_kernel<DT_F32, false>)
                            : (keep_in_l2 ? minmax_kernel<DT_BF16, true> : minmax_kernel<DT_BF16, false>);
-    int per_sm = 0;
-    PQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
     const int64_t tile = static_cast<int64_t>(kThreads) * 4;
-    int64_t blocks_needed = (a.n_items + tile - 1) / tile;
-    int64_t grid = static_cast<int64_t>(cfg.sm_count) * (per_sm > 0 ? per_sm : 1);
-    if (grid > scratch.max_blocks) grid = scratch.max_blocks;
-    if (blocks_needed < grid) grid = blocks_needed;
+    const int64_t n_tiles = (a.n_items + tile - 1) / tile;
+    a.tiles_per_cta = (n_tiles + scratch.max_blocks - 1) / scratch.max_blocks;      // one partial per CTA must fit the scratch
+    if (a.tiles_per_cta < 1) a.tiles_per_cta = 1;
+    int64_t grid = (n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
     if (grid < 1) grid = 1;
     launch_kernel(fn, static_cast<unsigned>(grid), kThreads, 0, cfg.stream, a);
     PQ_CUDA_CHECK(cudaGetLastError());

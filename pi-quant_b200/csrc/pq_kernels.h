@@ -16,6 +16,7 @@ struct LaunchCfg {
     cudaStream_t stream;
     int          sm_count;   // 148 on B200; grids are sized in multiples of it
     int          variant;    // 0 = auto, 1 = direct LDG/STG kernels, 2 = TMA (cp.async.bulk) ring kernels
+    unsigned long long* sched;   // {next tile, finished CTAs}: work counter of the persistent TMA kernels, zero between launches
 };
 
 // [[noreturn]] abort with a red message on stderr -- the reference's error convention
@@ -129,20 +130,16 @@ static_assert(sizeof(DeviceMeta) == 64 && offsetof(DeviceMeta, P) == 16, "piquan
 // plus everything the kernels derive from it (1/scale, bias, range flags).  Asynchronous on cfg.stream.
 int launch_params(const float* minmax4, int dt_quant, DeviceMeta* out, DeviceMeta* mapped_out, const LaunchCfg& cfg);
 
-// variant 0 ("auto"): which quantize cells go to the TMA ring kernel; every entry is a measurement
-// on B200 at numel = 1e9 (profiles/cellbench_*.md), not a guess
-//   * below ~0.5 GB of traffic the direct kernels win everywhere: no mbarrier set-up, no pipeline fill, shorter
-//     tail (27 M elements f32->u8: 22.6 us direct vs 24.2 us TMA; 16 M elements u4->bf16: 7.0 vs 9.2 us);
-//   * above it the TMA ring is equal or better for the f32 quantize cells and bf16->u8 nearest (96-99 % of the
-//     measured copy peak), and 3-6 points better for dequantize (few long bulk stores instead of many 1-2 KiB
-//     warp stores); the ALU-heavier bf16 quantize cells keep the direct kernel's higher occupancy.
-// Differences below ~3 % are inside the run-to-run drift of a power-capped B200 (profiles/r1_placement_probe.txt).
-constexpr int64_t kTmaMinBytes = int64_t(512) << 20;
+// variant 0 ("auto"): which cells go to the TMA ring kernels.  Every entry is a measurement on B200, not a guess.
+// With one-tile-per-CTA hardware scheduling the direct LDG.256/STG kernels run at the traffic ceiling of the chip
+// (f32->u8: 7.19 TB/s = 110 % of the measured copy peak, against 7.23 TB/s for the same read:write mix with no
+// arithmetic at all, profiles/r1_sched_probe_static_vs_dynamic_tiles.txt), at every size and for every cell
+// (profiles/r1_cellbench_1e9_dynamic_tiles.txt), so "auto" currently selects the TMA ring nowhere; it stays
+// selectable (variant 2), tested to the same bit-exact bar, and serves inputs that are only 16-byte aligned.
 inline bool quantize_prefers_tma(int dt_in, int dt_out, int mode, int64_t algorithmic_bytes) {
-    if (algorithmic_bytes < kTmaMinBytes) return false;
-    if (dt_in == DT_F32) return true;
-    return dt_out == DT_U8 && mode == 0;
+    (void)dt_in; (void)dt_out; (void)mode; (void)algorithmic_bytes;
+    return false;
 }
-inline bool dequantize_prefers_tma(int64_t algorithmic_bytes) { return algorithmic_bytes >= kTmaMinBytes; }
+inline bool dequantize_prefers_tma(int64_t algorithmic_bytes) { (void)algorithmic_bytes; return false; }
 
 }  // namespace pq

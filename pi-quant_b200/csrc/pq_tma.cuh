@@ -53,4 +53,24 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 template <int THREADS>
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 
+// ---- dynamic tile assignment for the persistent ring kernels --------------------------------------------
+// A static tile -> CTA map makes the whole grid wait for its slowest SM (the two dies of a B200 differ by
+// ~10 % in memory latency): 6.7 vs 7.2 TB/s on a 4:1 read:write stream (profiles/r1_sched_probe_*.txt).  The
+// producer thread of each CTA therefore draws tile indices from a global counter.  sched[0] = next tile,
+// sched[1] = CTAs that have finished drawing; the last one resets both, so the pair is zero between launches.
+// Tiles are drawn kSchedChunk at a time (one atomic per 8 tiles keeps the single counter far from its
+// same-address throughput limit) and the NEXT chunk is requested while the current one is being issued.
+constexpr int kSchedChunk = 8;
+__device__ __forceinline__ long long sched_next_chunk(unsigned long long* sched) {
+    return static_cast<long long>(atomicAdd(sched, static_cast<unsigned long long>(kSchedChunk)));
+}
+__device__ __forceinline__ void sched_cta_done(unsigned long long* sched) {
+    __threadfence();
+    if (atomicAdd(sched + 1, 1ull) == gridDim.x - 1) {
+        sched[0] = 0ull;
+        sched[1] = 0ull;
+        __threadfence();
+    }
+}
+
 }  // namespace pq

@@ -15,7 +15,7 @@
 //   pack   = the 8/16 elements of a vector become 2..16 packed bytes in registers (quant_group: clamp
 //            and pack fused in I2IP) and leave with one STG.{16,32,64,128}; a warp's stores are
 //            contiguous, full sectors.
-//   grid   = persistent: (resident CTAs per SM) x 148 SMs, tiles dealt round-robin.
+//   grid   = one tile per CTA, dealt by the hardware scheduler (dynamic balance across the two dies).
 //   ragged = output bytes before the 16-byte aligned region and after the last full vector are
 //            produced byte-by-byte by the last CTA of the same launch (no second kernel).
 // Inputs whose alignment rules out vector loads go through the byte-granular kernel.
@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(kThreads) quant_stream_kernel(const QuantArgs 
     pdl_wait();
     load_device_params(a);
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // ONE tile per CTA: the hardware CTA scheduler deals tiles to whichever SM is free.  (A persistent grid with a
+    // static tile -> CTA map waits for its slowest SM -- the two dies differ by ~10 % -- and measured 7 % slower:
+    // profiles/r1_sched_probe_static_vs_dynamic_tiles.txt.)
+    if (const int64_t tile = blockIdx.x; tile < n_tiles) {
         const int64_t first = tile * TILE + threadIdx.x;
         uint32_t w[J][8];
         if (tile * TILE + TILE <= n_vecs) {
@@ -132,10 +135,13 @@ static void launch_cell(const QuantArgs& a0, bool vec, const LaunchCfg& cfg) {
         const int64_t total = (a.numel + PER - 1) / PER;
         blocks_needed = (total + kThreads - 1) / kThreads;
     }
-    int per_sm = 0;
-    PQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
-    int64_t grid = static_cast<int64_t>(cfg.sm_count) * (per_sm > 0 ? per_sm : 1);
-    if (blocks_needed < grid) grid = blocks_needed;
+    int64_t grid = blocks_needed;                      // vector kernel: one tile per CTA
+    if (!vec) {                                        // byte kernel: grid-stride over a resident grid
+        int per_sm = 0;
+        PQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
+        const int64_t resident = static_cast<int64_t>(cfg.sm_count) * (per_sm > 0 ? per_sm : 1);
+        if (resident < grid) grid = resident;
+    }
     if (grid < 1) grid = 1;
     launch_kernel(fn, static_cast<unsigned>(grid), kThreads, 0, cfg.stream, a);
     PQ_CUDA_CHECK(cudaGetLastError());

@@ -13,6 +13,7 @@ struct QuantArgs {
     int64_t     n_items;     // full 16-byte output items in the vectorised region
     QuantParams P;
     const QuantParams* dP;   // not null: the parameters were produced on the device (params_kernel) and are read from there
+    unsigned long long* sched;   // TMA kernels: {next tile, finished CTAs} (LaunchCfg::sched)
 };
 
 // Parameters computed by an earlier kernel on the stream replace the by-value ones (the per-call stochastic

@@ -30,7 +30,7 @@ struct TmaShape {
     static constexpr int OBV = EV * BITS / 8;           // packed output bytes per vector: 1, 2, 4 or 8
     static constexpr int IN_TILE = kTileVecs * 16;
     static constexpr int OUT_TILE = kTileVecs * OBV;
-    static constexpr int SMEM = kStages * IN_TILE + 2 * OUT_TILE + 2 * kStages * 8;
+    static constexpr int SMEM = kStages * IN_TILE + 2 * OUT_TILE + 3 * kStages * 8;     // + full, empty, tile index per stage
 };
 
 template <int IN_DT, int BITS, int STEP>
@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(kTmaThreads) quant_tma_kernel(const QuantArgs 
     unsigned char* s_out = smem + kStages * S::IN_TILE;
     uint64_t* full = reinterpret_cast<uint64_t*>(s_out + 2 * S::OUT_TILE);
     uint64_t* empty = full + kStages;
+    long long* s_tile = reinterpret_cast<long long*>(empty + kStages);      // tile index of each stage, -1 = no more work
 
     const char* in = a.in + a.head_bytes * PER * S::ISZ;
     uint8_t* out = a.out + a.head_bytes;
@@ -61,29 +62,43 @@ __global__ void __launch_bounds__(kTmaThreads) quant_tma_kernel(const QuantArgs 
 
     if (threadIdx.x < 32) {
         if (threadIdx.x == 0) {
-            int i = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+            long long tile = sched_next_chunk(a.sched), chunk_end = tile + kSchedChunk;
+            long long next_chunk = sched_next_chunk(a.sched);     // requested one chunk ahead: its latency is never waited for
+            for (int i = 0;; ++i) {
                 const int s = i % kStages;
                 mbar_wait(empty + s, ((i / kStages) & 1) ^ 1);
+                if (tile >= n_tiles) {                          // tell the consumers and stop
+                    s_tile[s] = -1;
+                    mbar_arrive(full + s);
+                    break;
+                }
+                s_tile[s] = tile;
                 const int64_t v0 = tile * kTileVecs;
                 const int64_t rem = n_vecs - v0;
                 const uint32_t bytes = static_cast<uint32_t>((rem < kTileVecs ? rem : kTileVecs) * 16);
                 mbar_expect_tx(full + s, bytes);
                 tma_load_1d(s_in + s * S::IN_TILE, in + v0 * 16, bytes, full + s);
+                if (++tile == chunk_end) {
+                    tile = next_chunk;
+                    chunk_end = tile + kSchedChunk;
+                    next_chunk = sched_next_chunk(a.sched);
+                }
             }
+            sched_cta_done(a.sched);
         }
         return;
     }
 
     const int t = threadIdx.x - 32;
-    int i = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++i) {
+    for (int i = 0;; ++i) {
         const int s = i % kStages;
+        mbar_wait(full + s, (i / kStages) & 1);
+        const long long tile = s_tile[s];
+        if (tile < 0) break;
         const int64_t v0 = tile * kTileVecs;
         const int64_t rem = n_vecs - v0;
         const int vecs = static_cast<int>(rem < kTileVecs ? rem : kTileVecs);
         unsigned char* ob = s_out + (i & 1) * S::OUT_TILE;
-        mbar_wait(full + s, (i / kStages) & 1);
         const uint4* src = reinterpret_cast<const uint4*>(s_in + s * S::IN_TILE);
         constexpr int NV = kTileVecs / kConsumers;       // 16-byte vectors per thread per tile
         uint4 v[NV];
@@ -170,6 +185,7 @@ int launch_quantize_tma(const void* in, int dt_in, void* out, int dt_out, int64_
     a.numel = numel;
     a.P = P;
     a.dP = dP;
+    a.sched = cfg.sched;
     const int64_t full_bytes = numel / per;
     int64_t head = static_cast<int64_t>((16 - (reinterpret_cast<uintptr_t>(out) & 15u)) & 15u);
     if (head > full_bytes) head = full_bytes;

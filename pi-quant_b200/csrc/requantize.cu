@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kThreads) requant_stream_kernel(const RequantA
     pdl_wait();
     load_device_params(a);
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (const int64_t tile = blockIdx.x; tile < n_tiles) {      // one tile per CTA, hardware-scheduled (see quantize.cu)
         const int64_t first = tile * TILE + threadIdx.x;
         uint32_t w[U][8];
         uint32_t p[U][OP == OP_ADD ? 8 : 1];
@@ -142,10 +142,13 @@ static void launch_cell(RequantArgs a, int32_t qmax, bool vec, const LaunchCfg& 
         a.n_items = 0;
         blocks_needed = (a.numel + kThreads - 1) / kThreads;
     }
-    int per_sm = 0;
-    PQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
-    int64_t grid = static_cast<int64_t>(cfg.sm_count) * (per_sm > 0 ? per_sm : 1);
-    if (blocks_needed < grid) grid = blocks_needed;
+    int64_t grid = blocks_needed;                      // vector kernel: one tile per CTA
+    if (!vec) {                                        // scalar kernel: grid-stride over a resident grid
+        int per_sm = 0;
+        PQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
+        const int64_t resident = static_cast<int64_t>(cfg.sm_count) * (per_sm > 0 ? per_sm : 1);
+        if (resident < grid) grid = resident;
+    }
     if (grid < 1) grid = 1;
     launch_kernel(fn, static_cast<unsigned>(grid), kThreads, 0, cfg.stream, a, qmax);
     PQ_CUDA_CHECK(cudaGetLastError());
