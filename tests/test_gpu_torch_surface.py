@@ -180,3 +180,88 @@ def test_full_size_properties_1e9(pt):
     for lo in (0, n // 2 - 77, n - (1 << 22)):
         xs = x[lo:lo + (1 << 22)].cpu().numpy()
         assert np.array_equal(q[lo:lo + (1 << 22)].cpu().numpy(), port.quantize(xs, port.UINT8, s, z))
+
+
+def test_full_size_c2_bf16_quint4x2_round_trip_1e8(pt):
+    """BASELINE config 2 at its full size: bf16 -> quint4x2 -> bf16, numel = 1e8.  Properties: error <= 0.5*scale
+    (+ the bf16 rounding of the output), idempotence of quantize on dequantized data, 16 used levels, and the first /
+    last 4 Mi elements against the oracle bit for bit."""
+    n = 100_000_000
+    x = torch.empty(n, device="cuda").uniform_(-1, 1, generator=torch.Generator(device="cuda").manual_seed(2)).bfloat16()
+    s, z = pt.compute_quant_params(x, dtype=torch.quint4x2)
+    q = pt.quantize(x, scale=s, zero_point=z, dtype=torch.quint4x2)
+    y = pt.dequantize(q, scale=s, zero_point=z, dtype=torch.bfloat16)
+    err = (y.float() - x.float()).abs().max().item()
+    assert err <= 0.5 * s + 2.0**-8 * (1.0 + s)
+    q2 = pt.quantize(y, scale=s, zero_point=z, dtype=torch.quint4x2)
+    raw = torch.empty(0, dtype=torch.uint8, device="cuda").set_(q.untyped_storage())[: n // 2]
+    raw2 = torch.empty(0, dtype=torch.uint8, device="cuda").set_(q2.untyped_storage())[: n // 2]
+    assert torch.equal(raw, raw2)
+    levels = torch.bincount((raw & 15).int(), minlength=16) + torch.bincount((raw >> 4).int(), minlength=16)
+    # level 0 needs x/scale <= -7.5, i.e. x < -1 with inv_scale = fl(1/scale) = 7.4999995: unreachable on [-1, 1]
+    assert int(levels.sum()) == n and int(levels[1:].min()) > 0
+    from oracle import port
+    m = 1 << 22
+    for lo in (0, n - m):
+        xs = x[lo:lo + m].view(torch.int16).cpu().numpy().view(np.uint16)
+        want_q = port.quantize(xs, port.UINT4, s, z)
+        assert np.array_equal(raw[lo // 2:(lo + m) // 2].cpu().numpy(), want_q)
+        want_y = port.dequantize(want_q, port.UINT4, m, port.BF16, s, z)
+        assert np.array_equal(y[lo:lo + m].view(torch.int16).cpu().numpy().view(np.uint16), want_y)
+
+
+def test_full_size_c4_stochastic_and_c5_add_1e9(pt):
+    """BASELINE configs 4 and 5 at numel = 1e9.  Stochastic: every element is either the truncated or the
+    away-from-zero neighbour, consistent with ONE threshold (the one the context reports), and differs from
+    nearest by at most one step.  ADD: linear -- accumulating the same quantized tensor k times gives k times
+    the SET result, bit for bit where the sums are exact."""
+    import piquant
+
+    n = 1_000_000_000
+    if torch.cuda.mem_get_info()[0] < 24 * 2**30:
+        pytest.skip("needs 24 GiB of free device memory")
+    ctx = piquant.Context()
+    x = torch.empty(n, device="cuda").uniform_(-1, 1, generator=torch.Generator(device="cuda").manual_seed(4))
+    s, z = pt.compute_quant_params(x, dtype=torch.uint8, ctx=ctx)
+    qn = pt.quantize(x, scale=s, zero_point=z, dtype=torch.uint8, ctx=ctx)
+    qs = pt.quantize(x, scale=s, zero_point=z, dtype=torch.uint8, round_mode="stochastic", ctx=ctx)
+    xi = ctx.last_stochastic_threshold
+    assert 0.0 <= xi < 1.0
+    blk = 1 << 27
+    inv = torch.tensor(1.0, dtype=torch.float32) / torch.tensor(s, dtype=torch.float32)
+    for i in range(0, n, blk):
+        r = x[i:i + blk] * inv.item()
+        tr = torch.trunc(r)
+        away = (r - tr).abs() > xi
+        want = torch.clamp(tr + torch.where(away, torch.sign(r), torch.zeros_like(r)) + z, 0, 255).to(torch.uint8)
+        assert torch.equal(qs[i:i + blk], want)
+        assert (qs[i:i + blk].int() - qn[i:i + blk].int()).abs().max().item() <= 1
+    del qs, x
+    # C5: u8 -> f32 with the ADD store op is linear in the number of accumulations
+    set_once = pt.dequantize(qn, scale=s, zero_point=z, dtype=torch.float32, ctx=ctx)
+    acc = torch.zeros(n, device="cuda")
+    for _ in range(4):
+        pt.dequantize(qn, scale=s, zero_point=z, dtype=torch.float32, reduce_op="add", out=acc, ctx=ctx)
+    # every accumulation is ONE fma(d, s, acc) in f32; d*s + acc is exact in f64 here (33 significant bits), so
+    # rounding the f64 sum to f32 reproduces the fma bit for bit
+    for i in range(0, n, blk):
+        d = (qn[i:i + blk].int() - z).double()
+        ref = torch.zeros(d.numel(), device="cuda", dtype=torch.float32)
+        for _ in range(4):
+            ref = (ref.double() + d * s).float()
+        assert torch.equal(acc[i:i + blk], ref)
+        assert torch.allclose(acc[i:i + blk], 4 * set_once[i:i + blk], rtol=0, atol=4e-7)
+
+
+def test_full_size_c3_minmax_1e9_both_dtypes(pt):
+    n = 1_000_000_000
+    x = torch.empty(n, device="cuda").uniform_(-3, 5, generator=torch.Generator(device="cuda").manual_seed(3))
+    x[123_456_789] = -7.25
+    x[n - 1] = 9.5
+    for t in (x, x.bfloat16()):
+        mn, mx = t.float().min().item(), t.float().max().item()
+        for dt, qmax in ((torch.quint8, 255), (torch.quint4x2, 15), (torch.quint2x4, 3)):
+            s, z = pt.compute_quant_params(t, dtype=dt)
+            want_s = np.float32((np.float64(mx) - np.float64(mn)) / qmax)
+            want_z = int(max(0.0, min(float(qmax), float(np.round(0.0 - np.float64(mn) / ((np.float64(mx) - np.float64(mn)) / qmax))))))
+            assert np.float32(s) == want_s and z == want_z
