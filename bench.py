@@ -336,6 +336,26 @@ def run_extra(torch, ctx, D, RoundMode, ReduceOp, x, q, scale, zp, dev) -> dict:
             fn()
         t = (time.perf_counter() - t0) / 50
         out[name] = {"numel": n1, "us": round(t * 1e6, 2), "Gelem/s": round(n1 / t / 1e9, 1), "note": "wall clock incl. synchronisation; min/max + params + quantize"}
+    # per-launch distribution of the headline kernel (one event pair per launch) and the cost of a call on a tiny tensor
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(50)]
+    for e0, e1 in evs:
+        e0.record()
+        ctx.quantize_ptr(x.data_ptr(), D.F32, q.data_ptr(), D.UINT8, n, scale, zp, RoundMode.NEAREST)
+        e1.record()
+    torch.cuda.synchronize()
+    per = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
+    out["headline_per_launch_ms"] = {"best": round(per[0], 4), "median": round(per[len(per) // 2], 4), "worst": round(per[-1], 4),
+                                     "best_GBps": round(5 * n / (per[0] * 1e-3) / 1e9, 1), "median_GBps": round(5 * n / (per[len(per) // 2] * 1e-3) / 1e9, 1)}
+    tiny = 4096
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(2000):
+        ctx.quantize_ptr(x.data_ptr(), D.F32, q.data_ptr(), D.UINT8, tiny, scale, zp, RoundMode.NEAREST)
+    t_issue = (time.perf_counter() - t0) / 2000
+    torch.cuda.synchronize()
+    t_total = (time.perf_counter() - t0) / 2000
+    out["call_overhead_us_numel_4096"] = {"host_issue": round(t_issue * 1e6, 2), "throughput_back_to_back": round(t_total * 1e6, 2),
+                                         "note": "cffi call + pointer classification + cudaLaunchKernelEx (PDL)"}
     # C4: stochastic rounding
     rec("C4_f32_u8_stochastic", n, 5, time_launches(torch, lambda: ctx.quantize_ptr(x.data_ptr(), D.F32, q.data_ptr(), D.UINT8, n, scale, zp, RoundMode.STOCHASTIC), 10))
     # C5: dequantize with ADD store op into an f32 accumulator (one 1/8 shard of 1e9 and the full size)
