@@ -704,12 +704,14 @@ struct DeviceCall {          // common prologue of the *_async entry points: eve
 DeviceCall require_device_ptrs(const void* a, const void* b, const void* c, const char* who) {
     const int cur = require_device();
     int device = -1;
+    // The kernel runs on the device that owns the FIRST buffer (the tensor being read).  The other buffers only have
+    // to be device memory: they may live on a peer GPU whose memory is mapped here (NVLink P2P / symmetric memory) --
+    // that is how a ring step quantizes straight into its neighbour's receive buffer.
     for (const void* p : {a, b, c}) {
         if (!p) continue;
         const PtrInfo pi = classify(p);
         pq_assert(pi.where == Where::Device, "%s needs CUDA device pointers", who);
-        pq_assert(device < 0 || device == pi.device, "%s: buffers live on different devices (%d and %d)", who, device, pi.device);
-        device = pi.device;
+        if (device < 0) device = pi.device;
     }
     return {cur, device};
 }

@@ -108,8 +108,25 @@ def ring_schedule(world_size: int, rank: int):
     return reduce_scatter, all_gather
 
 
+_P2P_SLOTS: dict = {}
+
+
+def _p2p_slots(nbytes: int, device: torch.device, group):
+    """Two receive slots per rank in symmetric memory (every rank can address every other rank's slots over
+    NVLink).  Cached per (group, device, size): the rendezvous is a collective and costs milliseconds."""
+    import torch.distributed._symmetric_memory as symm_mem
+
+    grp = group if group is not None else dist.group.WORLD
+    key = (grp.group_name, device.index, nbytes)
+    if key not in _P2P_SLOTS:
+        buf = symm_mem.empty(2 * nbytes, dtype=torch.uint8, device=device)
+        hdl = symm_mem.rendezvous(buf, grp)
+        _P2P_SLOTS[key] = (buf, hdl)
+    return _P2P_SLOTS[key]
+
+
 def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.quint8, group: Optional[dist.ProcessGroup] = None,
-                          ctx: Context = Context.get()) -> torch.Tensor:
+                          ctx: Context = Context.get(), transport: str = "nccl") -> torch.Tensor:
     """In-place SUM all-reduce of a contiguous CUDA float32 / bfloat16 tensor with quantized transport.
 
     Ring reduce-scatter + ring all-gather over NVLink; every hop carries ``[64-byte parameter block | packed
@@ -118,7 +135,12 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
     store op into the accumulator chunk on the receiver; parameters never visit the host, so the whole
     collective is enqueued without a single synchronisation.  In the all-gather phase the owner of a reduced
     chunk dequantizes its own packed bytes too, so every rank ends with bit-identical values.
-    The result is the sum up to quantization error (<= 0.5 * scale per hop and element)."""
+    The result is the sum up to quantization error (<= 0.5 * scale per hop and element).
+
+    ``transport="nccl"``: each hop is an NCCL send/recv of the packed buffer.  ``transport="p2p"``: the sender's
+    quantize kernel stores its packed output (and the parameter kernel its 64-byte block) DIRECTLY into the
+    receiver's slot through NVLink peer memory (torch symmetric memory) -- compute and transfer are one kernel,
+    there is no send/recv and no staging copy; a stream-ordered barrier per hop publishes the slot."""
     assert tensor.is_cuda and tensor.is_contiguous() and tensor.dtype in (torch.float32, torch.bfloat16)
     assert dtype in _QUANT_TYPES
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -156,6 +178,45 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
             req.wait()
 
     reduce_scatter, all_gather = ring_schedule(world, rank)
+    if transport == "p2p":
+        slot_bytes = (meta + max(qbytes) + 255) // 256 * 256
+        local_slots, hdl = _p2p_slots(slot_bytes, tensor.device, group)
+        nxt_rank, my_base, nxt_base = (rank + 1) % world, local_slots.data_ptr(), int(hdl.buffer_ptrs[(rank + 1) % world])
+        step = 0
+
+        def pack_to(i, base_ptr):            # chunk i -> [meta | packed] at base_ptr (local or peer memory)
+            c = chunk(i)
+            if c.numel():
+                ctx.compute_meta_async_ptr(c.data_ptr(), fdt, c.numel(), qdt, base_ptr)
+                ctx.quantize_meta_async_ptr(c.data_ptr(), fdt, base_ptr + meta, qdt, c.numel(), RoundMode.NEAREST, base_ptr)
+
+        def unpack_from(i, base_ptr, op):
+            c = chunk(i)
+            if c.numel():
+                ctx.dequantize_meta_async_ptr(base_ptr + meta, qdt, c.data_ptr(), fdt, c.numel(), op, base_ptr)
+
+        hdl.barrier(channel=0)               # nobody is still reading the slots of a previous call
+        for send_i, recv_i in reduce_scatter:
+            off = (step % 2) * slot_bytes
+            pack_to(send_i, nxt_base + off)                  # quantize straight into the neighbour's slot over NVLink
+            hdl.barrier(channel=0)                           # my slot `off` now holds chunk recv_i from my predecessor
+            unpack_from(recv_i, my_base + off, ReduceOp.ADD)
+            step += 1
+        own = (rank + 1) % world
+        keep = bufs[0]                                       # the owner's packed copy: what everybody else will receive
+        pack_to(own, keep.data_ptr())
+        unpack_from(own, keep.data_ptr(), ReduceOp.SET)
+        src_ptr, src_tensor = keep.data_ptr(), keep
+        peer_slots = hdl.get_buffer(nxt_rank, (2 * slot_bytes,), torch.uint8)
+        for send_i, recv_i in all_gather:
+            off = (step % 2) * slot_bytes
+            nbytes = meta + qbytes[send_i]
+            peer_slots[off: off + nbytes].copy_(src_tensor[:nbytes], non_blocking=True)      # NVLink peer store of the packed bytes
+            hdl.barrier(channel=0)
+            unpack_from(recv_i, my_base + off, ReduceOp.SET)
+            src_tensor = local_slots[off: off + slot_bytes]  # forward what was just received
+            step += 1
+        return tensor
     send_buf, recv_buf, spare = bufs
     for send_i, recv_i in reduce_scatter:
         pack(send_i, send_buf)

@@ -59,12 +59,14 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
             res[name] = (got_torch == want, got_native == want, got_local == want_local,
                          bool(np.array_equal(raw, whole[b // per: b // per + nbytes])))
         # quantized ring all-reduce: every rank ends with bit-identical values, close to the exact sum
-        for tdt, qdt, tol_steps in ((torch.float32, torch.quint8, 1.0), (torch.bfloat16, torch.quint8, 1.0), (torch.float32, torch.quint4x2, 1.0)):
+        for tdt, qdt, transport in ((torch.float32, torch.quint8, "nccl"), (torch.bfloat16, torch.quint8, "nccl"), (torch.float32, torch.quint4x2, "nccl"),
+                                    (torch.float32, torch.quint8, "p2p"), (torch.bfloat16, torch.quint4x2, "p2p"), (torch.float32, torch.quint8, "p2p")):
+            tol_steps = 1.0
             g = torch.Generator(device="cuda").manual_seed(100 + rank)
             t = (torch.rand(1_000_003, device="cuda", generator=g) * 2 - 1).to(tdt)
             exact = t.double().clone()
             dist.all_reduce(exact)
-            pd.quantized_all_reduce_(t, dtype=qdt, ctx=ctx)
+            pd.quantized_all_reduce_(t, dtype=qdt, ctx=ctx, transport=transport)
             gathered = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(gathered, t)
             identical = all(torch.equal(gathered[0].view(torch.uint8), gi.view(torch.uint8)) for gi in gathered)
@@ -72,7 +74,7 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
             step = 2.0 * world / qmax                     # |sum| <= world, so every hop's scale is <= 2*world/qmax
             err = (t.double() - exact).abs().max().item()
             bound = step * (0.5 * world + 0.5) * tol_steps + (0.02 * world if tdt == torch.bfloat16 else 1e-5)
-            res[f"ring_{tdt}_{qdt}"] = (identical, err <= bound)
+            res[f"ring_{transport}_{tdt}_{qdt}_{len(res)}"] = (identical, err <= bound)
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
