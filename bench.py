@@ -433,7 +433,9 @@ def ring_allreduce_leg(torch, dist, ctx, world, rank, dev) -> dict:
     bus = 2 * (world - 1) / world * n * 4 / 1e9
     return {"numel": n, "ms_nccl_f32": round(ms_nccl, 3), "ms_quantized_u8": round(ms_q8, 3), "ms_quantized_u8_p2p_fused": ms_p2p, "speedup": round(ms_nccl / ms_q8, 3),
             "nccl_busbw_GBps": round(bus / (ms_nccl * 1e-3), 1), "effective_busbw_GBps": round(bus / (ms_q8 * 1e-3), 1),
-            "max_abs_err": round(float(err.item()), 5), "note": "ring reduce-scatter + all-gather, [64 B params | u8 payload] per hop, no host sync"}
+            "speedup_p2p_fused": round(ms_nccl / ms_p2p, 3) if isinstance(ms_p2p, float) else None,
+            "max_abs_err": round(float(err.item()), 5),
+            "note": "ring reduce-scatter + all-gather, [64 B params | u8 payload] per hop, no host sync; p2p_fused = the quantize kernel stores into the neighbour's slot over NVLink peer memory"}
 
 
 def cpu_reference_leg(x_host, q_gpu_host, scale, zp):
