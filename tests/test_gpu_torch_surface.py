@@ -265,3 +265,47 @@ def test_full_size_c3_minmax_1e9_both_dtypes(pt):
             want_s = np.float32((np.float64(mx) - np.float64(mn)) / qmax)
             want_z = int(max(0.0, min(float(qmax), float(np.round(0.0 - np.float64(mn) / ((np.float64(mx) - np.float64(mn)) / qmax))))))
             assert np.float32(s) == want_s and z == want_z
+
+
+def test_device_parameter_path_is_cuda_graph_capturable(pt):
+    """min/max -> parameters -> quantize -> dequantize-ADD with parameters that never leave the GPU has no host
+    synchronisation, so the whole sequence can be captured once into a CUDA graph and replayed on new data."""
+    import piquant
+    from piquant import DataType as D, ReduceOp, RoundMode
+
+    n = 3_000_007
+    ctx = piquant.Context()
+    x = torch.empty(n, device="cuda")
+    q = torch.empty(n, dtype=torch.uint8, device="cuda")
+    acc = torch.zeros(n, device="cuda")
+    meta = pt.new_meta(x.device)
+
+    def sequence():
+        ctx.compute_meta_async_ptr(x.data_ptr(), D.F32, n, D.UINT8, meta.data_ptr())
+        ctx.quantize_meta_async_ptr(x.data_ptr(), D.F32, q.data_ptr(), D.UINT8, n, RoundMode.NEAREST, meta.data_ptr())
+        ctx.dequantize_meta_async_ptr(q.data_ptr(), D.UINT8, acc.data_ptr(), D.F32, n, ReduceOp.ADD, meta.data_ptr())
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ctx.set_stream(side.cuda_stream)
+        x.uniform_(-1, 1)
+        sequence()                                   # warm-up outside the capture: per-device scratch gets allocated here
+    side.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        sequence()
+    launches = ctx.kernel_launches
+    total = torch.zeros(n, device="cuda", dtype=torch.float64)
+    acc.zero_()
+    for i in range(5):
+        x.uniform_(-(i + 1), i + 1, generator=torch.Generator(device="cuda").manual_seed(i))
+        graph.replay()
+        torch.cuda.synchronize()
+        s, z = pt.meta_to_host(meta)
+        assert (s, z) == pt.compute_quant_params(x, dtype=torch.quint8)       # same parameters as the host-synchronous path
+        assert torch.equal(q, pt.quantize(x, scale=s, zero_point=z, dtype=torch.uint8))
+        total += pt.dequantize(q, scale=s, zero_point=z, dtype=torch.float32).double()
+    assert ctx.kernel_launches == launches           # replays issue no new launches through the library
+    assert torch.allclose(acc.double(), total, atol=1e-4)
