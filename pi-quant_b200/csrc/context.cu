@@ -6,7 +6,8 @@
 //   * quantization-parameter arithmetic     reference src/piquant.cpp:213-259, :371-381
 //   * panic()                               reference src/piquant.cpp:88-98
 // The thread pool, per-thread partitioner and CPUID kernel selection have no counterpart: the
-// "threads" are a persistent grid sized to the SM count and the only ISA is sm_100a.
+// "threads" are CTAs dealt tile by tile by the GPU's own scheduler, the "join" is stream order, and
+// the only ISA is sm_100a.
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -22,9 +23,9 @@
 #include "../../include/piquant_cuda.h"
 #include "pq_kernels.h"
 
-static_assert(pq::DT_F32 == PIQUANT_DTYPE_F32 && pq::DT_BF16 == PIQUANT_DTYPE_BF16 && pq::DT_U2 == PIQUANT_DTYPE_UINT2 &&
-              pq::DT_U4 == PIQUANT_DTYPE_UINT4 && pq::DT_U8 == PIQUANT_DTYPE_UINT8, "dtype enum ABI");
-static_assert(pq::OP_SET == PIQUANT_REDUCE_OP_SET && pq::OP_ADD == PIQUANT_REDUCE_OP_ADD, "reduce-op enum ABI");
+static_assert(int(pq::DT_F32) == int(PIQUANT_DTYPE_F32) && int(pq::DT_BF16) == int(PIQUANT_DTYPE_BF16) && int(pq::DT_U2) == int(PIQUANT_DTYPE_UINT2) &&
+              int(pq::DT_U4) == int(PIQUANT_DTYPE_UINT4) && int(pq::DT_U8) == int(PIQUANT_DTYPE_UINT8), "dtype enum ABI");
+static_assert(int(pq::OP_SET) == int(PIQUANT_REDUCE_OP_SET) && int(pq::OP_ADD) == int(PIQUANT_REDUCE_OP_ADD), "reduce-op enum ABI");
 
 namespace pq {
 

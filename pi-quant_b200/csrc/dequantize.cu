@@ -109,6 +109,7 @@ static void launch_cell(const void* in, void* out, int64_t numel, const QuantPar
     a.numel = numel;
     a.P = P;
     a.dP = dP;
+    a.sched = nullptr;           // the direct kernels are scheduled by the hardware, one tile per CTA
     a.head_bytes = 0;
     a.n_items = 0;
     set_dequant_fast(a, BITS, OUT_DT);

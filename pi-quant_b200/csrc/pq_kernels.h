@@ -14,7 +14,7 @@ constexpr int kThreads = 256;   // threads per CTA of every streaming kernel
 
 struct LaunchCfg {
     cudaStream_t stream;
-    int          sm_count;   // 148 on B200; grids are sized in multiples of it
+    int          sm_count;   // 148 on B200; sizes the resident grids of the persistent (TMA ring, byte-granular) kernels
     int          variant;    // 0 = auto, 1 = direct LDG/STG kernels, 2 = TMA (cp.async.bulk) ring kernels
     unsigned long long* sched;   // {next tile, finished CTAs}: work counter of the persistent TMA kernels, zero between launches
 };

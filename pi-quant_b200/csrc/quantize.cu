@@ -177,6 +177,7 @@ int launch_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t nu
     a.numel = numel;
     a.P = P;
     a.dP = dP;
+    a.sched = nullptr;           // the direct kernels are scheduled by the hardware, one tile per CTA
     const int64_t full_bytes = numel / per;                      // bytes whose elements all exist
     int64_t head = static_cast<int64_t>((16 - (reinterpret_cast<uintptr_t>(out) & 15u)) & 15u);
     if (head > full_bytes) head = full_bytes;
