@@ -124,6 +124,8 @@ struct DeviceState {
     void*         d_in[kRing]{};
     void*         d_out[kRing]{};
     size_t        in_cap = 0, out_cap = 0;
+    float*        h_parts = nullptr;          // host-tensor min/max: one result slot per pipeline chunk
+    size_t        h_parts_cap = 0;
     bool          pipe_ready = false;
 };
 
@@ -163,6 +165,7 @@ struct Context {
             cudaFree(d.d_meta);
             cudaFree(d.d_sched);
             cudaFreeHost(d.h_meta);
+            if (d.h_parts) cudaFreeHost(d.h_parts);
             if (d.pipe_ready) {
                 for (int i = 0; i < kRing; ++i) {
                     cudaFree(d.d_in[i]);
@@ -333,7 +336,8 @@ int launch_job(const Job& j, const void* in, void* out, size_t n, const LaunchCf
 void run_staged(Context& c, DeviceState& d, const Job& j, bool in_host, bool out_host) {
     const size_t chunk = kChunkElems;     // multiple of every pack width and of 128 elements
     const bool out_rmw = j.op == OP_ADD && j.cmd != Cmd::Quant;
-    c.ensure_pipe(d, in_host ? job_in_bytes(j, chunk) : 0, out_host ? job_out_bytes(j, chunk) : 0);
+    const size_t per_slot = j.numel < chunk ? j.numel : chunk;          // small tensors get small staging buffers
+    c.ensure_pipe(d, in_host ? job_in_bytes(j, per_slot) : 0, out_host ? job_out_bytes(j, per_slot) : 0);
     // everything already queued on the context stream (producers of device-side operands) goes first
     cudaEvent_t& gate = d.ev_h2d[0];
     PQ_CUDA_CHECK(cudaEventRecord(gate, c.stream));
@@ -453,11 +457,15 @@ void compute_params(Context& c, const void* x, int dt_in, size_t n, int dt_quant
             // host tensor: chunks through the ring, partial results folded on the host
             const size_t chunk = kChunkElems * 2;
             const size_t isz = static_cast<size_t>(dtype_bits(dt_in) / 8);
-            c.ensure_pipe(d, chunk * isz, 0);
+            c.ensure_pipe(d, (n < chunk ? n : chunk) * isz, 0);
             const LaunchCfg cfg = make_cfg(c, d, d.s_run);
-            float* h_parts = nullptr;
             const size_t n_chunks = (n + chunk - 1) / chunk;
-            PQ_CUDA_CHECK(cudaHostAlloc(&h_parts, n_chunks * 4 * sizeof(float), cudaHostAllocMapped));
+            if (n_chunks > d.h_parts_cap) {                   // per-chunk {min,max,-min,max}, pinned + mapped, kept for the next call
+                if (d.h_parts) PQ_CUDA_CHECK(cudaFreeHost(d.h_parts));
+                d.h_parts_cap = n_chunks < 256 ? 256 : n_chunks;
+                PQ_CUDA_CHECK(cudaHostAlloc(&d.h_parts, d.h_parts_cap * 4 * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
+            }
+            float* h_parts = d.h_parts;
             float* h_parts_dev = nullptr;
             PQ_CUDA_CHECK(cudaHostGetDevicePointer(&h_parts_dev, h_parts, 0));
             size_t i = 0;
@@ -476,7 +484,6 @@ void compute_params(Context& c, const void* x, int dt_in, size_t n, int dt_quant
                 mn = std::fmin(mn, h_parts[4 * q]);
                 mx = std::fmax(mx, h_parts[4 * q + 1]);
             }
-            PQ_CUDA_CHECK(cudaFreeHost(h_parts));
             if (c.comm) {
                 const float r[4] = {mn, mx, -mn, mx};
                 PQ_CUDA_CHECK(cudaMemcpyAsync(d.d_result, r, sizeof(r), cudaMemcpyHostToDevice, c.stream));

@@ -12,6 +12,8 @@
 //   store  : after a consumer barrier one elected thread bulk-stores the tile (UBLKCP.G.S); when the
 //            PREVIOUS tile's store has finished reading shared memory its stage is released (`empty`).
 // For ADD `out` crosses HBM exactly once in each direction and never touches a register file twice.
+#include <atomic>
+
 #include "dequantize_common.cuh"
 #include "pq_tma.cuh"
 
@@ -162,12 +164,12 @@ void launch_tma_cell(DequantArgs a, const LaunchCfg& cfg) {
     using S = DqShape<BITS, OUT_DT>;
     auto fn = dequant_tma_kernel<BITS, OUT_DT, OP>;
     set_dequant_fast(a, BITS, OUT_DT);
-    static unsigned long long configured = 0;           // one bit per device: the attribute is per device
-    int dev = 0;
+    static std::atomic<unsigned long long> configured{0};   // one bit per device (the attribute is per device); contexts on
+    int dev = 0;                                             // different threads may race here: setting it twice is harmless
     PQ_CUDA_CHECK(cudaGetDevice(&dev));
-    if (!(configured >> (dev & 63) & 1ull)) {
+    if (!(configured.load(std::memory_order_relaxed) >> (dev & 63) & 1ull)) {
         PQ_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
-        configured |= 1ull << (dev & 63);
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
     }
     int per_sm = 0;
     PQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kDqThreads, S::SMEM));

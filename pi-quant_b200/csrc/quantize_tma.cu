@@ -11,6 +11,8 @@
 //                                  packed tile (UBLKCP.G.S), double-buffered with bulk-group waits.
 // No thread computes a global address per element and the loads in flight are bounded by shared
 // memory (S x 16 KiB per CTA, several CTAs per SM), not by registers.
+#include <atomic>
+
 #include "pq_tma.cuh"
 #include "quantize_common.cuh"
 
@@ -148,12 +150,12 @@ template <int IN_DT, int BITS, int STEP>
 void launch_tma_cell(const QuantArgs& a, const LaunchCfg& cfg) {
     using S = TmaShape<IN_DT, BITS>;
     auto fn = quant_tma_kernel<IN_DT, BITS, STEP>;
-    static unsigned long long configured = 0;           // one bit per device: the attribute is per device
-    int dev = 0;
+    static std::atomic<unsigned long long> configured{0};   // one bit per device (the attribute is per device); contexts on
+    int dev = 0;                                             // different threads may race here: setting it twice is harmless
     PQ_CUDA_CHECK(cudaGetDevice(&dev));
-    if (!(configured >> (dev & 63) & 1ull)) {
+    if (!(configured.load(std::memory_order_relaxed) >> (dev & 63) & 1ull)) {
         PQ_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
-        configured |= 1ull << (dev & 63);
+        configured.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
     }
     int per_sm = 0;
     PQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTmaThreads, S::SMEM));
