@@ -357,3 +357,54 @@ def test_device_params_kernel_matches_host_arithmetic(gpu0):
             s, z = pt.meta_to_host(meta)
             ws, wz = port.compute_quant_params(x, dq)
             assert np.float32(s).tobytes() == np.float32(ws).tobytes() and z == wz, (x[:4], dq, (s, z), (ws, wz))
+
+
+# ------------------------------------------------------------------------------------------------
+# fuzz: random cell / size / alignment / zero point and DEGENERATE scales (0, inf, NaN, negative, denormal)
+# ------------------------------------------------------------------------------------------------
+
+_SCALES = (1.0, 0.5, 2.0 / 255, 1e-3, 123.456, 1e-30, 1e30, 1e-45, 3.4e38, 0.0, -0.0, float("inf"), -1.0, -0.037, float("nan"))
+
+
+def test_fuzz_quantize_against_oracle(gpu):
+    rng = np.random.default_rng(0xF022)
+    for it in range(150):
+        dt_in, dt_out = QUANT_CELLS[int(rng.integers(len(QUANT_CELLS)))]
+        n = int(rng.choice([1, 2, 3, 5, 31, 257, 1000, 4099, 65_537, 300_001]))
+        scale = float(np.float32(_SCALES[int(rng.integers(len(_SCALES)))]))
+        zp = int(rng.choice([0, 1, 3, 8, 128, 255, -5, 1000, -1000, 2**31 - 1, -2**31, 2**33 + 7]))
+        mode = int(rng.integers(2))
+        xi = float(np.float32(rng.uniform(0, 0.999)))
+        x = make_input(rng, n, dt_in, -float(rng.choice([1, 3, 300, 1e6])), float(rng.choice([1, 3, 300, 1e6])))
+        if n > 40 and rng.random() < 0.5:
+            sp = special_values(1.0 if not np.isfinite(scale) or scale == 0 else abs(scale))
+            sp = sp if dt_in == F32 else f32_to_bf16_bits(sp)
+            x[3:3 + sp.size] = sp[: max(0, min(sp.size, n - 3))]
+        isz = 4 if dt_in == F32 else 2
+        in_off, out_off = int(rng.choice([0, isz, 16, 32 + isz])), int(rng.choice([0, 1, 5, 16]))
+        with np.errstate(all="ignore"):
+            want = port.quantize(x, dt_out, scale, zp, mode, xi=xi, semantics=SEM_BODY)
+        got = gpu.quantize(x, dt_out, scale, zp, mode, xi=xi, in_off=in_off, out_off=out_off)
+        assert np.array_equal(got, want), f"it={it} cell=({dt_in},{dt_out}) n={n} scale={scale} zp={zp} mode={mode} xi={xi} offs=({in_off},{out_off})"
+
+
+def test_fuzz_dequantize_against_oracle(gpu):
+    rng = np.random.default_rng(0xF023)
+    for it in range(150):
+        dt_in, dt_out, op = DEQUANT_CELLS[int(rng.integers(len(DEQUANT_CELLS)))]
+        n = int(rng.choice([1, 2, 3, 5, 31, 257, 1000, 4099, 65_537, 300_001]))
+        scale = float(np.float32(_SCALES[int(rng.integers(len(_SCALES)))]))
+        zp = int(rng.choice([0, 1, 3, 8, 128, 255, -5, 1000, 2**22, 2**22 + 1, -2**22 - 1, 2**31 - 1, -2**31, 2**33 + 7]))
+        q = rng.integers(0, 256, packed_bytes(dt_in, n)).astype(np.uint8)
+        prev = rng.uniform(-100, 100, n).astype(np.float32)
+        prev = prev if dt_out == F32 else f32_to_bf16_bits(prev)
+        osz = 4 if dt_out == F32 else 2
+        in_off, out_off = int(rng.choice([0, 1, 4, 16])), int(rng.choice([0, osz, 16, 32 + osz]))
+        with np.errstate(all="ignore"):
+            want = port.dequantize(q, dt_in, n, dt_out, scale, zp, op, out=prev.copy(), semantics=SEM_BODY)
+        got = gpu.dequantize(q, dt_in, n, dt_out, scale, zp, op, prev=prev, in_off=in_off, out_off=out_off)
+        ok = np.array_equal(got.view(np.uint32), want.view(np.uint32)) if dt_out == F32 else bf16_equal(got, want)
+        if dt_out == F32 and not ok:            # f32 NaN payloads: any NaN matches any NaN
+            gn, wn = np.isnan(got), np.isnan(want)
+            ok = np.array_equal(gn, wn) and np.array_equal(got[~gn].view(np.uint32), want[~wn].view(np.uint32))
+        assert ok, f"it={it} cell=({dt_in},{dt_out},{op}) n={n} scale={scale} zp={zp} offs=({in_off},{out_off})"
