@@ -207,6 +207,17 @@ def run_ours(args) -> None:
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     barrier()
     e2e_value = world * n / e2e_s / 1e9
+    # what the link itself can do: a plain pinned -> device copy of the same 4 GB (and device -> pinned of the 1 GB)
+    t0 = time.perf_counter()
+    for _ in range(2):
+        x.copy_(xh, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_gbps = 2 * 4 * n / (time.perf_counter() - t0) / 1e9
+    t0 = time.perf_counter()
+    for _ in range(2):
+        qh.copy_(q, non_blocking=True)
+    torch.cuda.synchronize()
+    d2h_gbps = 2 * n / (time.perf_counter() - t0) / 1e9
     e2e_ok = bool(torch.equal(qh[: 1 << 24], q[: 1 << 24].cpu()))
 
     # ---- the other BASELINE configs, kernel-only, this rank's GPU -------------------------------
@@ -250,6 +261,8 @@ def run_ours(args) -> None:
                      "kernel": "quantize f32->u8 (one launch per step)", "of_nominal_8000": round(achieved / 8000.0, 4)},
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": 4 * n * world, "d2h_bytes_per_step": n * world,
                 "steps": e2e_steps, "path": "piquant_quantize(host pinned in, host pinned out): chunked H2D | kernel | D2H pipeline",
+                "bound": "pcie", "h2d_GBps_achieved_per_gpu": round(4 * n / e2e_s / 1e9, 1), "h2d_GBps_plain_memcpy": round(h2d_gbps, 1),
+                "d2h_GBps_plain_memcpy": round(d2h_gbps, 1), "frac_of_link": round((4 * n / e2e_s / 1e9) / h2d_gbps, 4),
                 "output_matches_device_path": e2e_ok},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(mark0, mark1, window),
