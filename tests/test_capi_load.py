@@ -150,3 +150,12 @@ def test_cxx_facade_compiles_and_links_against_the_library(lib, tmp_path):
                     f"-Wl,-rpath,{LIB.parent}", "-o", str(exe)], check=True, capture_output=True, text=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_headers_are_valid_c99(tmp_path):
+    """piquant.h is the reference's C99 API (reference include/piquant.h:1-3): both public headers must compile as C."""
+    src = tmp_path / "c99.c"
+    src.write_text('#include <piquant.h>\n#include <piquant_cuda.h>\n'
+                   'int main(void) { piquant_cuda_meta_t m; m.error = 0; return (int)sizeof(m) == 64 ? m.error : 1; }\n')
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", f"-I{ROOT / 'include'}", "-c", str(src), "-o", str(tmp_path / "c99.o")],
+                   check=True, capture_output=True, text=True)
