@@ -309,6 +309,8 @@ def run_extra(torch, ctx, D, RoundMode, ReduceOp, x, q, scale, zp, dev) -> dict:
             i = state["i"] = (state["i"] + 1) % 3
             ctx.quantize_ptr(xs[i].data_ptr(), D.F32, qs[i].data_ptr(), D.UINT8, n1, scale, zp, RoundMode.NEAREST)
         rec("C1_f32_u8_nearest_27.264M", n1, 5, time_launches(torch, c1, 60, 6), "3 rotating buffer pairs, back-to-back launches")
+        rec("C1_f32_u8_nearest_27.264M_hot_L2", n1, 5, time_launches(torch, lambda: ctx.quantize_ptr(xs[0].data_ptr(), D.F32, qs[0].data_ptr(), D.UINT8, n1, scale, zp, RoundMode.NEAREST), 60, 6),
+            "the SAME buffer pair every launch: 136 MB of traffic against a 126 MB L2, partly L2-resident -- not an HBM number")
         # the only figure the reference publishes for this path: a README bar chart, ~1.7 s per 1000 runs at this size on an
         # EPYC 9654 (~16 Gelem/s, read off the chart, +-5 %).  Other hardware, so context, not vs_baseline.
         out["C1_f32_u8_nearest_27.264M"]["reference_readme_chart_Gelem/s"] = 16.0
