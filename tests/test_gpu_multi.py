@@ -58,6 +58,13 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
             per = 8 // orc.BITS[odt]
             res[name] = (got_torch == want, got_native == want, got_local == want_local,
                          bool(np.array_equal(raw, whole[b // per: b // per + nbytes])))
+        # device-resident parameters of a SHARDED tensor: with a communicator the parameter block holds whole-tensor values
+        pd.init_native_comm(ctx)
+        meta = pt.new_meta(shard.device)
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx.compute_meta_async_ptr(shard.data_ptr(), piquant.DataType.F32, shard.numel(), piquant.DataType.UINT8, meta.data_ptr())
+        res["sharded_meta"] = (pt.meta_to_host(meta) == orc.compute_quant_params(x, orc.UINT8),)
+        pd.destroy_native_comm(ctx)
         # quantized ring all-reduce: every rank ends with bit-identical values, close to the exact sum
         for tdt, qdt, transport in ((torch.float32, torch.quint8, "nccl"), (torch.bfloat16, torch.quint8, "nccl"), (torch.float32, torch.quint4x2, "nccl"),
                                     (torch.float32, torch.quint8, "p2p"), (torch.bfloat16, torch.quint4x2, "p2p"), (torch.float32, torch.quint8, "p2p")):

@@ -309,3 +309,25 @@ def test_device_parameter_path_is_cuda_graph_capturable(pt):
         total += pt.dequantize(q, scale=s, zero_point=z, dtype=torch.float32).double()
     assert ctx.kernel_launches == launches           # replays issue no new launches through the library
     assert torch.allclose(acc.double(), total, atol=1e-4)
+
+
+def test_quantize_auto_with_host_tensors_and_zero_copy_mode(pt, monkeypatch):
+    """quantize_auto on CPU tensors falls back to the two synchronous calls; PIQUANT_CUDA_HOST_MODE=zerocopy makes
+    kernels read pinned host memory in place over PCIe (measured slower than the copy-engine pipeline, kept as an option)."""
+    import piquant
+
+    n = 1_234_567
+    x = torch.empty(n).uniform_(-2, 3, generator=torch.Generator().manual_seed(9))
+    want_s, want_z = pt.compute_quant_params(x.cuda(), dtype=torch.quint8)
+    want_q = pt.quantize(x.cuda(), scale=want_s, zero_point=want_z, dtype=torch.uint8).cpu()
+    q, s, z = pt.quantize_auto(x, dtype=torch.uint8)
+    assert (s, z) == (want_s, want_z) and torch.equal(q, want_q) and q.device.type == "cpu"
+    monkeypatch.setenv("PIQUANT_CUDA_HOST_MODE", "zerocopy")
+    ctx = piquant.Context()
+    xp = x.pin_memory()
+    before = ctx.kernel_launches
+    assert pt.compute_quant_params(xp, dtype=torch.quint8, ctx=ctx) == (want_s, want_z)
+    qp = torch.empty(n, dtype=torch.uint8).pin_memory()
+    pt.quantize(xp, scale=want_s, zero_point=want_z, dtype=torch.uint8, ctx=ctx, out=qp)
+    assert torch.equal(qp, want_q)
+    assert ctx.kernel_launches - before == 2          # one kernel each, no staging chunks
