@@ -295,17 +295,27 @@ __device__ __forceinline__ int32_t quant_spec(float x, const QuantParams& P, flo
         witness = a;
         return __float2int_rz(a);
     } else {
-        // std::round(p) (STEP_ROUND64) or trunc(p) +- [xi < frac] (STEP_STOCH), in integer form: for |p| < 2^30
-        // t = trunc(p) is exact, frac = |p - t| is exact, and t +- 1 equals the reference's float sum tr + adj
-        // (for |t| >= 2^24 the fraction is 0 and nothing is added)
-        const int32_t t = __float2int_rz(p);
-        const float dec = fabsf(__fsub_rn(p, static_cast<float>(t)));
+        // std::round(p) (STEP_ROUND64) or trunc(p) +- [xi < frac] (STEP_STOCH) on the magnitude, for |p| < 2^22:
+        //   trunc(m)  = (m + 2^23, rounded toward zero) - 2^23      two FMA-pipe adds, exact, no conversion
+        //   frac      = m - trunc(m)                                 exact; equals the reference's |r - trunc(r)|
+        //   mag       = trunc(m) + [away]                            a predicated FADD, exact
+        //   result    = int(copysign(mag, p))                        == the reference's trunc(r) + (r < 0 ? -adj : adj)
+        // Only ONE conversion (XU pipe) and three ALU-pipe instructions (compare, copysign, + zp) per element remain:
+        // the first version (F2I + I2F + integer sign logic) ran the bf16 cells at 90 % ALU-pipe utilisation.
+        const float m = fabsf(p);
+        const float trm = __fadd_rn(__fadd_rz(m, 8388608.0f), -8388608.0f);
+        const float dec = __fsub_rn(m, trm);
         const bool away = (STEP == STEP_ROUND64) ? (dec >= 0.5f) : (P.xi < dec);
-        const int32_t sgn = (static_cast<int32_t>(__float_as_uint(p)) >> 31) | 1;
+        float mag = trm;
+        if (away) mag = __fadd_rn(trm, 1.0f);
         witness = p;
-        return t + (away ? sgn : 0);
+        return __float2int_rz(copysignf(mag, p));
     }
 }
+
+// largest |witness| for which quant_spec<STEP> is exact
+template <int STEP>
+__device__ __forceinline__ constexpr float quant_spec_limit() { return STEP == STEP_BODY ? 1073741824.0f : 4194304.0f; }
 
 // Quantize the NE elements held in w[] (f32: one per word, bf16: two per word) and pack them,
 // element 0 in the lowest bits, into o[NE*BITS/32 words] (at least one word; unused high bits are 0).
@@ -325,7 +335,7 @@ __device__ __forceinline__ void quant_group(const uint32_t (&w)[NW], const Quant
 #pragma unroll
     for (int e = 0; e < NE; e += 2) m = max3_abs_nan(m, wit[e], wit[e + 1]);
     const bool spec_ok = (STEP == STEP_BODY) ? (P.spec_ok32 != 0) : (P.bigzp == 0);
-    if (spec_ok && m < 1073741824.0f) {
+    if (spec_ok && m < quant_spec_limit<STEP>()) {
 #pragma unroll
         for (int j = 0; j < OW; ++j) {
             uint32_t d = 0;

@@ -53,6 +53,58 @@ __device__ __forceinline__ uint32_t requant_elem(float x, uint32_t prev_bits, co
     }
 }
 
+// One 32-byte vector (8 f32 / 16 bf16 elements), speculative form: the quantize half is quant_spec (exact while every
+// |x/scale| < 2^22 and |zp| <= 2^29, checked with one FMNMX3 witness per vector), the clamp is two integer min/max, and
+// for bf16 the first rounding of the reference's bf16 arithmetic (float(q - zp) -> bf16) is skipped when 0 <= zp <= 255,
+// where |q - zp| <= 255 is exactly representable.  Anything else redoes the vector with the exact per-element steps.
+template <int DT, int STEP, int OP>
+__device__ __forceinline__ void requant_vector(const uint32_t (&w)[8], const uint32_t (&p)[8], const RequantArgs& a, int32_t qmax,
+                                               uint32_t (&o)[8]) {
+    constexpr int NE = DT == DT_F32 ? 8 : 16;
+    int32_t t[NE];
+    float wit[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) t[e] = quant_spec<STEP>(item_elem<DT, 8>(w, e), a.P, wit[e]);
+    float m = 0.0f;
+#pragma unroll
+    for (int e = 0; e < NE; e += 2) m = max3_abs_nan(m, wit[e], wit[e + 1]);
+    const bool small_zp = a.P.zp64 >= 0 && a.P.zp64 <= 255;
+    if (!a.P.bigzp && m < quant_spec_limit<STEP>() && (DT == DT_F32 || small_zp)) {
+        float v[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const int32_t q = min(max(t[e] + a.P.zp32, 0), qmax);
+            const float d = static_cast<float>(q - a.P.zp32);
+            if constexpr (DT == DT_F32) {
+                v[e] = OP == OP_ADD ? __fmaf_rn(d, a.P.scale, __uint_as_float(p[e])) : __fmul_rn(d, a.P.scale);
+            } else {
+                v[e] = __fmul_rn(d, a.scale_bf16);                  // d is already a bf16 value here
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if constexpr (DT == DT_F32) {
+                o[k] = __float_as_uint(v[k]);
+            } else {
+                uint32_t r = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+                if constexpr (OP == OP_ADD) r = pack_bf16x2(__fadd_rn(bf16_lo(p[k]), bf16_lo(r)), __fadd_rn(bf16_hi(p[k]), bf16_hi(r)));
+                o[k] = r;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if constexpr (DT == DT_F32) {
+                o[k] = requant_elem<DT, STEP, OP>(__uint_as_float(w[k]), p[k], a, qmax);
+            } else {
+                const uint32_t lo = requant_elem<DT, STEP, OP>(bf16_lo(w[k]), p[k] & 0xffffu, a, qmax);
+                const uint32_t hi = requant_elem<DT, STEP, OP>(bf16_hi(w[k]), p[k] >> 16, a, qmax);
+                o[k] = lo | (hi << 16);
+            }
+        }
+    }
+}
+
 template <int DT, int STEP, int OP>
 __device__ __forceinline__ void requant_scalar(const RequantArgs& a, int64_t e, int32_t qmax) {
     if constexpr (DT == DT_F32) {
@@ -83,7 +135,7 @@ __global__ void __launch_bounds__(kThreads) requant_stream_kernel(const RequantA
     if (const int64_t tile = blockIdx.x; tile < n_tiles) {      // one tile per CTA, hardware-scheduled (see quantize.cu)
         const int64_t first = tile * TILE + threadIdx.x;
         uint32_t w[U][8];
-        uint32_t p[U][OP == OP_ADD ? 8 : 1];
+        uint32_t p[U][8];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t item = first + static_cast<int64_t>(u) * kThreads;
@@ -97,17 +149,7 @@ __global__ void __launch_bounds__(kThreads) requant_stream_kernel(const RequantA
             const int64_t item = first + static_cast<int64_t>(u) * kThreads;
             if (item < a.n_items) {
                 uint32_t o[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t pw = OP == OP_ADD ? p[u][OP == OP_ADD ? k : 0] : 0u;
-                    if constexpr (DT == DT_F32) {
-                        o[k] = requant_elem<DT, STEP, OP>(__uint_as_float(w[u][k]), pw, a, qmax);
-                    } else {
-                        const uint32_t lo = requant_elem<DT, STEP, OP>(bf16_lo(w[u][k]), pw & 0xffffu, a, qmax);
-                        const uint32_t hi = requant_elem<DT, STEP, OP>(bf16_hi(w[u][k]), pw >> 16, a, qmax);
-                        o[k] = lo | (hi << 16);
-                    }
-                }
+                requant_vector<DT, STEP, OP>(w[u], p[u], a, qmax, o);
                 stg_stream(out + item * 32, o);
             }
         }
