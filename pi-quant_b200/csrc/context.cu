@@ -282,8 +282,12 @@ PtrInfo classify(const void* p) {
         return {Where::HostPageable, -1};
     }
     switch (attr.type) {
-        case cudaMemoryTypeDevice:
-        case cudaMemoryTypeManaged: return {Where::Device, attr.device};
+        case cudaMemoryTypeDevice: return {Where::Device, attr.device};
+        case cudaMemoryTypeManaged: {   // managed memory migrates on demand: run where the caller is if it has no home device
+            int dev = attr.device;
+            if (dev < 0) PQ_CUDA_CHECK(cudaGetDevice(&dev));
+            return {Where::Device, dev};
+        }
         case cudaMemoryTypeHost: return {Where::HostPinned, -1};
         default: return {Where::HostPageable, -1};
     }

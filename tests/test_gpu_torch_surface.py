@@ -331,3 +331,36 @@ def test_quantize_auto_with_host_tensors_and_zero_copy_mode(pt, monkeypatch):
     pt.quantize(xp, scale=want_s, zero_point=want_z, dtype=torch.uint8, ctx=ctx, out=qp)
     assert torch.equal(qp, want_q)
     assert ctx.kernel_launches - before == 2          # one kernel each, no staging chunks
+
+
+def test_managed_memory_pointers(pt):
+    """cudaMallocManaged buffers are device-accessible: the kernels run on them in place."""
+    try:
+        from cuda import cudart as rt
+    except Exception:
+        pytest.skip("cuda-python not importable")
+    import ctypes
+
+    import piquant
+    from piquant import DataType as D, RoundMode
+
+    n = 1_000_003
+    err, px = rt.cudaMallocManaged(4 * n, rt.cudaMemAttachGlobal)
+    assert err == rt.cudaError_t.cudaSuccess
+    err, pq_ = rt.cudaMallocManaged(n, rt.cudaMemAttachGlobal)
+    assert err == rt.cudaError_t.cudaSuccess
+    try:
+        x = np.ctypeslib.as_array((ctypes.c_float * n).from_address(int(px)))
+        x[:] = np.random.default_rng(5).uniform(-1, 1, n).astype(np.float32)
+        ctx = piquant.Context()
+        s, z = ctx.compute_quant_params_ptr_float32(int(px), D.UINT8, n)
+        ctx.quantize_ptr(int(px), D.F32, int(pq_), D.UINT8, n, s, z, RoundMode.NEAREST)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        q = np.ctypeslib.as_array((ctypes.c_uint8 * n).from_address(int(pq_))).copy()
+        from oracle import port
+        assert (s, z) == port.compute_quant_params(x, port.UINT8)
+        assert np.array_equal(q, port.quantize(np.ascontiguousarray(x), port.UINT8, s, z))
+    finally:
+        rt.cudaFree(px)
+        rt.cudaFree(pq_)
