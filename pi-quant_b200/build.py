@@ -50,15 +50,17 @@ def stale() -> bool:
     return any(p.stat().st_mtime > t for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not stale():
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: Path = OUT) -> Path:
+    """`defines` / `out` build an experimental variant next to the product library (A/B runs on the GPU box)."""
+    if not force and not defines and not stale():
         return OUT
-    OBJ.mkdir(exist_ok=True)
+    obj_dir = OBJ if not defines else HERE / ("build_" + "_".join(d.split("=")[0] for d in defines))
+    obj_dir.mkdir(exist_ok=True)
     cc = nvcc()
 
     def compile_one(src: str) -> Path:
-        obj = OBJ / (src + ".o")
-        cmd = [cc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        obj = obj_dir / (src + ".o")
+        cmd = [cc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
@@ -71,20 +73,22 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    tmp = OUT.with_suffix(".so.tmp")
+    tmp = out.with_suffix(".so.tmp")
     link = [cc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
             "-o", str(tmp), *map(str, objs), "-ldl", "-lpthread", "-lrt"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
-    tmp.replace(OUT)
-    return OUT
+    tmp.replace(out)
+    return out
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--define", action="append", default=[], help="extra -D for an experimental variant, e.g. PQ_BF16_FHADD")
+    ap.add_argument("--out", default=str(OUT), help="output path of the variant (default: the product library)")
     a = ap.parse_args()
-    print(build(a.force, a.verbose))
+    print(build(a.force, a.verbose, tuple(a.define), Path(a.out)))

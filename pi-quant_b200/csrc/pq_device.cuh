@@ -195,6 +195,8 @@ __device__ __forceinline__ uint16_t f32_to_bf16_bits(float x) { return static_ca
 template <int IN_DT, int NW>
 __device__ __forceinline__ float item_elem(const uint32_t (&w)[NW], int e) {
     if constexpr (IN_DT == DT_F32) return __uint_as_float(w[e]);
+    // (Widening a half with the sm_100a mixed-precision add -- FHADD.BF16 Rd, Rw.H1, -RZ, no shift / mask -- was measured
+    // too: 1-3 % slower on every bf16 cell, profiles/r1_cellbench_1e9_fhadd_variant.txt.)
     else return (e & 1) ? bf16_hi(w[e >> 1]) : bf16_lo(w[e >> 1]);
 }
 
@@ -285,37 +287,72 @@ __device__ __forceinline__ float max3_abs_nan(float a, float b, float c) {
 }
 
 // Speculative step: the integer BEFORE zero point and clamp, plus the float whose magnitude decides
-// whether the speculation was valid.
+// whether the speculation was valid (quant_spec_limit).
+//
+// STEP_ROUND64, std::round(p) == sign(p) * floor(|p| + 0.5):
+//     z = p + copysign(0.5, p) rounded TOWARD ZERO, t = trunc(z).  floor(RZ(y)) == floor(y) for every y >= 0 (an integer
+//     k <= y is representable, so k <= RZ(y) <= y), hence exact for every |p| < 2^31 -- unlike the SIMD body's
+//     round-to-nearest add, which is what makes pred(0.5) round up there.  FMUL, LOP3, FADD.RZ, F2I.
+// STEP_STOCH, trunc(r) + sign(r) * [xi < |r - trunc(r)|] == sign(r) * ceil(|r| - xi) for 0 <= xi < 1:
+//     with m = |r|: frac(m) > xi  <=>  m - xi > trunc(m)  <=>  ceil(m - xi) == trunc(m) + 1, and frac(m) <= xi gives
+//     trunc(m) - 1 < m - xi <= trunc(m).  The subtraction rounds TOWARD +INF and ceil(RP(y)) == ceil(y) by the same
+//     argument, so one FADD.RP and one F2I.CEIL replace the reference's trunc / subtract / compare / add chain; the
+//     sign goes back on with an integer multiply by +-1 that ptxas fuses with the zero-point add (IMAD, FMA pipe).
+//     FMUL, FADD.RP, F2I.CEIL, SHF, LOP3, IMAD: 6 instructions where the literal formula took 11.
+// Both were checked against the literal formulas on 4e7 adversarial values (ties, neighbours of ties, every binade,
+// raw bit patterns) before they went in; tests/test_gpu_parity.py pins them on the GPU.
 template <int STEP>
 __device__ __forceinline__ int32_t quant_spec(float x, const QuantParams& P, float& witness) {
     const float p = __fmul_rn(x, P.inv_scale);
+    const float h = __uint_as_float(0x3f000000u | (__float_as_uint(p) & 0x80000000u));
     if constexpr (STEP == STEP_BODY) {
-        const float h = __uint_as_float(0x3f000000u | (__float_as_uint(p) & 0x80000000u));
         const float a = __fadd_rn(p, h);
         witness = a;
         return __float2int_rz(a);
-    } else {
-        // std::round(p) (STEP_ROUND64) or trunc(p) +- [xi < frac] (STEP_STOCH) on the magnitude, for |p| < 2^22:
-        //   trunc(m)  = (m + 2^23, rounded toward zero) - 2^23      two FMA-pipe adds, exact, no conversion
-        //   frac      = m - trunc(m)                                 exact; equals the reference's |r - trunc(r)|
-        //   mag       = trunc(m) + [away]                            a predicated FADD, exact
-        //   result    = int(copysign(mag, p))                        == the reference's trunc(r) + (r < 0 ? -adj : adj)
-        // Only ONE conversion (XU pipe) and three ALU-pipe instructions (compare, copysign, + zp) per element remain:
-        // the first version (F2I + I2F + integer sign logic) ran the bf16 cells at 90 % ALU-pipe utilisation.
-        const float m = fabsf(p);
-        const float trm = __fadd_rn(__fadd_rz(m, 8388608.0f), -8388608.0f);
-        const float dec = __fsub_rn(m, trm);
-        const bool away = (STEP == STEP_ROUND64) ? (dec >= 0.5f) : (P.xi < dec);
-        float mag = trm;
-        if (away) mag = __fadd_rn(trm, 1.0f);
+    } else if constexpr (STEP == STEP_ROUND64) {
         witness = p;
-        return __float2int_rz(copysignf(mag, p));
+        return __float2int_rz(__fadd_rz(p, h));
+    } else {
+        witness = p;
+        const int32_t mag = __float2int_ru(__fadd_ru(fabsf(p), -P.xi));
+        const int32_t sgn = (__float_as_int(p) >> 31) | 1;
+        return mag * sgn;
     }
 }
 
-// largest |witness| for which quant_spec<STEP> is exact
+// largest |witness| for which quant_spec<STEP> followed by a 32-bit zero-point add is exact
 template <int STEP>
-__device__ __forceinline__ constexpr float quant_spec_limit() { return STEP == STEP_BODY ? 1073741824.0f : 4194304.0f; }
+__device__ __forceinline__ constexpr float quant_spec_limit() { return 1073741824.0f; }
+
+// STEP_STOCH speculation also needs the threshold where the ceil identity holds (a context never passes anything else)
+template <int STEP>
+__device__ __forceinline__ bool quant_spec_params_ok(const QuantParams& P) {
+    if constexpr (STEP == STEP_BODY) return P.spec_ok32 != 0;
+    else if constexpr (STEP == STEP_ROUND64) return P.bigzp == 0;
+    else return P.bigzp == 0 && P.xi >= 0.0f && P.xi < 1.0f;
+}
+
+// The same two steps with the result kept as a FLOAT (requantize never needs the integer): the rounded value of
+// p = x/scale, exact for |p| < 2^22, with +0.0 for a zero result like the reference's float(q - zp).
+//   ROUND64: f = RZ(RZ(p + h) + M) - M with M = copysign(2^23, p) = h * 2^24: the add of M drops the fraction.
+//   STOCH:   f = RP(RP(|p| - xi) + 1.5*2^23) is 1.5*2^23 + ceil(|p| - xi) (the argument may be in (-1, 0]), then
+//            (f - 1.5*2^23) * sign as one exact FFMA with s = +-1.
+// No conversion instruction (XU pipe) at all.
+template <int STEP>
+__device__ __forceinline__ float requant_spec(float x, const QuantParams& P, float& witness) {
+    static_assert(STEP == STEP_ROUND64 || STEP == STEP_STOCH);
+    const float p = __fmul_rn(x, P.inv_scale);
+    witness = p;
+    if constexpr (STEP == STEP_ROUND64) {
+        const float h = __uint_as_float(0x3f000000u | (__float_as_uint(p) & 0x80000000u));
+        const float M = __fmul_rn(h, 16777216.0f);
+        return __fadd_rn(__fadd_rz(__fadd_rz(p, h), M), -M);
+    } else {
+        const float s = __uint_as_float(0x3f800000u | (__float_as_uint(p) & 0x80000000u));
+        const float f = __fadd_ru(__fadd_ru(fabsf(p), -P.xi), 12582912.0f);
+        return __fmaf_rn(f, s, __fmul_rn(s, -12582912.0f));
+    }
+}
 
 // Quantize the NE elements held in w[] (f32: one per word, bf16: two per word) and pack them,
 // element 0 in the lowest bits, into o[NE*BITS/32 words] (at least one word; unused high bits are 0).
@@ -334,8 +371,7 @@ __device__ __forceinline__ void quant_group(const uint32_t (&w)[NW], const Quant
     float m = 0.0f;
 #pragma unroll
     for (int e = 0; e < NE; e += 2) m = max3_abs_nan(m, wit[e], wit[e + 1]);
-    const bool spec_ok = (STEP == STEP_BODY) ? (P.spec_ok32 != 0) : (P.bigzp == 0);
-    if (spec_ok && m < quant_spec_limit<STEP>()) {
+    if (quant_spec_params_ok<STEP>(P) && m < quant_spec_limit<STEP>()) {
 #pragma unroll
         for (int j = 0; j < OW; ++j) {
             uint32_t d = 0;

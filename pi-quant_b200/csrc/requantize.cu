@@ -53,28 +53,32 @@ __device__ __forceinline__ uint32_t requant_elem(float x, uint32_t prev_bits, co
     }
 }
 
-// One 32-byte vector (8 f32 / 16 bf16 elements), speculative form: the quantize half is quant_spec (exact while every
-// |x/scale| < 2^22 and |zp| <= 2^29, checked with one FMNMX3 witness per vector), the clamp is two integer min/max, and
-// for bf16 the first rounding of the reference's bf16 arithmetic (float(q - zp) -> bf16) is skipped when 0 <= zp <= 255,
-// where |q - zp| <= 255 is exactly representable.  Anything else redoes the vector with the exact per-element steps.
+// One 32-byte vector (8 f32 / 16 bf16 elements), speculative form, entirely in floating point: requant_spec gives the
+// rounded x/scale as a float (exact while |x/scale| < 2^22, one FMNMX3 witness per vector), clamp(q + zp, 0, qmax) - zp
+// becomes clamp(r, -zp, qmax - zp) with two FMNMX, and that float IS the reference's float(q - zp): no F2I, no I2F.
+// Valid while the bounds are exact floats (|zp| <= 2^22); for bf16 the first rounding of the reference's bf16
+// arithmetic (float(q - zp) -> bf16) is the identity when 0 <= zp <= 255, where |q - zp| <= 255.  Anything else
+// (huge values, NaN, extreme zero points, a threshold outside [0, 1)) redoes the vector with the exact per-element steps.
 template <int DT, int STEP, int OP>
 __device__ __forceinline__ void requant_vector(const uint32_t (&w)[8], const uint32_t (&p)[8], const RequantArgs& a, int32_t qmax,
                                                uint32_t (&o)[8]) {
     constexpr int NE = DT == DT_F32 ? 8 : 16;
-    int32_t t[NE];
+    float r[NE];
     float wit[NE];
 #pragma unroll
-    for (int e = 0; e < NE; ++e) t[e] = quant_spec<STEP>(item_elem<DT, 8>(w, e), a.P, wit[e]);
+    for (int e = 0; e < NE; ++e) r[e] = requant_spec<STEP>(item_elem<DT, 8>(w, e), a.P, wit[e]);
     float m = 0.0f;
 #pragma unroll
     for (int e = 0; e < NE; e += 2) m = max3_abs_nan(m, wit[e], wit[e + 1]);
-    const bool small_zp = a.P.zp64 >= 0 && a.P.zp64 <= 255;
-    if (!a.P.bigzp && m < quant_spec_limit<STEP>() && (DT == DT_F32 || small_zp)) {
+    const bool zp_ok = DT == DT_F32 ? (a.P.zp64 >= -4194304 && a.P.zp64 <= 4194304) : (a.P.zp64 >= 0 && a.P.zp64 <= 255);
+    const bool xi_ok = STEP != STEP_STOCH || (a.P.xi >= 0.0f && a.P.xi < 1.0f);
+    if (zp_ok && xi_ok && m < 4194304.0f) {
+        const float lo = __fsub_rn(0.0f, static_cast<float>(a.P.zp32));     // +0.0, not -0.0, for zp == 0
+        const float hi = static_cast<float>(qmax - a.P.zp32);
         float v[NE];
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
-            const int32_t q = min(max(t[e] + a.P.zp32, 0), qmax);
-            const float d = static_cast<float>(q - a.P.zp32);
+            const float d = fminf(fmaxf(r[e], lo), hi);
             if constexpr (DT == DT_F32) {
                 v[e] = OP == OP_ADD ? __fmaf_rn(d, a.P.scale, __uint_as_float(p[e])) : __fmul_rn(d, a.P.scale);
             } else {
@@ -86,9 +90,9 @@ __device__ __forceinline__ void requant_vector(const uint32_t (&w)[8], const uin
             if constexpr (DT == DT_F32) {
                 o[k] = __float_as_uint(v[k]);
             } else {
-                uint32_t r = pack_bf16x2(v[2 * k], v[2 * k + 1]);
-                if constexpr (OP == OP_ADD) r = pack_bf16x2(__fadd_rn(bf16_lo(p[k]), bf16_lo(r)), __fadd_rn(bf16_hi(p[k]), bf16_hi(r)));
-                o[k] = r;
+                uint32_t r2 = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+                if constexpr (OP == OP_ADD) r2 = pack_bf16x2(__fadd_rn(bf16_lo(p[k]), bf16_lo(r2)), __fadd_rn(bf16_hi(p[k]), bf16_hi(r2)));
+                o[k] = r2;
             }
         }
     } else {

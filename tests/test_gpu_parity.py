@@ -250,6 +250,66 @@ def test_requantize_bit_exact(gpu0, dt_io, dt_q, op, mode):
             assert bf16_equal(got, want), f"n={n}"
 
 
+@pytest.mark.parametrize("dt_io", (F32, BF16), ids=("f32", "bf16"))
+@pytest.mark.parametrize("mode", (NEAREST, STOCHASTIC), ids=("nearest", "stochastic"))
+def test_requantize_adversarial(gpu0, dt_io, mode):
+    """The float-domain fast path of requantize.cu (magic-number rounding, clamp as two float min/max) against the
+    oracle where it could go wrong: ties and their neighbours, results that round to zero from below (+0.0, never
+    -0.0), NaN / inf / huge values inside an otherwise ordinary vector, zero points on both sides of the fast-path
+    limits, and thresholds at the ends of [0, 1)."""
+    rng = np.random.default_rng(11)
+    one_below = float(np.nextafter(np.float32(1.0), np.float32(0.0)))
+    for dt_q in (UINT2, UINT4, UINT8):
+        qmax = (1 << BITS[dt_q]) - 1
+        for scale in (1.0, 0.5, 2.0 / 255, 0.037):
+            for zp in (0, 1, qmax // 2, qmax, 255, 256, -1, -7, 1000, 2**22, 2**22 + 1, -2**22 - 1, 2**31 - 1, 2**40 + 3):
+                n = 4096 + 37
+                x = make_input(rng, n, dt_io, -3.0 * scale * (qmax + 2), 3.0 * scale * (qmax + 2))
+                sp = special_values(scale)
+                grid = (np.arange(-40, 41, dtype=np.float32) * np.float32(0.25) * np.float32(scale)).astype(np.float32)
+                near = np.concatenate([np.nextafter(grid, np.float32(np.inf)), np.nextafter(grid, np.float32(-np.inf))])
+                extra = np.concatenate([sp, grid, near]).astype(np.float32)
+                x[5:5 + extra.size] = extra if dt_io == F32 else f32_to_bf16_bits(extra)
+                prev = rng.uniform(-1, 1, n).astype(np.float32)
+                prev[::7] = -0.0
+                prev = prev if dt_io == F32 else f32_to_bf16_bits(prev)
+                for xi in ((0.4,) if mode == NEAREST else (0.0, 1e-30, 0.5, one_below)):
+                    for op in (SET, ADD):
+                        with np.errstate(all="ignore"):
+                            want = port.requantize(x, dt_q, scale, zp, mode, xi, op, out=prev.copy(), fma_add=True)
+                        got = gpu0.requantize(x, dt_q, scale, zp, mode, xi, op, prev=prev)
+                        what = f"dt_q={dt_q} scale={scale} zp={zp} xi={xi} op={op}"
+                        if dt_io == F32:
+                            bad = np.flatnonzero(got.view(np.uint32) != want.view(np.uint32))
+                            bad = bad[~(np.isnan(got[bad]) & np.isnan(want[bad]))]
+                            assert bad.size == 0, f"{what}: x={x[bad[:4]]} got={got[bad[:4]]} want={want[bad[:4]]}"
+                        else:
+                            assert bf16_equal(got, want), what
+
+
+@pytest.mark.parametrize("cell", QUANT_CELLS, ids=cell_id)
+def test_quantize_stochastic_extreme_thresholds(gpu, cell):
+    """sign(r) * ceil(|r| - xi), the form the kernels use, against the literal trunc / compare / add of
+    quantize.inl:8-19 at the thresholds where a rounding slip would show: 0, denormal, tiny, just below 1."""
+    dt_in, dt_out = cell
+    rng = np.random.default_rng(12)
+    qmax = (1 << BITS[dt_out]) - 1
+    one_below = float(np.nextafter(np.float32(1.0), np.float32(0.0)))
+    for xi in (0.0, 1e-45, 1e-30, 5.9604645e-08, 0.49999997, 0.5, 0.50000006, one_below):
+        for scale, zp in ((1.0, 0), (0.25, qmax // 2), (2.0 / 255, qmax), (0.037, -3)):
+            n = 3000
+            x = make_input(rng, n, dt_in, -2.0 * scale * (qmax + 2), 2.0 * scale * (qmax + 2))
+            sp = special_values(scale)
+            grid = (np.arange(-40, 41, dtype=np.float32) * np.float32(0.25) * np.float32(scale)).astype(np.float32)
+            near = np.concatenate([np.nextafter(grid, np.float32(np.inf)), np.nextafter(grid, np.float32(-np.inf))])
+            extra = np.concatenate([sp, grid, near]).astype(np.float32)
+            x[5:5 + extra.size] = extra if dt_in == F32 else f32_to_bf16_bits(extra)
+            with np.errstate(all="ignore"):
+                want = port.quantize(x, dt_out, scale, zp, STOCHASTIC, xi=xi, semantics=SEM_BODY)
+            got = gpu.quantize(x, dt_out, scale, zp, STOCHASTIC, xi=xi)
+            assert np.array_equal(got, want), f"xi={xi} scale={scale} zp={zp}: {np.flatnonzero(got != want)[:8]}"
+
+
 # ------------------------------------------------------------------------------------------------
 # min/max -> (scale, zero_point)
 # ------------------------------------------------------------------------------------------------

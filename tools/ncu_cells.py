@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Launches a few chosen cells of the kernel matrix a fixed number of times so that `ncu` can capture them
+(development tool).  Usage, on the GPU box:
+
+    ncu --set full --clock-control none --import-source on -k regex:'quant_stream|requant' \
+        -o gpurun_out/cells python tools/ncu_cells.py --numel 1000000000 --launches 2
+"""
+from __future__ import annotations
+
+import argparse
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (str(ROOT), str(ROOT / "pi-quant_b200")):
+    sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+import piquant  # noqa: E402
+from piquant import DataType as D, RoundMode  # noqa: E402
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--numel", type=int, default=1_000_000_000)
+    ap.add_argument("--launches", type=int, default=2)
+    ap.add_argument("--cells", default="bf16u2n,bf16u2s,bf16u4s,bf16u4n,requant_bf16")
+    a = ap.parse_args()
+    n = a.numel
+    torch.cuda.set_device(0)
+    ctx = piquant.Context()
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.set_stochastic_threshold(0.37)
+    ctx.set_kernel_variant(1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    xf = torch.empty(n, dtype=torch.float32, device="cuda").uniform_(-1, 1, generator=g)
+    xb = xf.to(torch.bfloat16)
+    q = torch.empty(n, dtype=torch.uint8, device="cuda")
+    ob = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    table = {
+        "f32u8n": lambda: ctx.quantize_ptr(xf.data_ptr(), D.F32, q.data_ptr(), D.UINT8, n, 2 / 255, 128, RoundMode.NEAREST),
+        "bf16u8n": lambda: ctx.quantize_ptr(xb.data_ptr(), D.BF16, q.data_ptr(), D.UINT8, n, 2 / 255, 128, RoundMode.NEAREST),
+        "bf16u8s": lambda: ctx.quantize_ptr(xb.data_ptr(), D.BF16, q.data_ptr(), D.UINT8, n, 2 / 255, 128, RoundMode.STOCHASTIC),
+        "bf16u4n": lambda: ctx.quantize_ptr(xb.data_ptr(), D.BF16, q.data_ptr(), D.UINT4, n, 2 / 15, 8, RoundMode.NEAREST),
+        "bf16u4s": lambda: ctx.quantize_ptr(xb.data_ptr(), D.BF16, q.data_ptr(), D.UINT4, n, 2 / 15, 8, RoundMode.STOCHASTIC),
+        "bf16u2n": lambda: ctx.quantize_ptr(xb.data_ptr(), D.BF16, q.data_ptr(), D.UINT2, n, 2 / 3, 2, RoundMode.NEAREST),
+        "bf16u2s": lambda: ctx.quantize_ptr(xb.data_ptr(), D.BF16, q.data_ptr(), D.UINT2, n, 2 / 3, 2, RoundMode.STOCHASTIC),
+        "requant_bf16": lambda: ctx.requantize_ptr(xb.data_ptr(), D.BF16, ob.data_ptr(), D.UINT8, n, 2 / 255, 128),
+    }
+    for name in a.cells.split(","):
+        for _ in range(a.launches):
+            table[name]()
+        torch.cuda.synchronize()
+        print("launched", name, flush=True)
+
+
+if __name__ == "__main__":
+    main()
