@@ -377,6 +377,12 @@ def run_extra(torch, ctx, D, RoundMode, ReduceOp, x, q, scale, zp, dev) -> dict:
                                          "note": "cffi call + pointer classification + cudaLaunchKernelEx (PDL)"}
     # C4: stochastic rounding
     rec("C4_f32_u8_stochastic", n, 5, time_launches(torch, lambda: ctx.quantize_ptr(x.data_ptr(), D.F32, q.data_ptr(), D.UINT8, n, scale, zp, RoundMode.STOCHASTIC), 10))
+    # C4 as BASELINE.json spells it ("f32->int8"): the reference has no signed dtype at this commit (mapped to
+    # uint8 above); INT8 is this library's extension (piquant_cuda.h), the same kernel on the offset-binary view
+    zp_i8 = zp - 128
+    rec("C4_f32_int8_stochastic_signed_extension", n, 5,
+        time_launches(torch, lambda: ctx.quantize_ptr(x.data_ptr(), D.F32, q.data_ptr(), D.INT8, n, scale, zp_i8, RoundMode.STOCHASTIC), 10),
+        "INT8 = extension dtype; zero point = uint8 zero point - 128")
     # C5: dequantize with ADD store op into an f32 accumulator (one 1/8 shard of 1e9 and the full size)
     n5 = max(n // 8, 1)
     acc = torch.zeros(n5, dtype=torch.float32, device=dev)

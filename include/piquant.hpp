@@ -34,13 +34,15 @@ namespace piquant {
 // ---- enums: numeric values are the C ABI's (piquant.h), checked below ---------------------------------
 enum class round_mode { nearest, stochastic, count_ };
 enum class reduce_op { set, add, count_ };
-enum class dtype { f32 = 0, bf16, uint2, uint4, uint8, count_ };
+// int2 / int4 / int8: signed extension of the B200 library (piquant_cuda.h), not in the reference at this commit
+enum class dtype { f32 = 0, bf16, uint2, uint4, uint8, int2, int4, int8, count_ };
 
 static_assert(static_cast<int>(round_mode::nearest) == PIQUANT_NEAREST && static_cast<int>(round_mode::stochastic) == PIQUANT_STOCHASTIC);
 static_assert(static_cast<int>(reduce_op::set) == PIQUANT_REDUCE_OP_SET && static_cast<int>(reduce_op::add) == PIQUANT_REDUCE_OP_ADD);
 static_assert(static_cast<int>(dtype::f32) == PIQUANT_DTYPE_F32 && static_cast<int>(dtype::bf16) == PIQUANT_DTYPE_BF16 &&
               static_cast<int>(dtype::uint2) == PIQUANT_DTYPE_UINT2 && static_cast<int>(dtype::uint4) == PIQUANT_DTYPE_UINT4 &&
-              static_cast<int>(dtype::uint8) == PIQUANT_DTYPE_UINT8);
+              static_cast<int>(dtype::uint8) == PIQUANT_DTYPE_UINT8 && static_cast<int>(dtype::int2) == PIQUANT_CUDA_DTYPE_INT2 &&
+              static_cast<int>(dtype::int4) == PIQUANT_CUDA_DTYPE_INT4 && static_cast<int>(dtype::int8) == PIQUANT_CUDA_DTYPE_INT8);
 
 // ---- element types ------------------------------------------------------------------------------------
 
@@ -108,6 +110,9 @@ inline constexpr std::array<dtype_info, static_cast<std::size_t>(dtype::count_)>
     {"uint2", 1, 2, dtype_flags::is_quant | dtype_flags::is_int | dtype_flags::is_packed},
     {"uint4", 1, 4, dtype_flags::is_quant | dtype_flags::is_int | dtype_flags::is_packed},
     {"uint8", 1, 8, dtype_flags::is_quant | dtype_flags::is_int},
+    {"int2", 1, 2, dtype_flags::is_quant | dtype_flags::is_int | dtype_flags::is_packed | dtype_flags::is_signed},
+    {"int4", 1, 4, dtype_flags::is_quant | dtype_flags::is_int | dtype_flags::is_packed | dtype_flags::is_signed},
+    {"int8", 1, 8, dtype_flags::is_quant | dtype_flags::is_int | dtype_flags::is_signed},
 }};
 [[nodiscard]] constexpr auto dtype_info_of(dtype dt) noexcept -> const dtype_info& { return dtype_infos[static_cast<std::size_t>(dt)]; }
 
@@ -121,6 +126,7 @@ template <> struct dtype_traits<bfp16_t> { static constexpr dtype type_code {dty
 template <> struct dtype_traits<uint2_t> { static constexpr dtype type_code {dtype::uint2}; };
 template <> struct dtype_traits<uint4_t> { static constexpr dtype type_code {dtype::uint4}; };
 template <> struct dtype_traits<std::uint8_t> { static constexpr dtype type_code {dtype::uint8}; };
+template <> struct dtype_traits<std::int8_t> { static constexpr dtype type_code {dtype::int8}; };
 
 template <typename> struct dtype_limits final {};
 template <> struct dtype_limits<fp32_t> final {

@@ -28,6 +28,22 @@ PIQUANT_EXPORT uint64_t piquant_cuda_kernel_launches(piquant_context_t* ctx);
 /* Number of usable CUDA devices; 0 when there is none (never aborts). */
 PIQUANT_EXPORT int   piquant_cuda_device_count(void);
 
+/* ---- signed quantized dtypes (extension) -----------------------------------------------------
+ * The reference at this commit has only UINT2/4/8 (reference include/piquant.h:33-40), but its parameter code
+ * already carries the signed case (compute_type_max's is_signed branch and type_min = -type_max - 1,
+ * reference src/piquant.cpp:212-220,246-248).  These three values are accepted wherever piquant.h takes a
+ * quantized dtype (quantize output, dequantize input, compute_quant_params target, requantize / *_meta_async / auto).
+ *
+ * Definition: intN is the offset-binary view of uintN --
+ *     quantize(x -> intN; scale, zp)   == quantize(x -> uintN; scale, zp + 2^(N-1)) with the sign bit of every field flipped,
+ *     dequantize(q: intN; scale, zp)   == dequantize(q with sign bits flipped: uintN; scale, zp + 2^(N-1)),
+ * i.e. q = clamp(round(x / scale) + zp, -2^(N-1), 2^(N-1) - 1) stored in two's complement, same packing order as the
+ * unsigned types (element k of a byte at bits [k*N, k*N+N)); every rounding rule and corner case of the unsigned kernels
+ * carries over.  compute_quant_params follows the reference's formula with q_min = -2^(N-1) (constant input: zero point -1). */
+#define PIQUANT_CUDA_DTYPE_INT2 ((piquant_dtype_t)5)
+#define PIQUANT_CUDA_DTYPE_INT4 ((piquant_dtype_t)6)
+#define PIQUANT_CUDA_DTYPE_INT8 ((piquant_dtype_t)7)
+
 /* ---- stochastic rounding control.  The reference draws its per-call threshold from a
  * random_device-seeded generator that no API can reach (reference src/piquant.cpp:194-201). */
 

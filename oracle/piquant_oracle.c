@@ -10,6 +10,7 @@
 
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 /* ------------------------------------------------------------------------------------------ */
@@ -51,6 +52,9 @@ static inline int64_t wrap_add64(int64_t a, int64_t b) { return (int64_t)((uint6
 static inline int64_t wrap_sub64(int64_t a, int64_t b) { return (int64_t)((uint64_t)a - (uint64_t)b); }
 
 static inline int is_quant(int dt) { return dt == ORC_UINT2 || dt == ORC_UINT4 || dt == ORC_UINT8; }
+/* signed extension types (piquant_oracle.h): defined through the unsigned functions below */
+static inline int is_signed_quant(int dt) { return dt == ORC_INT2 || dt == ORC_INT4 || dt == ORC_INT8; }
+static inline int unsigned_view(int dt) { return dt == ORC_INT2 ? ORC_UINT2 : dt == ORC_INT4 ? ORC_UINT4 : dt == ORC_INT8 ? ORC_UINT8 : dt; }
 static inline int is_float(int dt) { return dt == ORC_F32 || dt == ORC_BF16; }
 static inline int bits_of(int dt) {
     switch (dt) { case ORC_F32: return 32; case ORC_BF16: return 16; case ORC_UINT2: return 2;
@@ -58,11 +62,19 @@ static inline int bits_of(int dt) {
 }
 static inline int64_t qmax_of(int dt) { return (1ll << bits_of(dt)) - 1; } /* dtype_limits, piquant.hpp:175-186 */
 
+/* intN <-> uintN: flip the sign bit of the fields of elements [0, numel) of a packed buffer (offset binary <-> two's complement) */
+static void flip_sign_bits(uint8_t* q, int bits, int64_t numel) {
+    const int per = 8 / bits;
+    for (int64_t e = 0; e < numel; ++e) q[e / per] ^= (uint8_t)(1u << ((int)(e % per) * bits + bits - 1));
+}
+
 size_t orc_packed_bytes(int dtype, size_t numel) {           /* piquant_internal.hpp:41-44 */
+    dtype = unsigned_view(dtype);
     size_t per_byte = 8u / (size_t)bits_of(dtype);
     return (numel + per_byte - 1) / per_byte;
 }
 size_t orc_storage_bytes(int dtype, size_t numel) {
+    dtype = unsigned_view(dtype);
     return is_quant(dtype) ? orc_packed_bytes(dtype, numel) : numel * (size_t)(bits_of(dtype) / 8);
 }
 
@@ -186,6 +198,13 @@ static int partition(int64_t n, int64_t t, int64_t tc, int64_t pack_elems, int64
 int orc_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t numel,
                  float scale, int64_t zero_point, int round_mode, float rnd_threshold,
                  int semantics, int nthreads) {
+    if (is_signed_quant(dt_out)) {      /* extension: intN = uintN with zero point + 2^(N-1), sign bits flipped */
+        const int bits = bits_of(unsigned_view(dt_out));
+        int rc = orc_quantize(in, dt_in, out, unsigned_view(dt_out), numel, scale, wrap_add64(zero_point, 1ll << (bits - 1)),
+                              round_mode, rnd_threshold, semantics, nthreads);
+        if (rc == 0) flip_sign_bits((uint8_t*)out, bits, numel);
+        return rc;
+    }
     if (!is_float(dt_in) || !is_quant(dt_out)) return -1;          /* piquant.cpp:288-289 */
     if (semantics == ORC_SEM_BODY || nthreads < 1) {
         quant_range(in, dt_in, (uint8_t*)out, dt_out, 0, numel, scale, zero_point, round_mode, rnd_threshold, ORC_SEM_BODY);
@@ -281,6 +300,18 @@ static void dequant_range(const uint8_t* in, int dt_in, void* out, int dt_out, i
 
 int orc_dequantize(const void* in, int dt_in, void* out, int dt_out, int64_t numel,
                    float scale, int64_t zero_point, int reduce_op, int semantics, int nthreads) {
+    if (is_signed_quant(dt_in)) {       /* extension: flip the sign bits of a copy, dequantize as uintN with zero point + 2^(N-1) */
+        const int bits = bits_of(unsigned_view(dt_in));
+        const size_t nb = orc_packed_bytes(dt_in, (size_t)numel);
+        uint8_t* tmp = (uint8_t*)malloc(nb ? nb : 1);
+        if (!tmp) return -1;
+        memcpy(tmp, in, nb);
+        flip_sign_bits(tmp, bits, numel);
+        int rc = orc_dequantize(tmp, unsigned_view(dt_in), out, dt_out, numel, scale, wrap_add64(zero_point, 1ll << (bits - 1)),
+                                reduce_op, semantics, nthreads);
+        free(tmp);
+        return rc;
+    }
     if (!is_quant(dt_in) || !is_float(dt_out)) return -1;           /* piquant.cpp:321-322 */
     if (semantics == ORC_SEM_BODY || nthreads < 1) {
         dequant_range((const uint8_t*)in, dt_in, out, dt_out, 0, numel, scale, zero_point, reduce_op, ORC_SEM_BODY);
@@ -302,6 +333,9 @@ int orc_dequantize(const void* in, int dt_in, void* out, int dt_out, int64_t num
 int orc_requantize(const void* in, int dt_inout, void* out, int dt_quant, int64_t numel,
                    float scale, int64_t zero_point, int round_mode, float rnd_threshold,
                    int reduce_op, int fma_add) {
+    if (is_signed_quant(dt_quant))      /* extension: clamp(q + zp, -2^(N-1), 2^(N-1)-1) - zp == clamp(q + zp', 0, 2^N-1) - zp' with zp' = zp + 2^(N-1) */
+        return orc_requantize(in, dt_inout, out, unsigned_view(dt_quant), numel, scale,
+                              wrap_add64(zero_point, 1ll << (bits_of(unsigned_view(dt_quant)) - 1)), round_mode, rnd_threshold, reduce_op, fma_add);
     if (!is_float(dt_inout) || !is_quant(dt_quant)) return -1;      /* piquant.cpp:353-354 */
     const float inv = 1.0f / scale;
     const int64_t qmax = qmax_of(dt_quant);
@@ -351,12 +385,16 @@ void orc_minmax_bf16(const uint16_t* x, int64_t n, float out[2]) {  /* :1518-160
 }
 
 int orc_params_from_minmax(double r_min, double r_max, int dt_quant, float* scale, int64_t* zero_point) {
+    const int sgn = is_signed_quant(dt_quant);                      /* extension; the reference's is_signed branch, piquant.cpp:218,247-248 */
+    dt_quant = unsigned_view(dt_quant);
     if (!is_quant(dt_quant)) return -1;                             /* compute_type_max, piquant.cpp:213-220 */
-    const uint64_t type_max = (1ull << bits_of(dt_quant)) - 1;
-    const int64_t type_min = 0;                                     /* no signed dtypes at this commit */
+    const uint64_t type_max = (1ull << (bits_of(dt_quant) - (sgn ? 1 : 0))) - 1;
+    const int64_t type_min = sgn ? -(int64_t)type_max - 1 : 0;      /* no signed dtypes at this commit: always 0 there */
     if (r_max == r_min) {                                           /* piquant.cpp:249-252 */
         *scale = 1.0f;
-        *zero_point = (int64_t)((type_max + (uint64_t)type_min) >> 1);
+        /* signed: the reference's expression would wrap to INT64_MAX (uint64 + int64, logical shift) in code it never
+         * reaches; the extension uses the signed midpoint (type_max + type_min) >> 1 == -1 */
+        *zero_point = sgn ? -1 : (int64_t)((type_max + (uint64_t)type_min) >> 1);
         return 0;
     }
     double q_min = (double)type_min, q_max = (double)type_max;

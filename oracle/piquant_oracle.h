@@ -28,6 +28,18 @@ extern "C" {
 enum { ORC_NEAREST = 0, ORC_STOCHASTIC = 1 };
 enum { ORC_SET = 0, ORC_ADD = 1 };
 enum { ORC_F32 = 0, ORC_BF16 = 1, ORC_UINT2 = 2, ORC_UINT4 = 3, ORC_UINT8 = 4 };
+/*
+ * EXTENSION, PARITY UNPINNED (there is nothing to pin it to): signed quantized dtypes.  The reference at this commit has
+ * none (include/piquant.h:33-40) -- only the is_signed branches of compute_type_max / compute_quant_config
+ * (src/piquant.cpp:212-220,246-248) hint at them.  The library under test (include/piquant_cuda.h) defines intN as the
+ * offset-binary view of uintN, and so does this oracle, by calling its own pinned unsigned functions:
+ *     quantize(x -> intN; scale, zp)   = quantize(x -> uintN; scale, zp + 2^(N-1)), sign bit of every existing field flipped
+ *     dequantize(q: intN; scale, zp)   = dequantize(q with sign bits flipped: uintN; scale, zp + 2^(N-1))
+ *     requantize(via intN; scale, zp)  = requantize(via uintN; scale, zp + 2^(N-1))
+ * tests/test_oracle_signed.py checks that on ordinary inputs this equals the textbook
+ * clamp(round_half_away(x / scale) + zp, -2^(N-1), 2^(N-1)-1) in two's complement.
+ */
+enum { ORC_INT2 = 5, ORC_INT4 = 6, ORC_INT8 = 7 };
 
 /*
  * Which of the reference's (not fully self-consistent) per-element formulas to apply.

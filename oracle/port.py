@@ -11,11 +11,13 @@ import numpy as np
 from . import PORT_LIB, build
 
 F32, BF16, UINT2, UINT4, UINT8 = 0, 1, 2, 3, 4
+INT2, INT4, INT8 = 5, 6, 7          # signed extension (piquant_oracle.h): offset-binary view of the unsigned types
 NEAREST, STOCHASTIC = 0, 1
 SET, ADD = 0, 1
 SEM_BODY, SEM_REF = 0, 1
-BITS = {F32: 32, BF16: 16, UINT2: 2, UINT4: 4, UINT8: 8}
-NP_DTYPE = {F32: np.float32, BF16: np.uint16, UINT2: np.uint8, UINT4: np.uint8, UINT8: np.uint8}
+BITS = {F32: 32, BF16: 16, UINT2: 2, UINT4: 4, UINT8: 8, INT2: 2, INT4: 4, INT8: 8}
+NP_DTYPE = {F32: np.float32, BF16: np.uint16, UINT2: np.uint8, UINT4: np.uint8, UINT8: np.uint8, INT2: np.uint8, INT4: np.uint8, INT8: np.uint8}
+SIGNED = {INT2: UINT2, INT4: UINT4, INT8: UINT8}
 
 _lib = None
 

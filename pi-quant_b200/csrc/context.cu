@@ -40,8 +40,11 @@ void panic(const char* fmt, ...) {
     abort();
 }
 
-QuantParams make_params(float scale, int64_t zero_point, float xi) {
+QuantParams make_params(float scale, int64_t zero_point, float xi, int dt_quant) {
+    // signed extension types: the kernels work on the offset-binary view (pq_device.cuh)
+    zero_point = static_cast<int64_t>(static_cast<uint64_t>(zero_point) + static_cast<uint64_t>(dtype_zp_offset(dt_quant)));
     QuantParams P;
+    P.sign_xor = dtype_sign_xor(dt_quant);
     P.scale = scale;
     P.inv_scale = 1.0f / scale;                               // IEEE divide, once (kernels_specialized.inl:42)
     P.xi = xi;
@@ -420,13 +423,17 @@ int64_t x86_cvttsd_i64(double a) {
 // compute_quant_config after the gather (reference src/piquant.cpp:245-258), same double arithmetic
 void params_from_minmax(double r_min, double r_max, int dt_quant, float* scale, int64_t* zero_point) {
     pq_assert(dtype_is_quant(dt_quant), "type %s is not a quantization type", dtype_name(dt_quant));
-    const uint64_t type_max = (1ull << dtype_bits(dt_quant)) - 1;
-    const int64_t type_min = 0;
+    // compute_type_max / type_min (reference src/piquant.cpp:212-220, :246-248): a signed type loses one bit of range
+    const bool is_signed = dtype_is_signed_quant(dt_quant);
+    const uint64_t type_max = (1ull << (dtype_bits(dt_quant) - (is_signed ? 1 : 0))) - 1;
+    const int64_t type_min = is_signed ? -static_cast<int64_t>(type_max) - 1 : 0;
     float s;
     int64_t z;
     if (r_max == r_min) {
         s = 1.0f;
-        z = static_cast<int64_t>((type_max + static_cast<uint64_t>(type_min)) >> 1);
+        // unsigned: (type_max + type_min) >> 1 as in the reference.  For a signed type the reference's expression would wrap
+        // (uint64 + int64 -> uint64, logical shift: INT64_MAX) -- dead code there; here the signed midpoint, -1.
+        z = is_signed ? -1 : static_cast<int64_t>((type_max + static_cast<uint64_t>(type_min)) >> 1);
     } else {
         const double q_min = static_cast<double>(type_min), q_max = static_cast<double>(type_max);
         const double sd = (r_max - r_min) / (q_max - q_min);
@@ -559,7 +566,7 @@ extern "C" void piquant_quantize(piquant_context_t* ctx, const void* in, piquant
     check_float_ptr(in, dtype_in, "input");
     pq_assert(out != nullptr, "output pointer must not be NULL");
     const float xi = mode == PIQUANT_STOCHASTIC ? c->draw_xi() : 0.0f;
-    Job j{Cmd::Quant, in, dtype_in, out, dtype_out, numel, make_params(scale, zero_point, xi), static_cast<int>(mode), OP_SET};
+    Job j{Cmd::Quant, in, dtype_in, out, dtype_kernel_view(dtype_out), numel, make_params(scale, zero_point, xi, dtype_out), static_cast<int>(mode), OP_SET};
     run_job(*c, j);
 }
 
@@ -574,7 +581,7 @@ extern "C" void piquant_dequantize(piquant_context_t* ctx, const void* in, piqua
     if (numel == 0) return;
     pq_assert(in != nullptr, "input pointer must not be NULL");
     check_float_ptr(out, dtype_out, "output");
-    Job j{Cmd::Dequant, in, dtype_in, out, dtype_out, numel, make_params(scale, zero_point, 0.0f), 0, static_cast<int>(op)};
+    Job j{Cmd::Dequant, in, dtype_kernel_view(dtype_in), out, dtype_out, numel, make_params(scale, zero_point, 0.0f, dtype_in), 0, static_cast<int>(op)};
     run_job(*c, j);
 }
 
@@ -648,7 +655,7 @@ extern "C" void piquant_cuda_requantize(piquant_context_t* ctx, const void* in, 
     check_float_ptr(in, dtype_in_out, "input");
     check_float_ptr(out, dtype_in_out, "output");
     const float xi = mode == PIQUANT_STOCHASTIC ? c->draw_xi() : 0.0f;
-    Job j{Cmd::Requant, in, dtype_in_out, out, quant_dtype, numel, make_params(scale, zero_point, xi), static_cast<int>(mode), static_cast<int>(op)};
+    Job j{Cmd::Requant, in, dtype_in_out, out, dtype_kernel_view(quant_dtype), numel, make_params(scale, zero_point, xi, quant_dtype), static_cast<int>(mode), static_cast<int>(op)};
     run_job(*c, j);
 }
 
@@ -773,7 +780,7 @@ extern "C" void piquant_cuda_quantize_meta_async(piquant_context_t* ctx, const v
     DeviceState& d = c->dev_state(dc.device);
     const float xi = mode == PIQUANT_STOCHASTIC ? c->draw_xi() : 0.0f;
     const LaunchCfg cfg = make_cfg(*c, d, c->stream);
-    c->launches += launch_quantize(in, dtype_in, out, dtype_out, static_cast<int64_t>(numel), make_params(1.0f, 0, xi), static_cast<int>(mode),
+    c->launches += launch_quantize(in, dtype_in, out, dtype_kernel_view(dtype_out), static_cast<int64_t>(numel), make_params(1.0f, 0, xi, dtype_out), static_cast<int>(mode),
                                    cfg, &reinterpret_cast<const DeviceMeta*>(d_meta)->P);
 }
 
@@ -789,7 +796,7 @@ extern "C" void piquant_cuda_dequantize_meta_async(piquant_context_t* ctx, const
     DeviceGuard guard(dc.cur, dc.device);
     DeviceState& d = c->dev_state(dc.device);
     const LaunchCfg cfg = make_cfg(*c, d, c->stream);
-    c->launches += launch_dequantize(in, dtype_in, out, dtype_out, static_cast<int64_t>(numel), make_params(1.0f, 0, 0.0f), static_cast<int>(op),
+    c->launches += launch_dequantize(in, dtype_kernel_view(dtype_in), out, dtype_out, static_cast<int64_t>(numel), make_params(1.0f, 0, 0.0f, dtype_in), static_cast<int>(op),
                                      cfg, &reinterpret_cast<const DeviceMeta*>(d_meta)->P);
 }
 
@@ -817,7 +824,7 @@ extern "C" void piquant_cuda_quantize_auto(piquant_context_t* ctx, const void* i
     compute_meta_async(*c, d, in, dtype_in, numel, dtype_out, d.d_meta, d.h_meta_dev, in_bytes <= (size_t(96) << 20));
     const float xi = mode == PIQUANT_STOCHASTIC ? c->draw_xi() : 0.0f;
     const LaunchCfg cfg = make_cfg(*c, d, c->stream);
-    c->launches += launch_quantize(in, dtype_in, out, dtype_out, static_cast<int64_t>(numel), make_params(1.0f, 0, xi), static_cast<int>(mode),
+    c->launches += launch_quantize(in, dtype_in, out, dtype_kernel_view(dtype_out), static_cast<int64_t>(numel), make_params(1.0f, 0, xi, dtype_out), static_cast<int>(mode),
                                    cfg, &d.d_meta->P);
     PQ_CUDA_CHECK(cudaStreamSynchronize(c->stream));         // the ONE host sync of the whole sequence
     pq_assert(d.h_meta->error == 0, "scale must be positive");

@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(kThreads) dequant_stream_kernel(const DequantA
             if (item < a.n_items) {
                 uint32_t wo[NWO];
 #pragma unroll
+                for (int k = 0; k < NWI; ++k) wi[u][k] ^= a.P.sign_xor;     // signed dtypes: two's complement -> offset binary
+#pragma unroll
                 for (int e = 0; e < V; ++e) {
                     const uint32_t q = (wi[u][(e * BITS) / 32] >> ((e * BITS) % 32)) & QMAX;
                     if constexpr (OUT_DT == DT_F32) {

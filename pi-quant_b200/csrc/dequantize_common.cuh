@@ -38,7 +38,7 @@ template <int BITS, int OUT_DT, int OP>
 __device__ __forceinline__ void dequant_one_byte(const DequantArgs& a, int64_t b) {
     constexpr int PER = 8 / BITS;
     constexpr uint32_t QMAX = (1u << BITS) - 1u;
-    const uint32_t byte = a.in[b];
+    const uint32_t byte = a.in[b] ^ (a.P.sign_xor & 0xffu);     // signed dtypes: two's complement -> offset binary
     // reference quirk kept: the 1-3 element tail of the generic u2->f32 kernel always SETs, even
     // for ADD (src/kernels/dequantize.inl:72-86)
     const int64_t set_from = (BITS == 2 && OUT_DT == DT_F32) ? a.numel - (a.numel & 3) : a.numel;
@@ -73,8 +73,11 @@ __device__ __forceinline__ float magic_byte(uint32_t x) {
 // bit-identical to the reference's  float(int32(q) - zp) * scale  and  fma(float(q), scale, -float(zp)*scale).
 // Nibbles / 2-bit fields are first spread to one field per byte with a shift+mask per word.
 template <int BITS, int OUT_DT, int OP, int NWI, int NWO>
-__device__ __forceinline__ void dequant_words(const uint32_t (&w)[NWI], const uint32_t (&prev)[NWO], const DequantArgs& a,
+__device__ __forceinline__ void dequant_words(const uint32_t (&w_in)[NWI], const uint32_t (&prev)[NWO], const DequantArgs& a,
                                               uint32_t (&o)[NWO]) {
+    uint32_t w[NWI];
+#pragma unroll
+    for (int i = 0; i < NWI; ++i) w[i] = w_in[i] ^ a.P.sign_xor;     // signed dtypes: two's complement -> offset binary
     constexpr int EV = OUT_DT == DT_F32 ? NWO : 2 * NWO;
     constexpr int FPB = 8 / BITS;                       // fields per byte
     constexpr int EPW = 32 / BITS;                      // elements per packed word

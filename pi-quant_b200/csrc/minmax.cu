@@ -191,19 +191,20 @@ __device__ __forceinline__ long long dev_cvttsd_i64(double a) {     // x86 cvtts
     return (a >= -9223372036854775808.0 && a < 9223372036854775808.0) ? __double2ll_rz(a) : LLONG_MIN;
 }
 
-__global__ void params_kernel(const float* minmax4, int bits, DeviceMeta* out, DeviceMeta* mapped_out) {
+__global__ void params_kernel(const float* minmax4, int bits, int is_signed, uint32_t sign_xor, DeviceMeta* out, DeviceMeta* mapped_out) {
     pdl_launch_dependents();
     pdl_wait();
     // same expressions, same order, same IEEE double operations as params_from_minmax() in context.cu
     const double r_min = -static_cast<double>(minmax4[2]), r_max = static_cast<double>(minmax4[3]);
-    const unsigned long long type_max = (1ull << bits) - 1;
+    const unsigned long long type_max = (1ull << (bits - (is_signed ? 1 : 0))) - 1;
+    const long long type_min = is_signed ? -static_cast<long long>(type_max) - 1 : 0;
     float s;
     long long z;
     if (r_max == r_min) {
         s = 1.0f;
-        z = static_cast<long long>(type_max >> 1);
+        z = is_signed ? -1 : static_cast<long long>(type_max >> 1);
     } else {
-        const double q_min = 0.0, q_max = static_cast<double>(type_max);
+        const double q_min = static_cast<double>(type_min), q_max = static_cast<double>(type_max);
         const double sd = __ddiv_rn(__dsub_rn(r_max, r_min), __dsub_rn(q_max, q_min));
         double zp = __dsub_rn(q_min, __ddiv_rn(r_min, sd));
         zp = fmax(fmin(static_cast<double>(dev_cvttsd_i64(round(zp))), q_max), q_min);
@@ -214,6 +215,9 @@ __global__ void params_kernel(const float* minmax4, int bits, DeviceMeta* out, D
     m.scale = s;
     m.error = (isnan(s) || !(s >= 0.0f)) ? 1 : 0;
     m.zero_point = z;
+    // the kernels work on the unsigned (offset-binary) view of a signed type: make_params() in context.cu
+    z = static_cast<long long>(static_cast<unsigned long long>(z) + (is_signed ? (1ull << (bits - 1)) : 0ull));
+    m.P.sign_xor = sign_xor;
     m.P.scale = s;
     m.P.inv_scale = __fdiv_rn(1.0f, s);
     m.P.xi = 0.0f;
@@ -231,7 +235,8 @@ __global__ void params_kernel(const float* minmax4, int bits, DeviceMeta* out, D
 }
 
 int launch_params(const float* minmax4, int dt_quant, DeviceMeta* out, DeviceMeta* mapped_out, const LaunchCfg& cfg) {
-    launch_kernel(params_kernel, 1u, 1u, 0, cfg.stream, minmax4, dtype_bits(dt_quant), out, mapped_out);
+    launch_kernel(params_kernel, 1u, 1u, 0, cfg.stream, minmax4, dtype_bits(dt_quant), dtype_is_signed_quant(dt_quant) ? 1 : 0,
+                  dtype_sign_xor(dt_quant), out, mapped_out);
     PQ_CUDA_CHECK(cudaGetLastError());
     return 1;
 }

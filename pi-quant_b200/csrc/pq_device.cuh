@@ -21,8 +21,12 @@
 
 namespace pq {
 
-// same numeric values as include/piquant.h (reference include/piquant.h:33-40)
-enum : int { DT_F32 = 0, DT_BF16 = 1, DT_U2 = 2, DT_U4 = 3, DT_U8 = 4 };
+// same numeric values as include/piquant.h (reference include/piquant.h:33-40); 5..7 are this library's signed extension
+// (include/piquant_cuda.h).  The kernels only ever see the unsigned types: intN is the offset-binary view of uintN,
+//     quantize_intN(x; scale, zp)   = quantize_uintN(x; scale, zp + 2^(N-1))  XOR  the sign bit of every field
+//     dequantize_intN(q; scale, zp) = dequantize_uintN(q XOR sign bits; scale, zp + 2^(N-1))
+// so every rounding and corner case of the unsigned kernels (and their parity with the reference) carries over.
+enum : int { DT_F32 = 0, DT_BF16 = 1, DT_U2 = 2, DT_U4 = 3, DT_U8 = 4, DT_I2 = 5, DT_I4 = 6, DT_I8 = 7 };
 // which per-element formula a quantize cell uses
 enum : int { STEP_BODY = 0, STEP_ROUND64 = 1, STEP_STOCH = 2 };
 enum : int { OP_SET = 0, OP_ADD = 1 };
@@ -35,6 +39,7 @@ struct QuantParams {
     int32_t zp32;        // (int32_t)zero_point, the truncation of quantize.inl:112-128
     int32_t bigzp;       // |zero_point| > 2^29: the int32 fast path of the int64 formulas is not valid
     int32_t spec_ok32;   // |zp32| <= 2^29: the speculative group path is valid for the int32 (SIMD-body) formula
+    uint32_t sign_xor;   // signed dtypes: the sign bit of every packed field of a 32-bit word (0x80808080 / 0x88888888 / 0xAAAAAAAA), else 0
     int64_t zp64;
 };
 
@@ -390,6 +395,10 @@ __device__ __forceinline__ void quant_group(const uint32_t (&w)[NW], const Quant
             o[(e * BITS) / 32] |= q << ((e * BITS) % 32);
         }
     }
+    // signed dtypes: offset binary -> two's complement, one LOP3 per packed word (fields that do not exist stay 0)
+    constexpr uint32_t LAST_VALID = (NE * BITS) % 32 == 0 ? 0xffffffffu : ((1u << ((NE * BITS) % 32)) - 1u);
+#pragma unroll
+    for (int j = 0; j < OW; ++j) o[j] ^= P.sign_xor & (j == OW - 1 ? LAST_VALID : 0xffffffffu);
 }
 
 // ------------------------------------------------------------------------------------------------

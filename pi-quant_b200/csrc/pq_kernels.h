@@ -64,10 +64,20 @@ inline int dtype_bits(int dt) {
         case DT_U2: return 2;
         case DT_U4: return 4;
         case DT_U8: return 8;
+        case DT_I2: return 2;
+        case DT_I4: return 4;
+        case DT_I8: return 8;
         default: return 0;
     }
 }
-inline bool dtype_is_quant(int dt) { return dt == DT_U2 || dt == DT_U4 || dt == DT_U8; }
+inline bool dtype_is_quant(int dt) { return dt == DT_U2 || dt == DT_U4 || dt == DT_U8 || dt == DT_I2 || dt == DT_I4 || dt == DT_I8; }
+inline bool dtype_is_signed_quant(int dt) { return dt == DT_I2 || dt == DT_I4 || dt == DT_I8; }
+// the unsigned type whose kernels serve `dt` (identity for everything but the signed extension types)
+inline int dtype_kernel_view(int dt) { return dt == DT_I2 ? DT_U2 : dt == DT_I4 ? DT_U4 : dt == DT_I8 ? DT_U8 : dt; }
+// sign bit of every field of a packed 32-bit word, 0 for unsigned types
+inline uint32_t dtype_sign_xor(int dt) { return dt == DT_I2 ? 0xAAAAAAAAu : dt == DT_I4 ? 0x88888888u : dt == DT_I8 ? 0x80808080u : 0u; }
+// 2^(bits-1) for signed types: added to the zero point to reach the offset-binary view
+inline int64_t dtype_zp_offset(int dt) { return dtype_is_signed_quant(dt) ? (int64_t{1} << (dtype_bits(dt) - 1)) : 0; }
 inline bool dtype_is_float(int dt) { return dt == DT_F32 || dt == DT_BF16; }
 inline const char* dtype_name(int dt) {
     switch (dt) {
@@ -76,6 +86,9 @@ inline const char* dtype_name(int dt) {
         case DT_U2: return "uint2";
         case DT_U4: return "uint4";
         case DT_U8: return "uint8";
+        case DT_I2: return "int2";
+        case DT_I4: return "int4";
+        case DT_I8: return "int8";
         default: return "?";
     }
 }
@@ -88,7 +101,9 @@ inline size_t storage_bytes(int dt, size_t numel) {
     return dtype_is_quant(dt) ? packed_bytes(dt, numel) : numel * static_cast<size_t>(dtype_bits(dt) / 8);
 }
 
-QuantParams make_params(float scale, int64_t zero_point, float xi);
+// dt_quant: the caller's quantized dtype; for a signed type the returned parameters are those of the unsigned
+// kernel view (zero point + 2^(bits-1), wrapping; sign_xor set) -- launch with dtype_kernel_view(dt_quant).
+QuantParams make_params(float scale, int64_t zero_point, float xi, int dt_quant = DT_U8);
 
 // Device pointers (or device-accessible mapped host pointers) only.  All launches are asynchronous
 // on cfg.stream.  `mode`: 0 nearest, 1 stochastic (P.xi).  Returns the number of kernels launched.
@@ -123,11 +138,14 @@ struct DeviceMeta {
     QuantParams P;
     char        pad[64 - 16 - sizeof(QuantParams)];
 };
+static_assert(sizeof(QuantParams) == 40, "QuantParams must keep fitting the opaque part of piquant_cuda_meta_t");
 static_assert(sizeof(DeviceMeta) == 64 && offsetof(DeviceMeta, P) == 16, "piquant_cuda_meta_t layout");
 
 // One-thread kernel: the double-precision scale / zero-point arithmetic of the reference
 // (src/piquant.cpp:245-258) on the {-min, max} pair at minmax4[2..3], bit-identical to the host version,
 // plus everything the kernels derive from it (1/scale, bias, range flags).  Asynchronous on cfg.stream.
+// dt_quant may be a signed extension type: the public (scale, zero_point) are then the signed ones
+// (reference src/piquant.cpp:245-258 with type_min = -type_max - 1) and P is the unsigned kernel view.
 int launch_params(const float* minmax4, int dt_quant, DeviceMeta* out, DeviceMeta* mapped_out, const LaunchCfg& cfg);
 
 // variant 0 ("auto"): which cells go to the TMA ring kernels.  Every entry is a measurement on B200, not a guess.

@@ -38,13 +38,16 @@ template <int IN_DT, int BITS, int STEP>
 __device__ __forceinline__ void quant_one_byte(const QuantArgs& a, int64_t b) {
     constexpr int PER = 8 / BITS;
     constexpr int QMAX = (1 << BITS) - 1;
-    uint32_t byte = 0;
+    uint32_t byte = 0, present = 0;
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
         const int64_t e = b * PER + k;
-        if (e < a.numel) byte |= static_cast<uint32_t>(quant_step<STEP>(load_elem<IN_DT>(a.in, e), a.P, QMAX)) << (k * BITS);
+        if (e < a.numel) {
+            byte |= static_cast<uint32_t>(quant_step<STEP>(load_elem<IN_DT>(a.in, e), a.P, QMAX)) << (k * BITS);
+            present |= static_cast<uint32_t>(QMAX) << (k * BITS);
+        }
     }
-    a.out[b] = static_cast<uint8_t>(byte);
+    a.out[b] = static_cast<uint8_t>(byte ^ (a.P.sign_xor & present));     // signed dtypes: sign bit of the fields that exist
 }
 
 }  // namespace pq

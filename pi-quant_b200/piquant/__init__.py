@@ -38,14 +38,24 @@ class DataType(Enum):
     UINT2 = C.PIQUANT_DTYPE_UINT2
     UINT4 = C.PIQUANT_DTYPE_UINT4
     UINT8 = C.PIQUANT_DTYPE_UINT8
+    # signed extension of the B200 build (include/piquant_cuda.h: PIQUANT_CUDA_DTYPE_INT2/4/8): two's complement
+    # fields, same packing order; defined as the offset-binary view of the unsigned types
+    INT2 = 5
+    INT4 = 6
+    INT8 = 7
 
     @property
     def bit_size(self) -> int:
-        return {DataType.F32: 32, DataType.BF16: 16, DataType.UINT2: 2, DataType.UINT4: 4, DataType.UINT8: 8}[self]
+        return {DataType.F32: 32, DataType.BF16: 16, DataType.UINT2: 2, DataType.UINT4: 4, DataType.UINT8: 8,
+                DataType.INT2: 2, DataType.INT4: 4, DataType.INT8: 8}[self]
 
     @property
     def is_quantized(self) -> bool:
-        return self in (DataType.UINT2, DataType.UINT4, DataType.UINT8)
+        return self in (DataType.UINT2, DataType.UINT4, DataType.UINT8, DataType.INT2, DataType.INT4, DataType.INT8)
+
+    @property
+    def is_signed(self) -> bool:
+        return self in (DataType.INT2, DataType.INT4, DataType.INT8)
 
     @property
     def is_dequantized(self) -> bool:

@@ -29,9 +29,12 @@ _TORCH_DTYPE_MAP: dict = {
     torch.quint4x2: DataType.UINT4,
     torch.quint8: DataType.UINT8,
     torch.uint8: DataType.UINT8,
+    # signed extension of the B200 build (the reference has no signed types at this commit)
+    torch.qint8: DataType.INT8,
+    torch.int8: DataType.INT8,
 }
 
-_QUANT_TYPES = {torch.quint2x4, torch.quint4x2, torch.quint8, torch.uint8}
+_QUANT_TYPES = {torch.quint2x4, torch.quint4x2, torch.quint8, torch.uint8, torch.qint8, torch.int8}
 _DEQUANT_TYPES = {torch.float32, torch.bfloat16}
 _ROUND_MODES = {"nearest": RoundMode.NEAREST, "stochastic": RoundMode.STOCHASTIC}
 _REDUCE_OPS = {"set": ReduceOp.SET, "add": ReduceOp.ADD}

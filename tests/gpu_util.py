@@ -8,9 +8,10 @@ import torch
 import piquant
 from piquant import DataType, ReduceOp, RoundMode
 
-from oracle.port import BF16, F32, UINT2, UINT4, UINT8, packed_bytes
+from oracle.port import BF16, F32, INT2, INT4, INT8, UINT2, UINT4, UINT8, packed_bytes
 
-DT = {F32: DataType.F32, BF16: DataType.BF16, UINT2: DataType.UINT2, UINT4: DataType.UINT4, UINT8: DataType.UINT8}
+DT = {F32: DataType.F32, BF16: DataType.BF16, UINT2: DataType.UINT2, UINT4: DataType.UINT4, UINT8: DataType.UINT8,
+      INT2: DataType.INT2, INT4: DataType.INT4, INT8: DataType.INT8}
 MODE = {0: RoundMode.NEAREST, 1: RoundMode.STOCHASTIC}
 OP = {0: ReduceOp.SET, 1: ReduceOp.ADD}
 CANARY = 0xCD

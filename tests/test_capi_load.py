@@ -61,7 +61,10 @@ def test_python_package_mirrors_reference_surface(lib):
     import piquant
     from piquant import Context, DataType, ReduceOp, RoundMode
 
-    assert [m.value for m in DataType] == [0, 1, 2, 3, 4]
+    # the reference's five values keep their ABI numbers (reference include/piquant.h:33-40); 5..7 are the signed extension
+    assert [(m.name, m.value) for m in DataType][:5] == [("F32", 0), ("BF16", 1), ("UINT2", 2), ("UINT4", 3), ("UINT8", 4)]
+    assert [(m.name, m.value) for m in DataType][5:] == [("INT2", 5), ("INT4", 6), ("INT8", 7)]
+    assert DataType.INT4.is_signed and DataType.INT4.is_quantized and not DataType.UINT4.is_signed and DataType.INT4.storage_bytes(7) == 4
     assert RoundMode.NEAREST.value == 0 and RoundMode.STOCHASTIC.value == 1
     assert ReduceOp.SET.value == 0 and ReduceOp.ADD.value == 1
     assert DataType.UINT4.bit_size == 4 and DataType.UINT4.is_quantized and DataType.BF16.is_dequantized
@@ -85,10 +88,11 @@ def test_params_from_minmax_is_host_arithmetic(lib):
     from oracle import port
     from piquant import Context, DataType
 
-    dt = {port.UINT2: DataType.UINT2, port.UINT4: DataType.UINT4, port.UINT8: DataType.UINT8}
+    dt = {port.UINT2: DataType.UINT2, port.UINT4: DataType.UINT4, port.UINT8: DataType.UINT8,
+          port.INT2: DataType.INT2, port.INT4: DataType.INT4, port.INT8: DataType.INT8}
     cases = [(-1.0, 1.0), (0.0, 1.0), (1.0, 2.0), (-5.0, -1.0), (42.0, 42.0), (-3.0, 5.0), (-3e38, 3e38), (1e-30, 2e-30)]
     for mn, mx in cases:
-        for d in (port.UINT2, port.UINT4, port.UINT8):
+        for d in dt:
             assert Context.params_from_minmax(mn, mx, dt[d]) == port.params_from_minmax(mn, mx, d)
 
 
