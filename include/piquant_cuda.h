@@ -54,6 +54,26 @@ PIQUANT_EXPORT void  piquant_cuda_seed(piquant_context_t* ctx, uint64_t seed);
 /* The threshold used by the most recent STOCHASTIC call. */
 PIQUANT_EXPORT float piquant_cuda_last_stochastic_threshold(piquant_context_t* ctx);
 
+/* ---- per-element stochastic rounding (extension) ------------------------------------------------
+ * The reference's STOCHASTIC mode compares every element of a call with ONE threshold (reference src/piquant.cpp:199-201):
+ * cheap, but every call is biased.  This mode is accepted as the `mode` of piquant_quantize, piquant_cuda_quantize_meta_async
+ * and piquant_cuda_quantize_auto (not by requantize) and rounds every element with its own random number:
+ *
+ *     q_i = clamp(floor(x_i / scale + u_i) + zero_point, qmin, qmax),      u_i = (k_i + 1/2) * 2^-16
+ *     k_i = 16 bits of Philox4x32-10(counter = {lo32(i / 8), hi32(i / 8), 0, 0}, key = {lo32(key), hi32(key)}):
+ *           element i takes bits [16 * (i % 2), +16) of output word (i % 8) / 2,
+ *
+ * i = index of the element in the tensor passed to the call, x_i / scale = RN(x_i * (1.0f / scale)) as in every other mode.
+ * E[q_i] = x_i / scale + zero_point inside the range (unbiased to 2^-17 of a step); integers never move.  The 64-bit key
+ * of a call comes from the context's generator (reproducible after piquant_cuda_seed) unless one is set here. */
+#define PIQUANT_CUDA_STOCHASTIC_PER_ELEMENT ((piquant_round_mode_t)2)
+/* Use this key for every following per-element call (tests, replay). */
+PIQUANT_EXPORT void     piquant_cuda_set_sr_key(piquant_context_t* ctx, uint64_t key);
+/* Draw a fresh key per call again. */
+PIQUANT_EXPORT void     piquant_cuda_clear_sr_key(piquant_context_t* ctx);
+/* The key used by the most recent per-element call. */
+PIQUANT_EXPORT uint64_t piquant_cuda_last_sr_key(piquant_context_t* ctx);
+
 /* ---- fused quantize -> dequantize (reference C++ API only: context::quantize_dequantize_fused,
  * reference include/piquant.hpp:276-285, src/piquant.cpp:342-369).  in and out have dtype
  * dtype_in_out (F32 / BF16) and numel elements each; the result is not packed. */

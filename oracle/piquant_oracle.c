@@ -220,6 +220,54 @@ int orc_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t numel
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* extension: per-element stochastic rounding (spec in piquant_oracle.h)                       */
+/* ------------------------------------------------------------------------------------------ */
+
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+int orc_quantize_sr(const void* in, int dt_in, void* out, int dt_out, int64_t numel,
+                    float scale, int64_t zero_point, uint64_t key, int64_t base) {
+    if (is_signed_quant(dt_out)) {
+        const int bits = bits_of(unsigned_view(dt_out));
+        int rc = orc_quantize_sr(in, dt_in, out, unsigned_view(dt_out), numel, scale, wrap_add64(zero_point, 1ll << (bits - 1)), key, base);
+        if (rc == 0) flip_sign_bits((uint8_t*)out, bits, numel);
+        return rc;
+    }
+    if (!is_float(dt_in) || !is_quant(dt_out)) return -1;
+    const int bits = bits_of(dt_out), per = 8 / bits;
+    const int64_t qmax = qmax_of(dt_out);
+    const float inv = 1.0f / scale;
+    const uint32_t k2[2] = {(uint32_t)key, (uint32_t)(key >> 32)};
+    uint8_t* o = (uint8_t*)out;
+    memset(o, 0, orc_packed_bytes(dt_out, (size_t)numel));
+    for (int64_t i = 0; i < numel; ++i) {
+        const int64_t j = base + i;
+        const uint32_t ctr[4] = {(uint32_t)((uint64_t)j >> 3), (uint32_t)((uint64_t)j >> 35), 0u, 0u};
+        uint32_t r[4];
+        orc_philox4x32_10(ctr, k2, r);
+        const uint32_t k = (r[(j & 7) >> 1] >> (16 * (int)(j & 1))) & 0xffffu;
+        const double u = ((double)k + 0.5) / 65536.0;
+        const float p = load_fp(in, dt_in, i) * inv;
+        int64_t t;
+        if (fabsf(p) < 8388608.0f) t = (int64_t)floor((double)p + u);   /* exact: < 53 significant bits */
+        else t = x86_cvtt_i64(p);
+        int64_t q = wrap_add64(t, zero_point);
+        q = q < 0 ? 0 : (q > qmax ? qmax : q);
+        o[i / per] |= (uint8_t)(q << ((int)(i % per) * bits));
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* dequantize                                                                                 */
 /* ------------------------------------------------------------------------------------------ */
 

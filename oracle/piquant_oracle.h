@@ -70,6 +70,20 @@ int orc_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t numel
                  float scale, int64_t zero_point, int round_mode, float rnd_threshold,
                  int semantics, int nthreads);
 
+/*
+ * EXTENSION, PARITY UNPINNED: per-element stochastic rounding (include/piquant_cuda.h,
+ * PIQUANT_CUDA_STOCHASTIC_PER_ELEMENT).  The reference only has the one-threshold-per-call mode above.  Spec:
+ *     q_i = clamp(floor(p_i + u_i) + zero_point, qmin, qmax),  p_i = RN(x_i * (1.0f / scale)),  u_i = (k_i + 1/2) * 2^-16,
+ *     k_i = 16 bits of Philox4x32-10(counter = {lo32(j / 8), hi32(j / 8), 0, 0}, key = {lo32(key), hi32(key)}), j = base + i:
+ *           bits [16 * (j % 2), +16) of output word (j % 8) / 2.
+ * |p_i| >= 2^23 (already an integer), NaN and inf take (int64)p_i with the x86 conversion rule, like the other int64 formulas.
+ * The Philox4x32-10 core is pinned by the Random123 known-answer vectors (tests/test_oracle_sr.py).
+ */
+int orc_quantize_sr(const void* in, int dt_in, void* out, int dt_out, int64_t numel,
+                    float scale, int64_t zero_point, uint64_t key, int64_t base);
+/* Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11) */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
 /* context::dequantize (piquant.cpp:310-340) -> dequant_generic (dequantize.inl:89-140). */
 int orc_dequantize(const void* in, int dt_in, void* out, int dt_out, int64_t numel,
                    float scale, int64_t zero_point, int reduce_op,

@@ -31,6 +31,8 @@ def lib() -> C.CDLL:
         L.orc_packed_bytes.argtypes = [i32, C.c_size_t]; L.orc_packed_bytes.restype = C.c_size_t
         L.orc_storage_bytes.argtypes = [i32, C.c_size_t]; L.orc_storage_bytes.restype = C.c_size_t
         L.orc_quantize.argtypes = [vp, i32, vp, i32, i64, f32, i64, i32, f32, i32, i32]; L.orc_quantize.restype = i32
+        L.orc_quantize_sr.argtypes = [vp, i32, vp, i32, i64, f32, i64, C.c_uint64, i64]; L.orc_quantize_sr.restype = i32
+        L.orc_philox4x32_10.argtypes = [vp, vp, vp]; L.orc_philox4x32_10.restype = None
         L.orc_dequantize.argtypes = [vp, i32, vp, i32, i64, f32, i64, i32, i32, i32]; L.orc_dequantize.restype = i32
         L.orc_requantize.argtypes = [vp, i32, vp, i32, i64, f32, i64, i32, f32, i32, i32]; L.orc_requantize.restype = i32
         L.orc_minmax_f32.argtypes = [vp, i64, vp]; L.orc_minmax_f32.restype = None
@@ -90,6 +92,23 @@ def quantize(x: np.ndarray, dt_out: int, scale: float, zero_point: int, mode: in
     if rc != 0:
         raise ValueError("invalid dtype combination")
     return out
+
+
+def quantize_sr(x: np.ndarray, dt_out: int, scale: float, zero_point: int, key: int, base: int = 0) -> np.ndarray:
+    """Extension: per-element stochastic rounding (piquant_oracle.h), Philox key `key`, element 0 has index `base`."""
+    out = np.zeros(packed_bytes(dt_out, x.size), dtype=np.uint8)
+    rc = lib().orc_quantize_sr(_ptr(x), dtype_of(x), _ptr(out), dt_out, x.size, scale, zero_point, key & (2**64 - 1), base)
+    if rc != 0:
+        raise ValueError("invalid dtype combination")
+    return out
+
+
+def philox4x32_10(ctr, key) -> list[int]:
+    c = np.array(ctr, dtype=np.uint32)
+    k = np.array(key, dtype=np.uint32)
+    o = np.zeros(4, dtype=np.uint32)
+    lib().orc_philox4x32_10(_ptr(c), _ptr(k), _ptr(o))
+    return [int(v) for v in o]
 
 
 def dequantize(q: np.ndarray, dt_in: int, numel: int, dt_out: int, scale: float, zero_point: int, op: int = SET,

@@ -147,6 +147,8 @@ struct Context {
     int                        variant = 0;
     bool                       xi_fixed = false;
     float                      xi = 0.0f, last_xi = 0.0f;
+    bool                       sr_key_fixed = false;      // per-element stochastic rounding (piquant_cuda.h)
+    uint64_t                   sr_key = 0, last_sr_key = 0;
     std::mt19937_64            rng{std::random_device{}()};
     std::mutex                 mu;
     std::map<int, DeviceState> devs;
@@ -189,6 +191,12 @@ struct Context {
         // one threshold per call, U[0,1) (reference src/piquant.cpp:199-201)
         last_xi = xi_fixed ? xi : std::uniform_real_distribution<float>{0.0f, 1.0f}(rng);
         return last_xi;
+    }
+
+    uint64_t draw_sr_key() {
+        // one Philox key per call: fresh random bits for every element of every call, replayable after piquant_cuda_seed
+        last_sr_key = sr_key_fixed ? sr_key : rng();
+        return last_sr_key;
     }
 
     DeviceState& dev_state(int device) {
@@ -324,13 +332,18 @@ struct Job {
     int         mode;
     int         op;
     const QuantParams* dP = nullptr;   // parameters that live in device memory (produced by params_kernel)
+    uint64_t    sr_key = 0;            // mode 2 (per-element stochastic rounding): Philox key of this call
 };
 
 // bytes of the `in` / `out` buffers for a range of `n` elements
 size_t job_in_bytes(const Job& j, size_t n) { return storage_bytes(j.dt_in, n); }
 size_t job_out_bytes(const Job& j, size_t n) { return j.cmd == Cmd::Requant ? storage_bytes(j.dt_in, n) : storage_bytes(j.dt_out, n); }
 
-int launch_job(const Job& j, const void* in, void* out, size_t n, const LaunchCfg& cfg) {
+// e0: index of the first element of this launch in the caller's tensor (host-pointer chunks)
+int launch_job(const Job& j, const void* in, void* out, size_t n, const LaunchCfg& cfg0, size_t e0 = 0) {
+    LaunchCfg cfg = cfg0;
+    cfg.sr_key = j.sr_key;
+    cfg.sr_base = static_cast<int64_t>(e0);
     switch (j.cmd) {
         case Cmd::Quant: return launch_quantize(in, j.dt_in, out, j.dt_out, static_cast<int64_t>(n), j.P, j.mode, cfg, j.dP);
         case Cmd::Dequant: return launch_dequantize(in, j.dt_in, out, j.dt_out, static_cast<int64_t>(n), j.P, j.op, cfg, j.dP);
@@ -374,7 +387,7 @@ void run_staged(Context& c, DeviceState& d, const Job& j, bool in_host, bool out
         }
         PQ_CUDA_CHECK(cudaEventRecord(d.ev_h2d[k], d.s_h2d));
         PQ_CUDA_CHECK(cudaStreamWaitEvent(d.s_run, d.ev_h2d[k], 0));
-        c.launches += launch_job(j, k_in, k_out, n, cfg);
+        c.launches += launch_job(j, k_in, k_out, n, cfg, e0);
         PQ_CUDA_CHECK(cudaEventRecord(d.ev_run[k], d.s_run));
         if (out_host) {
             PQ_CUDA_CHECK(cudaStreamWaitEvent(d.s_d2h, d.ev_run[k], 0));
@@ -561,12 +574,14 @@ extern "C" void piquant_quantize(piquant_context_t* ctx, const void* in, piquant
     // reference src/piquant.cpp:288-289
     pq_assert(dtype_is_float(dtype_in), "input dtype (%s) must be a dequantized type", dtype_name(dtype_in));
     pq_assert(dtype_is_quant(dtype_out), "output dtype (%s) must be a quantized type", dtype_name(dtype_out));
-    pq_assert(mode == PIQUANT_NEAREST || mode == PIQUANT_STOCHASTIC, "invalid round mode %d", static_cast<int>(mode));
+    pq_assert(mode == PIQUANT_NEAREST || mode == PIQUANT_STOCHASTIC || mode == PIQUANT_CUDA_STOCHASTIC_PER_ELEMENT,
+              "invalid round mode %d", static_cast<int>(mode));
     if (numel == 0) return;
     check_float_ptr(in, dtype_in, "input");
     pq_assert(out != nullptr, "output pointer must not be NULL");
     const float xi = mode == PIQUANT_STOCHASTIC ? c->draw_xi() : 0.0f;
     Job j{Cmd::Quant, in, dtype_in, out, dtype_kernel_view(dtype_out), numel, make_params(scale, zero_point, xi, dtype_out), static_cast<int>(mode), OP_SET};
+    if (mode == PIQUANT_CUDA_STOCHASTIC_PER_ELEMENT) j.sr_key = c->draw_sr_key();
     run_job(*c, j);
 }
 
@@ -644,6 +659,14 @@ extern "C" void piquant_cuda_seed(piquant_context_t* ctx, uint64_t seed) { as_ct
 
 extern "C" float piquant_cuda_last_stochastic_threshold(piquant_context_t* ctx) { return as_ctx(ctx)->last_xi; }
 
+extern "C" void piquant_cuda_set_sr_key(piquant_context_t* ctx, uint64_t key) {
+    Context* c = as_ctx(ctx);
+    c->sr_key_fixed = true;
+    c->sr_key = key;
+}
+extern "C" void piquant_cuda_clear_sr_key(piquant_context_t* ctx) { as_ctx(ctx)->sr_key_fixed = false; }
+extern "C" uint64_t piquant_cuda_last_sr_key(piquant_context_t* ctx) { return as_ctx(ctx)->last_sr_key; }
+
 extern "C" void piquant_cuda_requantize(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in_out, void* out,
                                         piquant_dtype_t quant_dtype, size_t numel, float scale, int64_t zero_point,
                                         piquant_round_mode_t mode, piquant_reduce_op_t op) {
@@ -651,6 +674,7 @@ extern "C" void piquant_cuda_requantize(piquant_context_t* ctx, const void* in, 
     // reference src/piquant.cpp:353-354
     pq_assert(dtype_is_float(dtype_in_out), "input dtype must be a dequantized type");
     pq_assert(dtype_is_quant(quant_dtype), "quant dtype must be a quantized type");
+    pq_assert(mode == PIQUANT_NEAREST || mode == PIQUANT_STOCHASTIC, "invalid round mode %d for requantize", static_cast<int>(mode));
     if (numel == 0) return;
     check_float_ptr(in, dtype_in_out, "input");
     check_float_ptr(out, dtype_in_out, "output");
@@ -779,7 +803,8 @@ extern "C" void piquant_cuda_quantize_meta_async(piquant_context_t* ctx, const v
     DeviceGuard guard(dc.cur, dc.device);
     DeviceState& d = c->dev_state(dc.device);
     const float xi = mode == PIQUANT_STOCHASTIC ? c->draw_xi() : 0.0f;
-    const LaunchCfg cfg = make_cfg(*c, d, c->stream);
+    LaunchCfg cfg = make_cfg(*c, d, c->stream);
+    if (mode == PIQUANT_CUDA_STOCHASTIC_PER_ELEMENT) cfg.sr_key = c->draw_sr_key();
     c->launches += launch_quantize(in, dtype_in, out, dtype_kernel_view(dtype_out), static_cast<int64_t>(numel), make_params(1.0f, 0, xi, dtype_out), static_cast<int>(mode),
                                    cfg, &reinterpret_cast<const DeviceMeta*>(d_meta)->P);
 }
@@ -823,7 +848,8 @@ extern "C" void piquant_cuda_quantize_auto(piquant_context_t* ctx, const void* i
     const size_t in_bytes = numel * static_cast<size_t>(dtype_bits(dtype_in) / 8);
     compute_meta_async(*c, d, in, dtype_in, numel, dtype_out, d.d_meta, d.h_meta_dev, in_bytes <= (size_t(96) << 20));
     const float xi = mode == PIQUANT_STOCHASTIC ? c->draw_xi() : 0.0f;
-    const LaunchCfg cfg = make_cfg(*c, d, c->stream);
+    LaunchCfg cfg = make_cfg(*c, d, c->stream);
+    if (mode == PIQUANT_CUDA_STOCHASTIC_PER_ELEMENT) cfg.sr_key = c->draw_sr_key();
     c->launches += launch_quantize(in, dtype_in, out, dtype_kernel_view(dtype_out), static_cast<int64_t>(numel), make_params(1.0f, 0, xi, dtype_out), static_cast<int>(mode),
                                    cfg, &d.d_meta->P);
     PQ_CUDA_CHECK(cudaStreamSynchronize(c->stream));         // the ONE host sync of the whole sequence

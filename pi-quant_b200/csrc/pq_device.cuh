@@ -28,7 +28,7 @@ namespace pq {
 // so every rounding and corner case of the unsigned kernels (and their parity with the reference) carries over.
 enum : int { DT_F32 = 0, DT_BF16 = 1, DT_U2 = 2, DT_U4 = 3, DT_U8 = 4, DT_I2 = 5, DT_I4 = 6, DT_I8 = 7 };
 // which per-element formula a quantize cell uses
-enum : int { STEP_BODY = 0, STEP_ROUND64 = 1, STEP_STOCH = 2 };
+enum : int { STEP_BODY = 0, STEP_ROUND64 = 1, STEP_STOCH = 2, STEP_SRPE = 3 };   // SRPE: per-element stochastic rounding (extension)
 enum : int { OP_SET = 0, OP_ADD = 1 };
 
 struct QuantParams {
@@ -257,7 +257,62 @@ template <int STEP>
 __device__ __forceinline__ int32_t quant_step(float x, const QuantParams& P, int32_t qmax) {
     if constexpr (STEP == STEP_BODY) return quant_step_body(x, P.inv_scale, P.zp32, qmax);
     else if constexpr (STEP == STEP_ROUND64) return quant_step_round64(x, P, qmax);
-    else return quant_step_stochastic(x, P, qmax);
+    else { static_assert(STEP == STEP_STOCH, "STEP_SRPE goes through quant_step_srpe"); return quant_step_stochastic(x, P, qmax); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-element stochastic rounding (extension, include/piquant_cuda.h: PIQUANT_CUDA_STOCHASTIC_PER_ELEMENT)
+//
+//   q_i = clamp(floor(x_i / scale + u_i) + zp, 0, qmax),   u_i = (k_i + 1/2) * 2^-16,
+//   k_i = 16 bits of Philox4x32-10(counter = {i / 8, 0, 0, 0} (64-bit i / 8 in the first two words), key = the call's 64-bit key):
+//         element i takes bits [16 * (i % 2), +16) of output word (i % 8) / 2.
+// E[q_i] = x_i / scale + zp inside the range -- unbiased per element, which the reference's one-threshold-per-call mode
+// (src/piquant.cpp:199-201) is not.  x / scale is RN(x * (1.0f / scale)) like every other mode.
+// ------------------------------------------------------------------------------------------------
+
+// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; Random123): 10 rounds of
+//   {c0, c1, c2, c3} <- {hi(M1*c2) ^ c1 ^ k0, lo(M1*c2), hi(M0*c0) ^ c3 ^ k1, lo(M0*c0)},  key += {W0, W1} per round.
+// 2 IMAD.WIDE + 2 LOP3 per round; the round keys are uniform (key + r * W), so they cost nothing per element.
+struct PhiloxKey { uint32_t k0, k1; };
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, PhiloxKey key, uint32_t (&out)[4]) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = static_cast<unsigned long long>(M0) * c0;
+        const unsigned long long p1 = static_cast<unsigned long long>(M1) * c2;
+        const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ (key.k0 + static_cast<uint32_t>(r) * W0);
+        const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ (key.k1 + static_cast<uint32_t>(r) * W1);
+        c1 = static_cast<uint32_t>(p1);
+        c3 = static_cast<uint32_t>(p0);
+        c0 = n0;
+        c2 = n2;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// 1 + u for the 16 random bits in half `hi` of `r`: the float 1.0 + (k + 1/2) * 2^-16, built in the mantissa (one PRMT / LOP3)
+__device__ __forceinline__ float srpe_one_plus_u(uint32_t r, int hi) {
+    const uint32_t k = hi ? (r >> 16) : (r & 0xffffu);
+    return __uint_as_float(0x3f800040u | (k << 7));
+}
+
+// exact step, any input: floor(p + u) in double (p + 1 + u needs < 53 bits while |p| < 2^23; beyond that p is an integer,
+// floor(p + u) == p, and NaN / inf / |p| >= 2^63 take the x86 conversion result like the other int64 formulas)
+__device__ __forceinline__ int32_t quant_step_srpe(float x, const QuantParams& P, int32_t qmax, float one_plus_u) {
+    const float p = __fmul_rn(x, P.inv_scale);
+    long long t;
+    if (fabsf(p) < 8388608.0f) t = __double2ll_rd(static_cast<double>(p) + static_cast<double>(one_plus_u)) - 1;
+    else t = x86_cvtt_i64(p);
+    const long long q = static_cast<long long>(static_cast<unsigned long long>(t) + static_cast<unsigned long long>(P.zp64));
+    return static_cast<int32_t>(q < 0 ? 0ll : (q > static_cast<long long>(qmax) ? static_cast<long long>(qmax) : q));
+}
+
+// speculative step: floor(RM(p + (1 + u))) == floor(p + 1 + u) (an integer k <= y stays <= RM(y)); the "- 1" is folded into
+// the zero point by the caller.  FMUL, FADD.RM, F2I.FLOOR: exact for |p| < 2^22.
+__device__ __forceinline__ int32_t quant_spec_srpe(float x, const QuantParams& P, float one_plus_u, float& witness) {
+    const float p = __fmul_rn(x, P.inv_scale);
+    witness = p;
+    return __float2int_rd(__fadd_rd(p, one_plus_u));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -327,13 +382,13 @@ __device__ __forceinline__ int32_t quant_spec(float x, const QuantParams& P, flo
 
 // largest |witness| for which quant_spec<STEP> followed by a 32-bit zero-point add is exact
 template <int STEP>
-__device__ __forceinline__ constexpr float quant_spec_limit() { return 1073741824.0f; }
+__device__ __forceinline__ constexpr float quant_spec_limit() { return STEP == STEP_SRPE ? 4194304.0f : 1073741824.0f; }
 
 // STEP_STOCH speculation also needs the threshold where the ceil identity holds (a context never passes anything else)
 template <int STEP>
 __device__ __forceinline__ bool quant_spec_params_ok(const QuantParams& P) {
     if constexpr (STEP == STEP_BODY) return P.spec_ok32 != 0;
-    else if constexpr (STEP == STEP_ROUND64) return P.bigzp == 0;
+    else if constexpr (STEP == STEP_ROUND64 || STEP == STEP_SRPE) return P.bigzp == 0;
     else return P.bigzp == 0 && P.xi >= 0.0f && P.xi < 1.0f;
 }
 
@@ -361,9 +416,11 @@ __device__ __forceinline__ float requant_spec(float x, const QuantParams& P, flo
 
 // Quantize the NE elements held in w[] (f32: one per word, bf16: two per word) and pack them,
 // element 0 in the lowest bits, into o[NE*BITS/32 words] (at least one word; unused high bits are 0).
+// STEP_SRPE: rnd[] holds the 16 random bits of element e in half (e & 1) of word e / 2 (unused otherwise).
 template <int IN_DT, int BITS, int STEP, int NW>
 __device__ __forceinline__ void quant_group(const uint32_t (&w)[NW], const QuantParams& P,
-                                            uint32_t (&o)[(NW * (IN_DT == DT_F32 ? 1 : 2) * BITS + 31) / 32]) {
+                                            uint32_t (&o)[(NW * (IN_DT == DT_F32 ? 1 : 2) * BITS + 31) / 32],
+                                            const uint32_t (&rnd)[NW * (IN_DT == DT_F32 ? 1 : 2) / 2]) {
     constexpr int NE = NW * (IN_DT == DT_F32 ? 1 : 2);
     constexpr int OW = (NE * BITS + 31) / 32;
     constexpr int EPW = 32 / BITS;                      // elements per output word
@@ -372,10 +429,14 @@ __device__ __forceinline__ void quant_group(const uint32_t (&w)[NW], const Quant
     int32_t t[NE];
     float wit[NE];
 #pragma unroll
-    for (int e = 0; e < NE; ++e) t[e] = quant_spec<STEP>(item_elem<IN_DT, NW>(w, e), P, wit[e]);
+    for (int e = 0; e < NE; ++e) {
+        if constexpr (STEP == STEP_SRPE) t[e] = quant_spec_srpe(item_elem<IN_DT, NW>(w, e), P, srpe_one_plus_u(rnd[e >> 1], e & 1), wit[e]);
+        else t[e] = quant_spec<STEP>(item_elem<IN_DT, NW>(w, e), P, wit[e]);
+    }
     float m = 0.0f;
 #pragma unroll
     for (int e = 0; e < NE; e += 2) m = max3_abs_nan(m, wit[e], wit[e + 1]);
+    const int32_t zp_add = STEP == STEP_SRPE ? P.zp32 - 1 : P.zp32;      // SRPE: the speculative step is floor(p + 1 + u)
     if (quant_spec_params_ok<STEP>(P) && m < quant_spec_limit<STEP>()) {
 #pragma unroll
         for (int j = 0; j < OW; ++j) {
@@ -383,7 +444,7 @@ __device__ __forceinline__ void quant_group(const uint32_t (&w)[NW], const Quant
             constexpr int LAST = EPW < NE ? EPW : NE;
 #pragma unroll
             for (int k = LAST - 2; k >= 0; k -= 2)
-                d = pack_sat2<BITS>(t[j * EPW + k + 1] + P.zp32, t[j * EPW + k] + P.zp32, d);
+                d = pack_sat2<BITS>(t[j * EPW + k + 1] + zp_add, t[j * EPW + k] + zp_add, d);
             o[j] = d;
         }
     } else {
@@ -391,7 +452,9 @@ __device__ __forceinline__ void quant_group(const uint32_t (&w)[NW], const Quant
         for (int j = 0; j < OW; ++j) o[j] = 0u;
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
-            const uint32_t q = static_cast<uint32_t>(quant_step<STEP>(item_elem<IN_DT, NW>(w, e), P, QMAX));
+            uint32_t q;
+            if constexpr (STEP == STEP_SRPE) q = static_cast<uint32_t>(quant_step_srpe(item_elem<IN_DT, NW>(w, e), P, QMAX, srpe_one_plus_u(rnd[e >> 1], e & 1)));
+            else q = static_cast<uint32_t>(quant_step<STEP>(item_elem<IN_DT, NW>(w, e), P, QMAX));
             o[(e * BITS) / 32] |= q << ((e * BITS) % 32);
         }
     }
@@ -399,6 +462,14 @@ __device__ __forceinline__ void quant_group(const uint32_t (&w)[NW], const Quant
     constexpr uint32_t LAST_VALID = (NE * BITS) % 32 == 0 ? 0xffffffffu : ((1u << ((NE * BITS) % 32)) - 1u);
 #pragma unroll
     for (int j = 0; j < OW; ++j) o[j] ^= P.sign_xor & (j == OW - 1 ? LAST_VALID : 0xffffffffu);
+}
+
+template <int IN_DT, int BITS, int STEP, int NW>
+__device__ __forceinline__ void quant_group(const uint32_t (&w)[NW], const QuantParams& P,
+                                            uint32_t (&o)[(NW * (IN_DT == DT_F32 ? 1 : 2) * BITS + 31) / 32]) {
+    static_assert(STEP != STEP_SRPE, "per-element stochastic rounding needs the random words");
+    const uint32_t none[NW * (IN_DT == DT_F32 ? 1 : 2) / 2] = {};
+    quant_group<IN_DT, BITS, STEP, NW>(w, P, o, none);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -17,6 +17,8 @@ struct LaunchCfg {
     int          sm_count;   // 148 on B200; sizes the resident grids of the persistent (TMA ring, byte-granular) kernels
     int          variant;    // 0 = auto, 1 = direct LDG/STG kernels, 2 = TMA (cp.async.bulk) ring kernels
     unsigned long long* sched;   // {next tile, finished CTAs}: work counter of the persistent TMA kernels, zero between launches
+    uint64_t     sr_key = 0;     // per-element stochastic rounding (mode 2): Philox key of the call
+    int64_t      sr_base = 0;    // ... and the index of this launch's element 0 in the caller's tensor (host-pointer chunks)
 };
 
 // [[noreturn]] abort with a red message on stderr -- the reference's error convention
@@ -106,7 +108,8 @@ inline size_t storage_bytes(int dt, size_t numel) {
 QuantParams make_params(float scale, int64_t zero_point, float xi, int dt_quant = DT_U8);
 
 // Device pointers (or device-accessible mapped host pointers) only.  All launches are asynchronous
-// on cfg.stream.  `mode`: 0 nearest, 1 stochastic (P.xi).  Returns the number of kernels launched.
+// on cfg.stream.  `mode`: 0 nearest, 1 stochastic (P.xi), 2 per-element stochastic (quantize only; cfg.sr_key / sr_base).
+// Returns the number of kernels launched.
 int launch_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int mode,
                     const LaunchCfg& cfg, const QuantParams* device_params = nullptr);
 int launch_dequantize(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int op,

@@ -40,6 +40,27 @@ __device__ __forceinline__ void store_packed(uint8_t* p, const uint32_t* o) {
         asm volatile("st.global.L1::no_allocate.b16 [%0], %1;" ::"l"(p), "h"(static_cast<uint16_t>(o[0])) : "memory");
     }
 }
+
+// One 32-byte vector (8 f32 / 16 bf16 elements) -> packed words; `group` = index of its first element / 8 (STEP_SRPE only:
+// one Philox4x32-10 call per 8 elements, 16 random bits each).
+template <int IN_DT, int BITS, int STEP>
+__device__ __forceinline__ void quant_vector(const QuantArgs& a, int64_t group, const uint32_t (&w)[8],
+                                             uint32_t (&o)[((IN_DT == DT_F32 ? 8 : 16) * BITS + 31) / 32]) {
+    if constexpr (STEP == STEP_SRPE) {
+        constexpr int NG = IN_DT == DT_F32 ? 1 : 2;
+        uint32_t rnd[4 * NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            uint32_t r[4];
+            srpe_words(a, group + g, r);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rnd[4 * g + k] = r[k];
+        }
+        quant_group<IN_DT, BITS, STEP, 8>(w, a.P, o, rnd);
+    } else {
+        quant_group<IN_DT, BITS, STEP, 8>(w, a.P, o);
+    }
+}
 }  // namespace
 
 template <int IN_DT, int BITS, int STEP>
@@ -56,6 +77,8 @@ __global__ void __launch_bounds__(kThreads) quant_stream_kernel(const QuantArgs 
     uint8_t* out = a.out + a.head_bytes;
     const int64_t n_vecs = a.n_items * 16 / OB;
     const int64_t n_tiles = (n_vecs + TILE - 1) / TILE;
+    // STEP_SRPE: Philox counter (= element index / 8) of vector 0; the host guarantees that vectors start on multiples of 8
+    [[maybe_unused]] const int64_t vec_group0 = (a.sr_base + a.head_bytes * PER) >> 3;
     pdl_launch_dependents();
     pdl_wait();
     load_device_params(a);
@@ -72,7 +95,7 @@ __global__ void __launch_bounds__(kThreads) quant_stream_kernel(const QuantArgs 
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 uint32_t o[(OB + 3) / 4];
-                quant_group<IN_DT, BITS, STEP, 8>(w[j], a.P, o);
+                quant_vector<IN_DT, BITS, STEP>(a, vec_group0 + (first + static_cast<int64_t>(j) * kThreads) * (EV / 8), w[j], o);
                 store_packed<OB>(out + (first + static_cast<int64_t>(j) * kThreads) * OB, o);
             }
         } else {
@@ -82,7 +105,7 @@ __global__ void __launch_bounds__(kThreads) quant_stream_kernel(const QuantArgs 
                 if (v < n_vecs) {
                     ldg_stream(in + v * 32, w[j]);
                     uint32_t o[(OB + 3) / 4];
-                    quant_group<IN_DT, BITS, STEP, 8>(w[j], a.P, o);
+                    quant_vector<IN_DT, BITS, STEP>(a, vec_group0 + v * (EV / 8), w[j], o);
                     store_packed<OB>(out + v * OB, o);
                 }
             }
@@ -149,7 +172,8 @@ static void launch_cell(const QuantArgs& a0, bool vec, const LaunchCfg& cfg) {
 
 template <int IN_DT, int BITS>
 static void launch_mode(const QuantArgs& a, int mode, bool vec, const LaunchCfg& cfg) {
-    if (mode == 1) launch_cell<IN_DT, BITS, STEP_STOCH>(a, vec, cfg);
+    if (mode == 2) launch_cell<IN_DT, BITS, STEP_SRPE>(a, vec, cfg);
+    else if (mode == 1) launch_cell<IN_DT, BITS, STEP_STOCH>(a, vec, cfg);
     else if (IN_DT == DT_F32 && BITS == 2) launch_cell<IN_DT, BITS, STEP_ROUND64>(a, vec, cfg);   // no SIMD body in the reference: quantize.inl:132-148
     else launch_cell<IN_DT, BITS, STEP_BODY>(a, vec, cfg);
 }
@@ -178,6 +202,8 @@ int launch_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t nu
     a.P = P;
     a.dP = dP;
     a.sched = nullptr;           // the direct kernels are scheduled by the hardware, one tile per CTA
+    a.sr_key = PhiloxKey{static_cast<uint32_t>(cfg.sr_key), static_cast<uint32_t>(cfg.sr_key >> 32)};
+    a.sr_base = cfg.sr_base;
     const int64_t full_bytes = numel / per;                      // bytes whose elements all exist
     int64_t head = static_cast<int64_t>((16 - (reinterpret_cast<uintptr_t>(out) & 15u)) & 15u);
     if (head > full_bytes) head = full_bytes;
@@ -185,7 +211,16 @@ int launch_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t nu
     a.n_items = (full_bytes - head) / 16;
     const uintptr_t in_vec = reinterpret_cast<uintptr_t>(in) + static_cast<uintptr_t>(head) * per * isz;
     const bool a16 = a.n_items > 0 && (in_vec & 15u) == 0;      // what cp.async.bulk needs
-    const bool a32 = a.n_items > 0 && (in_vec & 31u) == 0;      // what LDG.256 needs
+    bool a32 = a.n_items > 0 && (in_vec & 31u) == 0;            // what LDG.256 needs
+    if (mode == 2) {
+        // per-element stochastic rounding: direct kernels only, and the vector kernel only when every vector starts on a
+        // multiple of 8 elements of the caller's tensor (one Philox call per 8 elements); the byte kernel serves the rest
+        pq_assert((cfg.sr_base & 7) == 0, "sr_base must be a multiple of 8");
+        if ((head * per) % 8 != 0) a32 = false;
+        if (dt_in == DT_F32) launch_out<DT_F32>(a, dt_out, mode, a32, cfg);
+        else launch_out<DT_BF16>(a, dt_out, mode, a32, cfg);
+        return 1;
+    }
     // variant 0 = per-cell choice from measurements on B200 (profiles/); 1 = direct, 2 = TMA where alignment allows
     const int64_t traffic = numel * isz + numel / per;
     const bool want_tma = cfg.variant == 2 || (cfg.variant == 0 && quantize_prefers_tma(dt_in, dt_out, mode, traffic)) || !a32;

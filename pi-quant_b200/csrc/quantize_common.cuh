@@ -14,7 +14,14 @@ struct QuantArgs {
     QuantParams P;
     const QuantParams* dP;   // not null: the parameters were produced on the device (params_kernel) and are read from there
     unsigned long long* sched;   // TMA kernels: {next tile, finished CTAs} (LaunchCfg::sched)
+    PhiloxKey   sr_key;      // STEP_SRPE: key of this call
+    int64_t     sr_base;     // STEP_SRPE: index of element 0 of this launch in the caller's tensor (multiple of 8; host-pointer chunks)
 };
+
+// STEP_SRPE: the 4 Philox words that hold the random bits of elements [8g, 8g + 8) of the caller's tensor
+__device__ __forceinline__ void srpe_words(const QuantArgs& a, int64_t g, uint32_t (&r)[4]) {
+    philox4x32_10(static_cast<uint32_t>(g), static_cast<uint32_t>(static_cast<uint64_t>(g) >> 32), 0u, 0u, a.sr_key, r);
+}
 
 // Parameters computed by an earlier kernel on the stream replace the by-value ones (the per-call stochastic
 // threshold always comes from the host).  Call after pdl_wait().
@@ -39,11 +46,20 @@ __device__ __forceinline__ void quant_one_byte(const QuantArgs& a, int64_t b) {
     constexpr int PER = 8 / BITS;
     constexpr int QMAX = (1 << BITS) - 1;
     uint32_t byte = 0, present = 0;
+    [[maybe_unused]] uint32_t rnd[4];
+    if constexpr (STEP == STEP_SRPE) srpe_words(a, (a.sr_base + b * PER) >> 3, rnd);      // a byte never straddles a group of 8
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
         const int64_t e = b * PER + k;
         if (e < a.numel) {
-            byte |= static_cast<uint32_t>(quant_step<STEP>(load_elem<IN_DT>(a.in, e), a.P, QMAX)) << (k * BITS);
+            uint32_t q;
+            if constexpr (STEP == STEP_SRPE) {
+                const int j = static_cast<int>((a.sr_base + e) & 7);
+                q = static_cast<uint32_t>(quant_step_srpe(load_elem<IN_DT>(a.in, e), a.P, QMAX, srpe_one_plus_u(rnd[j >> 1], j & 1)));
+            } else {
+                q = static_cast<uint32_t>(quant_step<STEP>(load_elem<IN_DT>(a.in, e), a.P, QMAX));
+            }
+            byte |= q << (k * BITS);
             present |= static_cast<uint32_t>(QMAX) << (k * BITS);
         }
     }

@@ -23,6 +23,9 @@ from piquant._bootstrap import C, ffi
 class RoundMode(Enum):
     NEAREST = C.PIQUANT_NEAREST
     STOCHASTIC = C.PIQUANT_STOCHASTIC
+    # extension of the B200 build (include/piquant_cuda.h): every element gets its own Philox4x32-10 random number
+    # instead of the reference's one threshold per call; quantize only
+    STOCHASTIC_PER_ELEMENT = 2
 
 
 @unique
@@ -164,6 +167,17 @@ class Context:
     def set_stochastic_threshold(self, xi: Optional[float]) -> None:
         """Fix the per-call stochastic threshold (None: draw a fresh one per call, like the reference)."""
         C.piquant_cuda_set_stochastic_threshold(self._ctx, -1.0 if xi is None else xi)
+
+    def set_sr_key(self, key: Optional[int]) -> None:
+        """Per-element stochastic rounding: use this 64-bit Philox key for every following call; None draws one per call again."""
+        if key is None:
+            C.piquant_cuda_clear_sr_key(self._ctx)
+        else:
+            C.piquant_cuda_set_sr_key(self._ctx, key & 0xFFFFFFFFFFFFFFFF)
+
+    @property
+    def last_sr_key(self) -> int:
+        return int(C.piquant_cuda_last_sr_key(self._ctx))
 
     def seed(self, seed: int) -> None:
         C.piquant_cuda_seed(self._ctx, seed)

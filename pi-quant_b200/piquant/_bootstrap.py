@@ -53,6 +53,9 @@ void  piquant_cuda_requantize(piquant_context_t* ctx, const void* in, piquant_dt
 void  piquant_cuda_minmax_async(piquant_context_t* ctx, const void* x, piquant_dtype_t dtype, size_t n, float* out4);
 void  piquant_cuda_params_from_minmax(float min, float max, piquant_dtype_t target_quant_dtype,
                                       float* out_scale, int64_t* out_zero_point);
+void  piquant_cuda_set_sr_key(piquant_context_t* ctx, uint64_t key);
+void  piquant_cuda_clear_sr_key(piquant_context_t* ctx);
+uint64_t piquant_cuda_last_sr_key(piquant_context_t* ctx);
 int   piquant_cuda_nccl_unique_id(void* out128);
 void  piquant_cuda_comm_init_rank(piquant_context_t* ctx, const void* unique_id128, int nranks, int rank);
 void  piquant_cuda_comm_destroy(piquant_context_t* ctx);

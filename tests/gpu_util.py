@@ -12,7 +12,7 @@ from oracle.port import BF16, F32, INT2, INT4, INT8, UINT2, UINT4, UINT8, packed
 
 DT = {F32: DataType.F32, BF16: DataType.BF16, UINT2: DataType.UINT2, UINT4: DataType.UINT4, UINT8: DataType.UINT8,
       INT2: DataType.INT2, INT4: DataType.INT4, INT8: DataType.INT8}
-MODE = {0: RoundMode.NEAREST, 1: RoundMode.STOCHASTIC}
+MODE = {0: RoundMode.NEAREST, 1: RoundMode.STOCHASTIC, 2: RoundMode.STOCHASTIC_PER_ELEMENT}
 OP = {0: ReduceOp.SET, 1: ReduceOp.ADD}
 CANARY = 0xCD
 _BASE: dict = {}
@@ -66,6 +66,14 @@ class Gpu:
         torch.cuda.synchronize()
         check_canary(d_out)
         return to_host(d_out, np.uint8)
+
+    def quantize_sr(self, x: np.ndarray, dt_out: int, scale: float, zp: int, key: int, in_off: int = 0, out_off: int = 0) -> np.ndarray:
+        """per-element stochastic rounding (extension), Philox key `key`"""
+        self.ctx.set_sr_key(key)
+        try:
+            return self.quantize(x, dt_out, scale, zp, mode=2, in_off=in_off, out_off=out_off)
+        finally:
+            self.ctx.set_sr_key(None)
 
     def dequantize(self, q: np.ndarray, dt_in: int, numel: int, dt_out: int, scale: float, zp: int, op: int = 0,
                    prev: np.ndarray | None = None, in_off: int = 0, out_off: int = 0) -> np.ndarray:

@@ -69,14 +69,14 @@ def main() -> None:
     def report(name, bytes_per_elem, t, variant):
         gbs = bytes_per_elem * n / t / 1e9
         rows.append((name, variant, n / t / 1e9, gbs, gbs / PEAK))
-        print(f"{name:34s} v{variant}  {t*1e3:9.3f} ms  {n/t/1e9:9.1f} Gelem/s  {gbs:8.1f} GB/s  {gbs/PEAK*100:6.1f}% of measured {PEAK:.0f}", flush=True)
+        print(f"{name:44s} v{variant}  {t*1e3:9.3f} ms  {n/t/1e9:9.1f} Gelem/s  {gbs:8.1f} GB/s  {gbs/PEAK*100:6.1f}% of measured {PEAK:.0f}", flush=True)
 
     for variant in [int(v) for v in a.variants.split(",")]:
         ctx.set_kernel_variant(variant)
         for din, x in ((D.F32, xf), (D.BF16, xb)):
             isz = 4 if din == D.F32 else 2
             for dq in (D.UINT8, D.UINT4, D.UINT2):
-                for mode in (RoundMode.NEAREST, RoundMode.STOCHASTIC):
+                for mode in (RoundMode.NEAREST, RoundMode.STOCHASTIC, RoundMode.STOCHASTIC_PER_ELEMENT):
                     name = f"quant {din.name}->{dq.name} {mode.name.lower()}"
                     if a.cells != "all" and a.cells not in name:
                         continue
