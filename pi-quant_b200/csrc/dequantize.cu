@@ -13,6 +13,11 @@
 
 namespace pq {
 
+#ifndef PQ_DEQUANT_U
+#define PQ_DEQUANT_U 2
+#endif
+constexpr int kDequantItemsPerThread = PQ_DEQUANT_U;
+
 template <int BITS, int OUT_DT, int OP, bool A32>
 __global__ void __launch_bounds__(kThreads) dequant_stream_kernel(const DequantArgs a_in) {
     DequantArgs a = a_in;
@@ -22,7 +27,7 @@ __global__ void __launch_bounds__(kThreads) dequant_stream_kernel(const DequantA
     constexpr int IB = V * BITS / 8;                    // packed input bytes per item: 4..32
     constexpr int NWI = IB / 4;
     constexpr int NWO = 16;
-    constexpr int U = 2;
+    constexpr int U = kDequantItemsPerThread;
     constexpr uint32_t QMAX = (1u << BITS) - 1u;
     constexpr int64_t TILE = static_cast<int64_t>(kThreads) * U;
 
@@ -141,7 +146,7 @@ static void launch_cell(const void* in, void* out, int64_t numel, const QuantPar
     int64_t blocks_needed;
     if (vec) {
         fn = a32 ? dequant_stream_kernel<BITS, OUT_DT, OP, true> : dequant_stream_kernel<BITS, OUT_DT, OP, false>;
-        const int64_t tile = static_cast<int64_t>(kThreads) * 2;
+        const int64_t tile = static_cast<int64_t>(kThreads) * kDequantItemsPerThread;
         blocks_needed = (a.n_items + tile - 1) / tile;
     } else {
         fn = dequant_bytes_kernel<BITS, OUT_DT, OP>;

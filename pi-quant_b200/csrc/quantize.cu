@@ -11,7 +11,9 @@
 //            memory (8 cache lines = 8 L1 wavefronts).  [Measured on B200: giving each thread
 //            64-256 contiguous bytes instead makes one instruction touch 16-32 lines and the L1
 //            wavefront rate, not HBM, bounds the kernel: 36 % of peak for f32->u4.]
-//   tile   = kThreads * 4 vectors: every thread has 4 x 32 B of loads in flight before it converts.
+//   tile   = kThreads * 2 vectors (16 KiB of input): every thread has 2 x 32 B of loads in flight before it converts.
+//            [Measured: 4 vectors per thread cost registers (48 -> 40, 5 -> 6 CTAs per SM) and tail granularity: equal at
+//            f32->u8 @1e9, 2-11 % slower on the bf16 cells and at 27 M elements; 1 vector per thread is 4-40 % slower.]
 //   pack   = the 8/16 elements of a vector become 2..16 packed bytes in registers (quant_group: clamp
 //            and pack fused in I2IP) and leave with one STG.{16,32,64,128}; a warp's stores are
 //            contiguous, full sectors.
@@ -24,7 +26,10 @@
 namespace pq {
 
 namespace {
-constexpr int kVecPerThread = 4;
+#ifndef PQ_VEC_PER_THREAD
+#define PQ_VEC_PER_THREAD 2
+#endif
+constexpr int kVecPerThread = PQ_VEC_PER_THREAD;   // 2 x 32 B of loads in flight per thread: measured against 1 and 4, profiles/r1_vectors_per_thread_sweep.txt
 
 template <int OB>
 __device__ __forceinline__ void store_packed(uint8_t* p, const uint32_t* o) {

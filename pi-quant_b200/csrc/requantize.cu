@@ -16,6 +16,11 @@
 
 namespace pq {
 
+#ifndef PQ_REQUANT_U
+#define PQ_REQUANT_U 4
+#endif
+constexpr int kRequantItemsPerThread = PQ_REQUANT_U;
+
 struct RequantArgs {
     const char* in;
     char*       out;
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(kThreads) requant_stream_kernel(const RequantA
     RequantArgs a = a_in;
     constexpr int ISZ = DT == DT_F32 ? 4 : 2;
     constexpr int EPI = 32 / ISZ;
-    constexpr int U = 4;
+    constexpr int U = kRequantItemsPerThread;
     constexpr int64_t TILE = static_cast<int64_t>(kThreads) * U;
     const char* in = a.in + a.head * ISZ;
     char* out = a.out + a.head * ISZ;
@@ -181,7 +186,7 @@ static void launch_cell(RequantArgs a, int32_t qmax, bool vec, const LaunchCfg& 
     auto fn = vec ? requant_stream_kernel<DT, STEP, OP> : requant_scalar_kernel<DT, STEP, OP>;
     int64_t blocks_needed;
     if (vec) {
-        const int64_t tile = static_cast<int64_t>(kThreads) * 4;
+        const int64_t tile = static_cast<int64_t>(kThreads) * kRequantItemsPerThread;
         blocks_needed = (a.n_items + tile - 1) / tile;
     } else {
         a.head = 0;

@@ -34,6 +34,9 @@ def bench(fn_of_i, k: int, reps: int) -> float:
 
 
 def main() -> None:
+    global SIZES
+    if len(sys.argv) > 2 and sys.argv[1] == "--sizes":
+        SIZES = [int(v) for v in sys.argv[2].split(",")]
     torch.cuda.set_device(0)
     ctx = piquant.Context()
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
