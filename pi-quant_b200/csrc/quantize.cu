@@ -78,41 +78,37 @@ __global__ void __launch_bounds__(kThreads) quant_stream_kernel(const QuantArgs 
     constexpr int J = kVecPerThread;
     constexpr int64_t TILE = static_cast<int64_t>(kThreads) * J;
 
-    const char* in = a.in + a.head_bytes * PER * ISZ;
-    uint8_t* out = a.out + a.head_bytes;
-    const int64_t n_vecs = a.n_items * 16 / OB;
-    const int64_t n_tiles = (n_vecs + TILE - 1) / TILE;
+    const char* in = a.in_body;
+    uint8_t* out = a.out_body;
     // STEP_SRPE: Philox counter (= element index / 8) of vector 0; the host guarantees that vectors start on multiples of 8
     [[maybe_unused]] const int64_t vec_group0 = (a.sr_base + a.head_bytes * PER) >> 3;
     pdl_launch_dependents();
     pdl_wait();
     load_device_params(a);
 
-    // ONE tile per CTA: the hardware CTA scheduler deals tiles to whichever SM is free.  (A persistent grid with a
-    // static tile -> CTA map waits for its slowest SM -- the two dies differ by ~10 % -- and measured 7 % slower:
-    // profiles/r1_sched_probe_static_vs_dynamic_tiles.txt.)
-    if (const int64_t tile = blockIdx.x; tile < n_tiles) {
-        const int64_t first = tile * TILE + threadIdx.x;
-        uint32_t w[J][8];
-        if (tile * TILE + TILE <= n_vecs) {
+    // ONE tile per CTA (grid == number of tiles): the hardware CTA scheduler deals tiles to whichever SM is free.  (A
+    // persistent grid with a static tile -> CTA map waits for its slowest SM -- the two dies differ by ~10 % -- and measured
+    // 7 % slower: profiles/r1_sched_probe_static_vs_dynamic_tiles.txt.)
+    const int64_t first = static_cast<int64_t>(blockIdx.x) * TILE + threadIdx.x;
+    uint32_t w[J][8];
+    if (blockIdx.x < a.n_full_tiles) {
 #pragma unroll
-            for (int j = 0; j < J; ++j) ldg_stream(in + (first + static_cast<int64_t>(j) * kThreads) * 32, w[j]);
+        for (int j = 0; j < J; ++j) ldg_stream(in + (first + static_cast<int64_t>(j) * kThreads) * 32, w[j]);
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
+        for (int j = 0; j < J; ++j) {
+            uint32_t o[(OB + 3) / 4];
+            quant_vector<IN_DT, BITS, STEP>(a, vec_group0 + (first + static_cast<int64_t>(j) * kThreads) * (EV / 8), w[j], o);
+            store_packed<OB>(out + (first + static_cast<int64_t>(j) * kThreads) * OB, o);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int64_t v = first + static_cast<int64_t>(j) * kThreads;
+            if (v < a.n_vecs) {
+                ldg_stream(in + v * 32, w[j]);
                 uint32_t o[(OB + 3) / 4];
-                quant_vector<IN_DT, BITS, STEP>(a, vec_group0 + (first + static_cast<int64_t>(j) * kThreads) * (EV / 8), w[j], o);
-                store_packed<OB>(out + (first + static_cast<int64_t>(j) * kThreads) * OB, o);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const int64_t v = first + static_cast<int64_t>(j) * kThreads;
-                if (v < n_vecs) {
-                    ldg_stream(in + v * 32, w[j]);
-                    uint32_t o[(OB + 3) / 4];
-                    quant_vector<IN_DT, BITS, STEP>(a, vec_group0 + v * (EV / 8), w[j], o);
-                    store_packed<OB>(out + v * OB, o);
-                }
+                quant_vector<IN_DT, BITS, STEP>(a, vec_group0 + v * (EV / 8), w[j], o);
+                store_packed<OB>(out + v * OB, o);
             }
         }
     }
@@ -155,7 +151,12 @@ static void launch_cell(const QuantArgs& a0, bool vec, const LaunchCfg& cfg) {
     if (vec) {
         fn = quant_stream_kernel<IN_DT, BITS, STEP>;
         const int64_t tile = static_cast<int64_t>(kThreads) * kVecPerThread;
-        blocks_needed = (a.n_items * 16 / OB + tile - 1) / tile;
+        a.n_vecs = a.n_items * 16 / OB;
+        blocks_needed = (a.n_vecs + tile - 1) / tile;
+        pq_assert(blocks_needed < (int64_t{1} << 31), "tensor too large for one launch (%lld tiles)", static_cast<long long>(blocks_needed));
+        a.n_full_tiles = static_cast<uint32_t>(a.n_vecs / tile);
+        a.in_body = a.in + a.head_bytes * PER * (IN_DT == DT_F32 ? 4 : 2);
+        a.out_body = a.out + a.head_bytes;
     } else {
         fn = quant_bytes_kernel<IN_DT, BITS, STEP>;
         a.head_bytes = 0;

@@ -14,6 +14,12 @@ struct QuantArgs {
     QuantParams P;
     const QuantParams* dP;   // not null: the parameters were produced on the device (params_kernel) and are read from there
     unsigned long long* sched;   // TMA kernels: {next tile, finished CTAs} (LaunchCfg::sched)
+    // direct stream kernel only, precomputed on the host so that the per-thread prologue stays short (2 vectors per thread
+    // leave little to amortise it over): the vectorised region and how many CTAs own a full tile
+    const char* in_body;     // in + head_bytes * elements-per-byte * sizeof(input element)
+    uint8_t*    out_body;    // out + head_bytes
+    int64_t     n_vecs;      // 32-byte input vectors in the region
+    uint32_t    n_full_tiles;
     PhiloxKey   sr_key;      // STEP_SRPE: key of this call
     int64_t     sr_base;     // STEP_SRPE: index of element 0 of this launch in the caller's tensor (multiple of 8; host-pointer chunks)
 };
