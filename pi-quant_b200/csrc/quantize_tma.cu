@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(kTmaThreads) quant_tma_kernel(const QuantArgs 
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kConsumers / 32); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kConsumers); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -111,8 +111,10 @@ __global__ void __launch_bounds__(kTmaThreads) quant_tma_kernel(const QuantArgs 
 #pragma unroll
             for (int j = 0; j < NV; ++j) v[j] = (j * kConsumers + t < vecs) ? src[j * kConsumers + t] : make_uint4(0u, 0u, 0u, 0u);
         }
-        __syncwarp();
-        if ((t & 31) == 0) mbar_arrive(empty + s);      // this warp is done with the input stage
+        // every consumer thread releases the input stage itself.  (One elected arrive per warp after __syncwarp() is
+        // equivalent in the PTX memory model but compute-sanitizer's racecheck does not chain the two and reported the
+        // stage reuse as a hazard; with per-thread arrives it reports none -- and the kernel measured 0-7 % faster.)
+        mbar_arrive(empty + s);
 #pragma unroll
         for (int j = 0; j < NV; j += 2) {                // two vectors per speculative group
             const uint32_t w[8] = {v[j].x, v[j].y, v[j].z, v[j].w, v[j + 1].x, v[j + 1].y, v[j + 1].z, v[j + 1].w};

@@ -11,7 +11,7 @@ import numpy as np
 
 from gpu_util import Gpu
 from oracle import port
-from oracle.port import ADD, BF16, F32, SET, UINT2, UINT4, UINT8, f32_to_bf16_bits, packed_bytes
+from oracle.port import ADD, BF16, F32, INT4, INT8, SET, UINT2, UINT4, UINT8, f32_to_bf16_bits, packed_bytes
 
 rng = np.random.default_rng(0)
 for variant in (1, 2):
@@ -23,6 +23,9 @@ for variant in (1, 2):
             for dq in (UINT8, UINT4, UINT2):
                 s, z = g.compute_quant_params(xin, dq)
                 assert (s, z) == port.compute_quant_params(xin, dq)
+                if variant == 1:      # per-element stochastic rounding (extension), direct kernels: vector and byte-granular paths
+                    for out_off in (0, 3):
+                        assert np.array_equal(g.quantize_sr(xin, dq, s, z, 77, out_off=out_off), port.quantize_sr(xin, dq, s, z, 77))
                 for mode in (0, 1):
                     q = g.quantize(xin, dq, s, z, mode, xi=0.3)
                     assert np.array_equal(q, port.quantize(xin, dq, s, z, mode, xi=0.3))
@@ -34,4 +37,11 @@ for variant in (1, 2):
                     assert np.array_equal(y, port.dequantize(q, dq, n, dt_out, s, z, op, out=prev.copy()))
                     r = g.requantize(xin, dq, s, z, 0, None, op, prev=prev)
                     assert np.array_equal(r, port.requantize(xin, dq, s, z, 0, 0.0, op, out=prev.copy()))
+    # signed extension dtypes
+    for sdt in (INT8, INT4):
+        x = rng.uniform(-1, 1, 70_001).astype(np.float32)
+        s, z = g.compute_quant_params(x, sdt)
+        q = g.quantize(x, sdt, s, z)
+        assert np.array_equal(q, port.quantize(x, sdt, s, z))
+        assert np.array_equal(g.dequantize(q, sdt, x.size, F32, s, z), port.dequantize(q, sdt, x.size, F32, s, z))
 print("sanitize probe ok")
