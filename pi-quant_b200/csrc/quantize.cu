@@ -21,6 +21,9 @@
 //   ragged = output bytes before the 16-byte aligned region and after the last full vector are
 //            produced byte-by-byte by the last CTA of the same launch (no second kernel).
 // Inputs whose alignment rules out vector loads go through the byte-granular kernel.
+#include <cmath>
+#include <cstring>
+
 #include "quantize_common.cuh"
 
 namespace pq {
@@ -68,8 +71,10 @@ __device__ __forceinline__ void quant_vector(const QuantArgs& a, int64_t group, 
 }
 }  // namespace
 
+// 8 CTAs per SM = 32 registers per thread: what the speculative path of every cell needs (bf16 stochastic wanted 39-40
+// for its exact fallback and ran at 6 CTAs per SM); the Philox cells keep their 58-76 registers.
 template <int IN_DT, int BITS, int STEP>
-__global__ void __launch_bounds__(kThreads) quant_stream_kernel(const QuantArgs a_in) {
+__global__ void __launch_bounds__(kThreads, STEP == STEP_SRPE ? 1 : 8) quant_stream_kernel(const QuantArgs a_in) {
     QuantArgs a = a_in;
     constexpr int PER = 8 / BITS;                       // elements per packed byte
     constexpr int ISZ = IN_DT == DT_F32 ? 4 : 2;
@@ -121,6 +126,183 @@ __global__ void __launch_bounds__(kThreads) quant_stream_kernel(const QuantArgs 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// bf16 -> 2-bit by threshold compares.
+//
+// At 2.25 bytes per element the exact per-element steps (7-8 instructions, one of them an XU-pipe conversion) leave this
+// cell bound by instruction issue, not by HBM, whenever the 1 kW cap holds the SMs near 1.5 GHz (87 % of the copy peak).
+// But a 2-bit quantizer is a step function with three steps, and -- for a positive scale and away from the wrap-around of
+// the int32 add -- a monotone one: x -> RN(x * inv) -> RN(. +- 0.5) -> trunc -> + zp -> clamp never decreases (the stochastic
+// step trunc(r) + sign * [xi < frac] with its one threshold per call is monotone too).  So q(x) = #{k : x >= T_k} with three
+// bf16 thresholds T_1 <= T_2 <= T_3, found on the host by bisection over the ordered bf16 values with a bit-exact host
+// replica of the step (quant_thresholds below) -- and bf16 compares come two per instruction:
+//   PRMT (pair element e with element e + 8), 3 x HSET2.BF16.GE, 3 x HADD2.BF16 (count), IMAD.SHL + LOP3 (place) per TWO
+//   elements, plus 1/2 HMNMX2.|abs|.NaN per element for the witness "every |x| <= X" (X = where |x * inv| reaches 2^29; NaN, inf and
+//   huge values fail it and the vector is redone by the exact steps): ~4 instructions per element instead of 7-8, no XU.
+// Exhaustively checked against the oracle over all 65536 bf16 inputs (tests/test_gpu_parity.py).
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t bf16x2_ge_one(uint32_t a, uint32_t b) {       // bf16 1.0 per half where a >= b, else 0.0
+    uint32_t d;
+    asm("set.ge.bf16x2.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t bf16x2_add(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t bf16x2_max_abs_nan(uint32_t a, uint32_t b) {  // magnitudes: max(|a|, |b|) per half, NaN wins
+    uint32_t d;
+    asm("max.NaN.xorsign.abs.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+// The compares (HSET2), the pairing permute, the witness (HMNMX2) and the final merge all run on the half-rate ALU pipe,
+// which a first version with mask-valued compares saturated (80 % ALU, FMA pipe idle: profiles/r1_ncu_bf16_u2_threshold_kernel.txt).
+// So the count of passed thresholds is formed ARITHMETICALLY on the FMA pipe: the compares return bf16 1.0 / 0.0,
+// 128.0 + s3 + s2 + s1 is exact in bf16 (ulp 1 in [128, 256)) and carries the count in the two lowest mantissa bits of each
+// half; one integer multiply (IMAD.SHL, FMA pipe too) moves both fields to their place and one LOP3 merges them:
+// per pair of elements 5 ALU-pipe + 4 FMA-pipe instructions instead of 7 ALU-pipe ones.
+template <int STEP>
+__device__ __forceinline__ uint32_t quant_vector_bf16_u2_thr(const QuantArgs& a, const uint32_t (&w)[8]) {
+    uint32_t mx = bf16x2_max_abs_nan(w[0], w[1]);
+#pragma unroll
+    for (int k = 2; k < 8; ++k) mx = bf16x2_max_abs_nan(mx, w[k]);
+    mx &= 0x7fff7fffu;
+    uint32_t o;
+    if ((mx & 0xffffu) <= a.thr_xlim && (mx >> 16) <= a.thr_xlim) {
+        o = 0u;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            // low half: element e, high half: element e + 8 -> their fields sit at bits 2e and 16 + 2e
+            const uint32_t v = __byte_perm(w[e >> 1], w[(e >> 1) + 4], (e & 1) ? 0x7632u : 0x5410u);
+            uint32_t cnt = bf16x2_add(bf16x2_ge_one(v, a.thr[2]), 0x43004300u);      // 128.0 + [x >= T3]
+            cnt = bf16x2_add(cnt, bf16x2_ge_one(v, a.thr[1]));
+            cnt = bf16x2_add(cnt, bf16x2_ge_one(v, a.thr[0]));
+            o |= (cnt << (2 * e)) & (0x00030003u << (2 * e));
+        }
+        o ^= a.P.sign_xor;
+    } else {
+        uint32_t oo[1];
+        quant_group<DT_BF16, 2, STEP, 8>(w, a.P, oo);
+        o = oo[0];
+    }
+    return o;
+}
+
+// 8 CTAs per SM (32 registers): the fast path needs no more, and the rarely taken exact fallback may spill
+template <int STEP>
+__global__ void __launch_bounds__(kThreads, 8) quant_bf16_u2_threshold_kernel(const QuantArgs a_in) {
+    QuantArgs a = a_in;
+    constexpr int J = kVecPerThread;
+    constexpr int64_t TILE = static_cast<int64_t>(kThreads) * J;
+    const char* in = a.in_body;
+    uint8_t* out = a.out_body;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t first = static_cast<int64_t>(blockIdx.x) * TILE + threadIdx.x;
+    uint32_t w[J][8];
+    if (blockIdx.x < a.n_full_tiles) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) ldg_stream(in + (first + static_cast<int64_t>(j) * kThreads) * 32, w[j]);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const uint32_t o[1] = {quant_vector_bf16_u2_thr<STEP>(a, w[j])};
+            store_packed<4>(out + (first + static_cast<int64_t>(j) * kThreads) * 4, o);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int64_t v = first + static_cast<int64_t>(j) * kThreads;
+            if (v < a.n_vecs) {
+                ldg_stream(in + v * 32, w[j]);
+                const uint32_t o[1] = {quant_vector_bf16_u2_thr<STEP>(a, w[j])};
+                store_packed<4>(out + v * 4, o);
+            }
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1) {
+        const int64_t total = (a.numel + 3) / 4;
+        for (int64_t b = threadIdx.x; b < a.head_bytes; b += kThreads) quant_one_byte<DT_BF16, 2, STEP>(a, b);
+        for (int64_t b = a.head_bytes + a.n_items * 16 + threadIdx.x; b < total; b += kThreads) quant_one_byte<DT_BF16, 2, STEP>(a, b);
+    }
+}
+
+// ---- host side of the threshold kernel: a bit-exact replica of the two steps (x86-64 SSE float arithmetic is IEEE, the
+// library is compiled with -ffp-contract=off) used ONLY to place the three thresholds; no data goes through it.
+namespace {
+inline float host_bf16(uint32_t bits16) {
+    const uint32_t u = bits16 << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+// q in the unsigned kernel view, valid while |x * inv| < 2^29, |zp| <= 2^29 (the caller guarantees both)
+inline int32_t host_step_u2(float x, const QuantParams& P, int mode) {
+    volatile float p = x * P.inv_scale;
+    long long t;
+    if (mode == 1) {                                    // quantize.inl:8-19
+        const float r = p;
+        const float tr = truncf(r);
+        volatile float diff = r - tr;
+        const float dec = fabsf(diff);
+        float adj = (P.xi < dec) ? 1.0f : 0.0f;
+        if (r < 0.0f) adj = -adj;
+        volatile float sum = tr + adj;
+        t = static_cast<long long>(sum);
+    } else {                                            // kernels_specialized.inl:57-82 (one SIMD lane)
+        volatile float a = p + copysignf(0.5f, p);
+        t = static_cast<long long>(truncf(a));
+    }
+    const long long q = t + P.zp64;
+    return static_cast<int32_t>(q < 0 ? 0 : (q > 3 ? 3 : q));
+}
+}  // namespace
+
+// Fills a.thr / a.thr_xlim; false when the step function is not known to be monotone (then the generic kernel runs).
+static bool quant_thresholds(QuantArgs& a, int mode) {
+    const QuantParams& P = a.P;
+    if (a.dP != nullptr) return false;                                  // parameters live on the device
+    if (!(P.inv_scale > 0.0f) || !std::isfinite(P.inv_scale) || !(P.scale > 0.0f) || !std::isfinite(P.scale)) return false;
+    if (P.bigzp || !P.spec_ok32) return false;
+    if (mode == 1 && !(P.xi >= 0.0f && P.xi < 1.0f)) return false;
+    if (mode != 0 && mode != 1) return false;
+    // X: the largest bf16 magnitude (bit pattern, finite) with |x * inv| < 2^29; magnitudes are ordered like their bits
+    uint32_t lo = 0, hi = 0x7f7f;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) / 2;
+        volatile float p = host_bf16(mid) * P.inv_scale;
+        if (p < 536870912.0f) lo = mid; else hi = mid - 1;
+    }
+    const uint32_t X = lo;
+    if (X == 0) return false;
+    // zero of either sign and every denormal must quantize alike: then no threshold falls inside (-2^-126, 2^-126) and the
+    // compares do not depend on how the hardware treats signed zeros or denormal operands
+    const int32_t q0 = host_step_u2(host_bf16(0u), P, mode);
+    if (host_step_u2(host_bf16(0x8000u), P, mode) != q0 || host_step_u2(host_bf16(0x807fu), P, mode) != q0 ||
+        host_step_u2(host_bf16(0x007fu), P, mode) != q0 || X < 0x0080u)
+        return false;
+    // ordered values: index i in [0, 2X]: i < X -> -(X - i), i >= X -> +(i - X)
+    const auto at = [&](uint32_t i) { return i < X ? (0x8000u | (X - i)) : (i - X); };
+    for (int k = 1; k <= 3; ++k) {
+        uint32_t bits;
+        if (host_step_u2(host_bf16(at(0)), P, mode) >= k) bits = 0xff80u;              // every x in the domain passes: -inf
+        else if (host_step_u2(host_bf16(at(2 * X)), P, mode) < k) bits = 0x7f80u;      // none does: +inf
+        else {
+            uint32_t l = 0, h = 2 * X;                  // q(at(l)) < k <= q(at(h))
+            while (h - l > 1) {
+                const uint32_t mid = l + (h - l) / 2;
+                if (host_step_u2(host_bf16(at(mid)), P, mode) >= k) h = mid; else l = mid;
+            }
+            bits = at(h);
+        }
+        a.thr[k - 1] = bits | (bits << 16);
+    }
+    a.thr_xlim = X;
+    return true;
+}
+
 // Any alignment: one thread per packed output byte (loads stay sector-coalesced through L1).
 template <int IN_DT, int BITS, int STEP>
 __global__ void __launch_bounds__(kThreads) quant_bytes_kernel(const QuantArgs a_in) {
@@ -150,6 +332,9 @@ static void launch_cell(const QuantArgs& a0, bool vec, const LaunchCfg& cfg) {
     int64_t blocks_needed;
     if (vec) {
         fn = quant_stream_kernel<IN_DT, BITS, STEP>;
+        if constexpr (IN_DT == DT_BF16 && BITS == 2 && (STEP == STEP_BODY || STEP == STEP_STOCH)) {
+            if (quant_thresholds(a, STEP == STEP_STOCH ? 1 : 0)) fn = quant_bf16_u2_threshold_kernel<STEP>;
+        }
         const int64_t tile = static_cast<int64_t>(kThreads) * kVecPerThread;
         a.n_vecs = a.n_items * 16 / OB;
         blocks_needed = (a.n_vecs + tile - 1) / tile;

@@ -20,6 +20,9 @@ struct QuantArgs {
     uint8_t*    out_body;    // out + head_bytes
     int64_t     n_vecs;      // 32-byte input vectors in the region
     uint32_t    n_full_tiles;
+    // bf16 -> 2-bit threshold kernel (quantize.cu): q(x) = #{k : x >= thr[k]} while |x| <= thr_xlim
+    uint32_t    thr[3];      // bf16 threshold k in both halves of the word
+    uint32_t    thr_xlim;    // largest |x| (bf16 bits) for which the three compares are the exact result
     PhiloxKey   sr_key;      // STEP_SRPE: key of this call
     int64_t     sr_base;     // STEP_SRPE: index of element 0 of this launch in the caller's tensor (multiple of 8; host-pointer chunks)
 };

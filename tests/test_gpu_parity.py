@@ -310,6 +310,31 @@ def test_quantize_stochastic_extreme_thresholds(gpu, cell):
             assert np.array_equal(got, want), f"xi={xi} scale={scale} zp={zp}: {np.flatnonzero(got != want)[:8]}"
 
 
+def test_bf16_to_2bit_exhaustive_over_all_65536_inputs(gpu0):
+    """bf16 -> uint2 / int2 runs on three threshold compares placed by the host (quantize.cu: quant_thresholds); the input
+    domain is small enough to try EVERY bf16 bit pattern: once grouped so that whole vectors stay inside the fast path's
+    domain (sorted by magnitude, then shuffled in blocks), once fully shuffled (NaN / inf / huge values in most vectors ->
+    exact fallback), for scales from 1e-3 to 123, zero points inside and outside the range, both rounding modes."""
+    from oracle.port import INT2
+    rng = np.random.default_rng(61)
+    allbits = np.arange(65536, dtype=np.uint16)
+    by_mag = allbits[np.argsort((allbits & 0x7FFF).astype(np.int64), kind="stable")]
+    blocks = by_mag.reshape(-1, 4096).copy()
+    for b in blocks:
+        rng.shuffle(b)
+    x = np.concatenate([blocks.reshape(-1), rng.permutation(allbits), by_mag[:40000], allbits[:12345]])
+    for dt_out in (UINT2, INT2):
+        for scale in (2.0 / 3.0, 0.5, 0.037, 1e-3, 123.456, 1.0, 3e-5):
+            for zp in (0, 1, 2, 3, -1, 5, -2):
+                for mode, xi in ((NEAREST, 0.0), (STOCHASTIC, 0.0), (STOCHASTIC, 0.3), (STOCHASTIC, 0.99999994)):
+                    with np.errstate(all="ignore"):
+                        want = port.quantize(x, dt_out, scale, zp, mode, xi=xi, semantics=SEM_BODY)
+                    got = gpu0.quantize(x, dt_out, scale, zp, mode, xi=xi)
+                    bad = np.flatnonzero(got != want)
+                    assert bad.size == 0, (f"dt={dt_out} scale={scale} zp={zp} mode={mode} xi={xi}: first bad byte {bad[:4]}, "
+                                           f"inputs {[hex(v) for v in x[bad[0] * 4: bad[0] * 4 + 4]]} got {got[bad[0]]:#x} want {want[bad[0]]:#x}")
+
+
 # ------------------------------------------------------------------------------------------------
 # min/max -> (scale, zero_point)
 # ------------------------------------------------------------------------------------------------
