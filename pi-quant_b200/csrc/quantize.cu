@@ -29,10 +29,16 @@
 namespace pq {
 
 namespace {
+#ifndef PQ_SRPE_F32_MINB
+#define PQ_SRPE_F32_MINB 4
+#endif
 #ifndef PQ_VEC_PER_THREAD
 #define PQ_VEC_PER_THREAD 2
 #endif
-constexpr int kVecPerThread = PQ_VEC_PER_THREAD;   // 2 x 32 B of loads in flight per thread: measured against 1 and 4, profiles/r1_vectors_per_thread_sweep.txt
+constexpr int kVecPerThread = PQ_VEC_PER_THREAD;
+// per-element stochastic rounding amortises its per-thread set-up (18 Philox round keys on the uniform datapath) over 4 vectors:
+// measured 98 % of the copy peak for f32->u8 against 75 % with 2
+template <int STEP> constexpr int kVecPerThreadOf = STEP == STEP_SRPE ? 4 : kVecPerThread;   // others: 2, measured against 1 and 4 (profiles/r1_vectors_per_thread_sweep.txt)
 
 template <int OB>
 __device__ __forceinline__ void store_packed(uint8_t* p, const uint32_t* o) {
@@ -72,15 +78,15 @@ __device__ __forceinline__ void quant_vector(const QuantArgs& a, int64_t group, 
 }  // namespace
 
 // 8 CTAs per SM = 32 registers per thread: what the speculative path of every cell needs (bf16 stochastic wanted 39-40
-// for its exact fallback and ran at 6 CTAs per SM); the Philox cells keep their 58-76 registers.
+// for its exact fallback and ran at 6 CTAs per SM); the Philox cells (4 vectors per thread) keep up to 85.
 template <int IN_DT, int BITS, int STEP>
-__global__ void __launch_bounds__(kThreads, STEP == STEP_SRPE ? 1 : 8) quant_stream_kernel(const QuantArgs a_in) {
+__global__ void __launch_bounds__(kThreads, STEP != STEP_SRPE ? 8 : (IN_DT == DT_F32 ? PQ_SRPE_F32_MINB : 3)) quant_stream_kernel(const QuantArgs a_in) {
     QuantArgs a = a_in;
     constexpr int PER = 8 / BITS;                       // elements per packed byte
     constexpr int ISZ = IN_DT == DT_F32 ? 4 : 2;
     constexpr int EV = 32 / ISZ;                        // elements per 32-byte vector
     constexpr int OB = EV * BITS / 8;                   // packed output bytes per vector: 2..16
-    constexpr int J = kVecPerThread;
+    constexpr int J = kVecPerThreadOf<STEP>;
     constexpr int64_t TILE = static_cast<int64_t>(kThreads) * J;
 
     const char* in = a.in_body;
@@ -335,7 +341,7 @@ static void launch_cell(const QuantArgs& a0, bool vec, const LaunchCfg& cfg) {
         if constexpr (IN_DT == DT_BF16 && BITS == 2 && (STEP == STEP_BODY || STEP == STEP_STOCH)) {
             if (quant_thresholds(a, STEP == STEP_STOCH ? 1 : 0)) fn = quant_bf16_u2_threshold_kernel<STEP>;
         }
-        const int64_t tile = static_cast<int64_t>(kThreads) * kVecPerThread;
+        const int64_t tile = static_cast<int64_t>(kThreads) * kVecPerThreadOf<STEP>;
         a.n_vecs = a.n_items * 16 / OB;
         blocks_needed = (a.n_vecs + tile - 1) / tile;
         pq_assert(blocks_needed < (int64_t{1} << 31), "tensor too large for one launch (%lld tiles)", static_cast<long long>(blocks_needed));

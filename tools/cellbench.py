@@ -109,6 +109,9 @@ def main() -> None:
             continue
         t = time_fn(lambda: ctx.requantize_ptr(x.data_ptr(), din, o.data_ptr(), D.UINT8, n, 2 / 255, 128), a.reps)
         report(name, 2 * (4 if din == D.F32 else 2), t, 0)
+        for mode, op, label in ((RoundMode.STOCHASTIC, ReduceOp.SET, "stochastic set"), (RoundMode.NEAREST, ReduceOp.ADD, "nearest add")):
+            t = time_fn(lambda: ctx.requantize_ptr(x.data_ptr(), din, o.data_ptr(), D.UINT8, n, 2 / 255, 128, mode, op), a.reps)
+            report(f"requant {din.name} via UINT8 {label}", (3 if op == ReduceOp.ADD else 2) * (4 if din == D.F32 else 2), t, 0)
     # torch copy for calibration of the peak on this very box
     t = time_fn(lambda: acc.copy_(xf), a.reps)
     report("torch copy_ f32 (calibration)", 8, t, 0)
