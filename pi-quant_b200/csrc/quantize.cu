@@ -29,9 +29,6 @@
 namespace pq {
 
 namespace {
-#ifndef PQ_SRPE_F32_MINB
-#define PQ_SRPE_F32_MINB 4
-#endif
 #ifndef PQ_VEC_PER_THREAD
 #define PQ_VEC_PER_THREAD 2
 #endif
@@ -78,9 +75,9 @@ __device__ __forceinline__ void quant_vector(const QuantArgs& a, int64_t group, 
 }  // namespace
 
 // 8 CTAs per SM = 32 registers per thread: what the speculative path of every cell needs (bf16 stochastic wanted 39-40
-// for its exact fallback and ran at 6 CTAs per SM); the Philox cells (4 vectors per thread) keep up to 85.
+// for its exact fallback and ran at 6 CTAs per SM); the Philox cells (4 vectors per thread) get what keeps their hot path free of spills: <= 85 (f32) / <= 128 (bf16).
 template <int IN_DT, int BITS, int STEP>
-__global__ void __launch_bounds__(kThreads, STEP != STEP_SRPE ? 8 : (IN_DT == DT_F32 ? PQ_SRPE_F32_MINB : 3)) quant_stream_kernel(const QuantArgs a_in) {
+__global__ void __launch_bounds__(kThreads, STEP != STEP_SRPE ? 8 : (IN_DT == DT_F32 ? 3 : 2)) quant_stream_kernel(const QuantArgs a_in) {
     QuantArgs a = a_in;
     constexpr int PER = 8 / BITS;                       // elements per packed byte
     constexpr int ISZ = IN_DT == DT_F32 ? 4 : 2;

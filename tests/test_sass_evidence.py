@@ -53,7 +53,33 @@ def test_blackwell_mnemonics_present(sass):
     assert count("HMMA") == 0 and count("UTC") == 0                          # elementwise path: no tensor-core instructions
 
 
-def test_no_kernel_uses_local_memory(sass):
-    """Streaming kernels must not spill: local-memory traffic (STL / LDL) would show up as extra DRAM bytes."""
-    local = re.findall(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?((?:STL|LDL)[A-Z0-9_.]*)", sass, flags=re.M)
-    assert not local, Counter(local)
+def test_no_kernel_uses_local_memory_outside_the_cold_fallbacks():
+    """Streaming kernels must not spill: local-memory traffic (STL / LDL) would show up as extra DRAM bytes.
+    The only stack frames allowed are the few bytes the EXACT FALLBACK of the bf16 stochastic kernels spills since those
+    kernels were capped at 32 registers (8 CTAs per SM): the fallback only runs for vectors holding
+    NaN / inf / huge values, the speculative path of the same kernels has no local-memory instruction."""
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(exe).exists():
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-res-usage", str(LIB)], capture_output=True, text=True, check=True).stdout
+    frames = dict(re.findall(r"Function (\S+):\s*\n\s*REG:\d+ STACK:(\d+)", out))
+    assert len(frames) > 100, "cuobjdump -res-usage output not understood"
+    allowed = re.compile(r"quant_stream_kernelILi1ELi[248]ELi2E|quant_bf16_u2_threshold_kernelILi2E")   # <bf16, *, stochastic>
+    for fn, stack in frames.items():
+        if allowed.search(fn):
+            assert int(stack) <= 64, (fn, stack)
+        else:
+            assert int(stack) == 0, (fn, stack)
+
+
+def test_speculative_paths_of_the_capped_kernels_do_not_touch_local_memory(sass):
+    """In the kernels that may spill, every STL / LDL sits in the exact fallback: none between the vector loads of a tile and
+    the first packed store that follows them."""
+    for fn in ("_ZN2pq19quant_stream_kernelILi1ELi4ELi2EEEvNS_9QuantArgsE", "_ZN2pq30quant_bf16_u2_threshold_kernelILi2EEEvNS_9QuantArgsE"):
+        body = sass.split(f"Function : {fn}")[1].split("Function :")[0]
+        ops = re.findall(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]+)", body, flags=re.M)
+        first_load = next(i for i, o in enumerate(ops) if o.startswith("LDG.E") and "256" in o)
+        bras = [i for i, o in enumerate(ops) if i > first_load and o == "BRA"]
+        fast_end = bras[1]      # loads, speculative steps, witness branch to the fallback, packing, jump over the fallback
+        assert not [o for o in ops[first_load:fast_end] if o.startswith(("STL", "LDL"))]
+        assert any(o.startswith(("I2IP", "HSET2")) for o in ops[first_load:fast_end])
