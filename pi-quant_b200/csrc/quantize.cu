@@ -32,10 +32,11 @@ namespace {
 #ifndef PQ_VEC_PER_THREAD
 #define PQ_VEC_PER_THREAD 2
 #endif
+// 32-byte vectors per thread: 2, measured against 1, 3 and 4 (profiles/r1_vectors_per_thread_sweep.txt).  Per-element
+// stochastic rounding amortises its per-thread set-up (18 Philox round keys on the uniform datapath) over 4: measured
+// 83-98 % of the copy peak for f32->u8 against 75 % with 2.
 constexpr int kVecPerThread = PQ_VEC_PER_THREAD;
-// per-element stochastic rounding amortises its per-thread set-up (18 Philox round keys on the uniform datapath) over 4 vectors:
-// measured 98 % of the copy peak for f32->u8 against 75 % with 2
-template <int STEP> constexpr int kVecPerThreadOf = STEP == STEP_SRPE ? 4 : kVecPerThread;   // others: 2, measured against 1 and 4 (profiles/r1_vectors_per_thread_sweep.txt)
+template <int STEP> constexpr int kVecPerThreadOf = STEP == STEP_SRPE ? 4 : kVecPerThread;
 
 template <int OB>
 __device__ __forceinline__ void store_packed(uint8_t* p, const uint32_t* o) {
