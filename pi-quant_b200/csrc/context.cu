@@ -150,6 +150,7 @@ struct Context {
     bool                       sr_key_fixed = false;      // per-element stochastic rounding (piquant_cuda.h)
     uint64_t                   sr_key = 0, last_sr_key = 0;
     std::mt19937_64            rng{std::random_device{}()};
+    std::mutex                 rng_mu;                    // the draws happen before the dispatch lock is taken
     std::mutex                 mu;
     std::map<int, DeviceState> devs;
     uint64_t                   launches = 0;
@@ -188,13 +189,16 @@ struct Context {
     }
 
     float draw_xi() {
-        // one threshold per call, U[0,1) (reference src/piquant.cpp:199-201)
+        // one threshold per call, U[0,1) (reference src/piquant.cpp:199-201; its generator is thread_local, here a lock
+        // keeps concurrent callers of one context off the shared one)
+        std::lock_guard<std::mutex> lock(rng_mu);
         last_xi = xi_fixed ? xi : std::uniform_real_distribution<float>{0.0f, 1.0f}(rng);
         return last_xi;
     }
 
     uint64_t draw_sr_key() {
         // one Philox key per call: fresh random bits for every element of every call, replayable after piquant_cuda_seed
+        std::lock_guard<std::mutex> lock(rng_mu);
         last_sr_key = sr_key_fixed ? sr_key : rng();
         return last_sr_key;
     }
@@ -655,7 +659,11 @@ extern "C" void piquant_cuda_set_stochastic_threshold(piquant_context_t* ctx, fl
     }
 }
 
-extern "C" void piquant_cuda_seed(piquant_context_t* ctx, uint64_t seed) { as_ctx(ctx)->rng.seed(seed); }
+extern "C" void piquant_cuda_seed(piquant_context_t* ctx, uint64_t seed) {
+    Context* c = as_ctx(ctx);
+    std::lock_guard<std::mutex> lock(c->rng_mu);
+    c->rng.seed(seed);
+}
 
 extern "C" float piquant_cuda_last_stochastic_threshold(piquant_context_t* ctx) { return as_ctx(ctx)->last_xi; }
 

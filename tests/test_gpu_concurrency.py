@@ -105,3 +105,39 @@ def test_many_streams_recycle_the_work_counter_table():
             q = pt.quantize(x, scale=2 / 255, zero_point=128, dtype=torch.uint8, ctx=ctx)
         st.synchronize()
         assert torch.equal(q, ref)
+
+
+def test_threads_sharing_one_context_draw_their_stochastic_numbers_safely():
+    """Stochastic calls from several threads on ONE context and one stream: the per-call threshold / Philox key comes from a
+    generator inside the context (the reference's is thread_local, src/piquant.cpp:194-195); concurrent draws must neither crash
+    nor hand out a torn value -- every output is consistent with SOME single threshold in [0, 1) resp. some key."""
+    import piquant
+    from piquant import DataType as D, RoundMode
+
+    ctx = piquant.Context()
+    errors: list = []
+    n = 200_000
+
+    def work(seed: int) -> None:
+        try:
+            x = torch.full((n,), 0.3, device="cuda")
+            q = torch.empty(n, dtype=torch.uint8, device="cuda")
+            for it in range(40):
+                mode = RoundMode.STOCHASTIC if it % 2 == 0 else RoundMode.STOCHASTIC_PER_ELEMENT
+                ctx.quantize_ptr(x.data_ptr(), D.F32, q.data_ptr(), D.UINT8, n, 1.0, 0, mode)
+                torch.cuda.synchronize()
+                lo, hi = int(q.min().item()), int(q.max().item())
+                if mode == RoundMode.STOCHASTIC and not (lo == hi and lo in (0, 1)):
+                    errors.append((seed, it, lo, hi))                  # one threshold per call: constant input -> constant output
+                if mode == RoundMode.STOCHASTIC_PER_ELEMENT and not (lo == 0 and hi == 1 and abs(q.float().mean().item() - 0.3) < 0.01):
+                    errors.append((seed, it, lo, hi, q.float().mean().item()))
+        except Exception as e:      # noqa: BLE001
+            errors.append((seed, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
+    assert ctx.kernel_launches == 6 * 40
