@@ -46,6 +46,9 @@ def main() -> None:
         "bf16u4s": lambda: ctx.quantize_ptr(xb.data_ptr(), D.BF16, q.data_ptr(), D.UINT4, n, 2 / 15, 8, RoundMode.STOCHASTIC),
         "bf16u2n": lambda: ctx.quantize_ptr(xb.data_ptr(), D.BF16, q.data_ptr(), D.UINT2, n, 2 / 3, 2, RoundMode.NEAREST),
         "bf16u2s": lambda: ctx.quantize_ptr(xb.data_ptr(), D.BF16, q.data_ptr(), D.UINT2, n, 2 / 3, 2, RoundMode.STOCHASTIC),
+        "f32u8pe": lambda: ctx.quantize_ptr(xf.data_ptr(), D.F32, q.data_ptr(), D.UINT8, n, 2 / 255, 128, RoundMode.STOCHASTIC_PER_ELEMENT),
+        "bf16u8pe": lambda: ctx.quantize_ptr(xb.data_ptr(), D.BF16, q.data_ptr(), D.UINT8, n, 2 / 255, 128, RoundMode.STOCHASTIC_PER_ELEMENT),
+        "f32i8n": lambda: ctx.quantize_ptr(xf.data_ptr(), D.F32, q.data_ptr(), D.INT8, n, 2 / 255, 0, RoundMode.NEAREST),
         "requant_bf16": lambda: ctx.requantize_ptr(xb.data_ptr(), D.BF16, ob.data_ptr(), D.UINT8, n, 2 / 255, 128),
     }
     for name in a.cells.split(","):
