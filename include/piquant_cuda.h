@@ -56,8 +56,8 @@ PIQUANT_EXPORT float piquant_cuda_last_stochastic_threshold(piquant_context_t* c
 
 /* ---- per-element stochastic rounding (extension) ------------------------------------------------
  * The reference's STOCHASTIC mode compares every element of a call with ONE threshold (reference src/piquant.cpp:199-201):
- * cheap, but every call is biased.  This mode is accepted as the `mode` of piquant_quantize, piquant_cuda_quantize_meta_async
- * and piquant_cuda_quantize_auto (not by requantize) and rounds every element with its own random number:
+ * cheap, but every call is biased.  This mode is accepted as the `mode` of piquant_quantize, piquant_cuda_quantize_meta_async,
+ * piquant_cuda_quantize_auto and piquant_cuda_requantize and rounds every element with its own random number:
  *
  *     q_i = clamp(floor(x_i / scale + u_i) + zero_point, qmin, qmax),      u_i = (k_i + 1/2) * 2^-16
  *     k_i = 16 bits of Philox4x32-10(counter = {lo32(i / 8), hi32(i / 8), 0, 0}, key = {lo32(key), hi32(key)}):

@@ -234,6 +234,21 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+/* one element: k = the 16 random bits of tensor index j, q = clamp(floor(p + (k + 1/2) / 65536) + zp, 0, qmax) */
+static int64_t sr_quant_value(float x, float inv, int64_t zero_point, int64_t qmax, const uint32_t key[2], int64_t j) {
+    const uint32_t ctr[4] = {(uint32_t)((uint64_t)j >> 3), (uint32_t)((uint64_t)j >> 35), 0u, 0u};
+    uint32_t r[4];
+    orc_philox4x32_10(ctr, key, r);
+    const uint32_t k = (r[(j & 7) >> 1] >> (16 * (int)(j & 1))) & 0xffffu;
+    const double u = ((double)k + 0.5) / 65536.0;
+    const float p = x * inv;
+    int64_t t;
+    if (fabsf(p) < 8388608.0f) t = (int64_t)floor((double)p + u);   /* exact: < 53 significant bits */
+    else t = x86_cvtt_i64(p);
+    int64_t q = wrap_add64(t, zero_point);
+    return q < 0 ? 0 : (q > qmax ? qmax : q);
+}
+
 int orc_quantize_sr(const void* in, int dt_in, void* out, int dt_out, int64_t numel,
                     float scale, int64_t zero_point, uint64_t key, int64_t base) {
     if (is_signed_quant(dt_out)) {
@@ -250,19 +265,37 @@ int orc_quantize_sr(const void* in, int dt_in, void* out, int dt_out, int64_t nu
     uint8_t* o = (uint8_t*)out;
     memset(o, 0, orc_packed_bytes(dt_out, (size_t)numel));
     for (int64_t i = 0; i < numel; ++i) {
-        const int64_t j = base + i;
-        const uint32_t ctr[4] = {(uint32_t)((uint64_t)j >> 3), (uint32_t)((uint64_t)j >> 35), 0u, 0u};
-        uint32_t r[4];
-        orc_philox4x32_10(ctr, k2, r);
-        const uint32_t k = (r[(j & 7) >> 1] >> (16 * (int)(j & 1))) & 0xffffu;
-        const double u = ((double)k + 0.5) / 65536.0;
-        const float p = load_fp(in, dt_in, i) * inv;
-        int64_t t;
-        if (fabsf(p) < 8388608.0f) t = (int64_t)floor((double)p + u);   /* exact: < 53 significant bits */
-        else t = x86_cvtt_i64(p);
-        int64_t q = wrap_add64(t, zero_point);
-        q = q < 0 ? 0 : (q > qmax ? qmax : q);
+        const int64_t q = sr_quant_value(load_fp(in, dt_in, i), inv, zero_point, qmax, k2, base + i);
         o[i / per] |= (uint8_t)(q << ((int)(i % per) * bits));
+    }
+    return 0;
+}
+
+/* requantize with the per-element rule: the quantized value as above, then the generic dequant_step of orc_requantize */
+int orc_requantize_sr(const void* in, int dt_inout, void* out, int dt_quant, int64_t numel,
+                      float scale, int64_t zero_point, uint64_t key, int64_t base, int reduce_op, int fma_add) {
+    if (is_signed_quant(dt_quant))
+        return orc_requantize_sr(in, dt_inout, out, unsigned_view(dt_quant), numel, scale,
+                                 wrap_add64(zero_point, 1ll << (bits_of(unsigned_view(dt_quant)) - 1)), key, base, reduce_op, fma_add);
+    if (!is_float(dt_inout) || !is_quant(dt_quant)) return -1;
+    const float inv = 1.0f / scale;
+    const int64_t qmax = qmax_of(dt_quant);
+    const uint32_t k2[2] = {(uint32_t)key, (uint32_t)(key >> 32)};
+    for (int64_t i = 0; i < numel; ++i) {
+        const int64_t q = sr_quant_value(load_fp(in, dt_inout, i), inv, zero_point, qmax, k2, base + i);
+        const int64_t d = wrap_sub64(q, zero_point);
+        if (dt_inout == ORC_F32) {
+            float* o = (float*)out + i;
+            if (reduce_op == ORC_ADD) *o = fma_add ? fmaf((float)d, scale, *o) : *o + (float)d * scale;
+            else *o = (float)d * scale;
+        } else {
+            uint16_t* o = (uint16_t*)out + i;
+            float a = orc_bf16_to_f32(orc_f32_to_bf16((float)d));
+            float sc = orc_bf16_to_f32(orc_f32_to_bf16(scale));
+            uint16_t r = orc_f32_to_bf16(a * sc);
+            if (reduce_op == ORC_ADD) r = orc_f32_to_bf16(orc_bf16_to_f32(*o) + orc_bf16_to_f32(r));
+            *o = r;
+        }
     }
     return 0;
 }

@@ -81,6 +81,9 @@ int orc_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t numel
  */
 int orc_quantize_sr(const void* in, int dt_in, void* out, int dt_out, int64_t numel,
                     float scale, int64_t zero_point, uint64_t key, int64_t base);
+/* fused quantize -> dequantize with the same per-element rule (the library's piquant_cuda_requantize with mode 2) */
+int orc_requantize_sr(const void* in, int dt_inout, void* out, int dt_quant, int64_t numel,
+                      float scale, int64_t zero_point, uint64_t key, int64_t base, int reduce_op, int fma_add);
 /* Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11) */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 

@@ -32,6 +32,7 @@ def lib() -> C.CDLL:
         L.orc_storage_bytes.argtypes = [i32, C.c_size_t]; L.orc_storage_bytes.restype = C.c_size_t
         L.orc_quantize.argtypes = [vp, i32, vp, i32, i64, f32, i64, i32, f32, i32, i32]; L.orc_quantize.restype = i32
         L.orc_quantize_sr.argtypes = [vp, i32, vp, i32, i64, f32, i64, C.c_uint64, i64]; L.orc_quantize_sr.restype = i32
+        L.orc_requantize_sr.argtypes = [vp, i32, vp, i32, i64, f32, i64, C.c_uint64, i64, i32, i32]; L.orc_requantize_sr.restype = i32
         L.orc_philox4x32_10.argtypes = [vp, vp, vp]; L.orc_philox4x32_10.restype = None
         L.orc_dequantize.argtypes = [vp, i32, vp, i32, i64, f32, i64, i32, i32, i32]; L.orc_dequantize.restype = i32
         L.orc_requantize.argtypes = [vp, i32, vp, i32, i64, f32, i64, i32, f32, i32, i32]; L.orc_requantize.restype = i32
@@ -98,6 +99,16 @@ def quantize_sr(x: np.ndarray, dt_out: int, scale: float, zero_point: int, key: 
     """Extension: per-element stochastic rounding (piquant_oracle.h), Philox key `key`, element 0 has index `base`."""
     out = np.zeros(packed_bytes(dt_out, x.size), dtype=np.uint8)
     rc = lib().orc_quantize_sr(_ptr(x), dtype_of(x), _ptr(out), dt_out, x.size, scale, zero_point, key & (2**64 - 1), base)
+    if rc != 0:
+        raise ValueError("invalid dtype combination")
+    return out
+
+
+def requantize_sr(x: np.ndarray, dt_quant: int, scale: float, zero_point: int, key: int, base: int = 0, op: int = SET,
+                  out: np.ndarray | None = None, fma_add: bool = True) -> np.ndarray:
+    if out is None:
+        out = np.zeros(x.size, dtype=x.dtype)
+    rc = lib().orc_requantize_sr(_ptr(x), dtype_of(x), _ptr(out), dt_quant, x.size, scale, zero_point, key & (2**64 - 1), base, op, int(fma_add))
     if rc != 0:
         raise ValueError("invalid dtype combination")
     return out

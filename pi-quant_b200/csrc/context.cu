@@ -682,12 +682,14 @@ extern "C" void piquant_cuda_requantize(piquant_context_t* ctx, const void* in, 
     // reference src/piquant.cpp:353-354
     pq_assert(dtype_is_float(dtype_in_out), "input dtype must be a dequantized type");
     pq_assert(dtype_is_quant(quant_dtype), "quant dtype must be a quantized type");
-    pq_assert(mode == PIQUANT_NEAREST || mode == PIQUANT_STOCHASTIC, "invalid round mode %d for requantize", static_cast<int>(mode));
+    pq_assert(mode == PIQUANT_NEAREST || mode == PIQUANT_STOCHASTIC || mode == PIQUANT_CUDA_STOCHASTIC_PER_ELEMENT,
+              "invalid round mode %d", static_cast<int>(mode));
     if (numel == 0) return;
     check_float_ptr(in, dtype_in_out, "input");
     check_float_ptr(out, dtype_in_out, "output");
     const float xi = mode == PIQUANT_STOCHASTIC ? c->draw_xi() : 0.0f;
     Job j{Cmd::Requant, in, dtype_in_out, out, dtype_kernel_view(quant_dtype), numel, make_params(scale, zero_point, xi, quant_dtype), static_cast<int>(mode), static_cast<int>(op)};
+    if (mode == PIQUANT_CUDA_STOCHASTIC_PER_ELEMENT) j.sr_key = c->draw_sr_key();
     run_job(*c, j);
 }
 

@@ -315,6 +315,14 @@ __device__ __forceinline__ int32_t quant_spec_srpe(float x, const QuantParams& P
     return __float2int_rd(__fadd_rd(p, one_plus_u));
 }
 
+// the same step with the result kept as a float (requantize): floor(p + u) for |p| < 2^22, +0.0 for a zero result.
+//   y = RM(p + (1 + u));  RM(y + 1.5*2^23) = 1.5*2^23 + floor(y)  (ulp 1 in [2^23, 2^24));  minus (1.5*2^23 + 1): exact.
+__device__ __forceinline__ float requant_spec_srpe(float x, const QuantParams& P, float one_plus_u, float& witness) {
+    const float p = __fmul_rn(x, P.inv_scale);
+    witness = p;
+    return __fadd_rn(__fadd_rd(__fadd_rd(p, one_plus_u), 12582912.0f), -12582913.0f);
+}
+
 // ------------------------------------------------------------------------------------------------
 // quantize, group form: the hot loop.
 //

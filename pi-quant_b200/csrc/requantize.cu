@@ -30,7 +30,18 @@ struct RequantArgs {
     QuantParams P;
     float       scale_bf16;   // scale rounded to bf16 and widened again
     const QuantParams* dP;    // not null: parameters produced on the device (params_kernel), read from there
+    PhiloxKey   sr_key;       // STEP_SRPE (per-element stochastic rounding): key of this call
+    int64_t     sr_base;      // ... and the index of element 0 of this launch in the caller's tensor (multiple of 8)
 };
+
+// STEP_SRPE: 1 + u of element `e` of the caller's tensor (one Philox call; the vector path shares a call between 8 elements)
+__device__ __forceinline__ float requant_one_plus_u(const RequantArgs& a, int64_t e) {
+    const int64_t j = a.sr_base + e;
+    uint32_t r[4];
+    philox4x32_10(static_cast<uint32_t>(j >> 3), static_cast<uint32_t>(static_cast<uint64_t>(j >> 3) >> 32), 0u, 0u, a.sr_key, r);
+    const int k = static_cast<int>(j & 7);
+    return srpe_one_plus_u(r[k >> 1], k & 1);
+}
 
 __device__ __forceinline__ void load_device_params(RequantArgs& a) {
     if (a.dP) {
@@ -42,8 +53,10 @@ __device__ __forceinline__ void load_device_params(RequantArgs& a) {
 }
 
 template <int DT, int STEP, int OP>
-__device__ __forceinline__ uint32_t requant_elem(float x, uint32_t prev_bits, const RequantArgs& a, int32_t qmax) {
-    const int32_t q = quant_step<STEP>(x, a.P, qmax);
+__device__ __forceinline__ uint32_t requant_elem(float x, uint32_t prev_bits, const RequantArgs& a, int32_t qmax, float one_plus_u = 0.0f) {
+    int32_t q;
+    if constexpr (STEP == STEP_SRPE) q = quant_step_srpe(x, a.P, qmax, one_plus_u);
+    else q = quant_step<STEP>(x, a.P, qmax);
     const float d = a.P.bigzp
         ? __ll2float_rn(static_cast<long long>(static_cast<unsigned long long>(static_cast<long long>(q)) - static_cast<unsigned long long>(a.P.zp64)))
         : static_cast<float>(q - a.P.zp32);
@@ -66,17 +79,30 @@ __device__ __forceinline__ uint32_t requant_elem(float x, uint32_t prev_bits, co
 // (huge values, NaN, extreme zero points, a threshold outside [0, 1)) redoes the vector with the exact per-element steps.
 template <int DT, int STEP, int OP>
 __device__ __forceinline__ void requant_vector(const uint32_t (&w)[8], const uint32_t (&p)[8], const RequantArgs& a, int32_t qmax,
-                                               uint32_t (&o)[8]) {
+                                               uint32_t (&o)[8], [[maybe_unused]] int64_t group) {
     constexpr int NE = DT == DT_F32 ? 8 : 16;
     float r[NE];
     float wit[NE];
+    [[maybe_unused]] uint32_t rnd[NE / 2];             // STEP_SRPE: 16 random bits per element, `group` = index of element 0 / 8
+    if constexpr (STEP == STEP_SRPE) {
 #pragma unroll
-    for (int e = 0; e < NE; ++e) r[e] = requant_spec<STEP>(item_elem<DT, 8>(w, e), a.P, wit[e]);
+        for (int g = 0; g < NE / 8; ++g) {
+            uint32_t t4[4];
+            philox4x32_10(static_cast<uint32_t>(group + g), static_cast<uint32_t>(static_cast<uint64_t>(group + g) >> 32), 0u, 0u, a.sr_key, t4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rnd[4 * g + k] = t4[k];
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        if constexpr (STEP == STEP_SRPE) r[e] = requant_spec_srpe(item_elem<DT, 8>(w, e), a.P, srpe_one_plus_u(rnd[e >> 1], e & 1), wit[e]);
+        else r[e] = requant_spec<STEP>(item_elem<DT, 8>(w, e), a.P, wit[e]);
+    }
     float m = 0.0f;
 #pragma unroll
     for (int e = 0; e < NE; e += 2) m = max3_abs_nan(m, wit[e], wit[e + 1]);
     const bool zp_ok = DT == DT_F32 ? (a.P.zp64 >= -4194304 && a.P.zp64 <= 4194304) : (a.P.zp64 >= 0 && a.P.zp64 <= 255);
-    const bool xi_ok = STEP != STEP_STOCH || (a.P.xi >= 0.0f && a.P.xi < 1.0f);
+    const bool xi_ok = STEP != STEP_STOCH || (a.P.xi >= 0.0f && a.P.xi < 1.0f);      // (STEP_SRPE has no threshold)
     if (zp_ok && xi_ok && m < 4194304.0f) {
         const float lo = __fsub_rn(0.0f, static_cast<float>(a.P.zp32));     // +0.0, not -0.0, for zp == 0
         const float hi = static_cast<float>(qmax - a.P.zp32);
@@ -104,10 +130,13 @@ __device__ __forceinline__ void requant_vector(const uint32_t (&w)[8], const uin
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             if constexpr (DT == DT_F32) {
-                o[k] = requant_elem<DT, STEP, OP>(__uint_as_float(w[k]), p[k], a, qmax);
+                const float u1 = STEP == STEP_SRPE ? srpe_one_plus_u(rnd[STEP == STEP_SRPE ? k >> 1 : 0], k & 1) : 0.0f;
+                o[k] = requant_elem<DT, STEP, OP>(__uint_as_float(w[k]), p[k], a, qmax, u1);
             } else {
-                const uint32_t lo = requant_elem<DT, STEP, OP>(bf16_lo(w[k]), p[k] & 0xffffu, a, qmax);
-                const uint32_t hi = requant_elem<DT, STEP, OP>(bf16_hi(w[k]), p[k] >> 16, a, qmax);
+                const float u_lo = STEP == STEP_SRPE ? srpe_one_plus_u(rnd[STEP == STEP_SRPE ? k : 0], 0) : 0.0f;
+                const float u_hi = STEP == STEP_SRPE ? srpe_one_plus_u(rnd[STEP == STEP_SRPE ? k : 0], 1) : 0.0f;
+                const uint32_t lo = requant_elem<DT, STEP, OP>(bf16_lo(w[k]), p[k] & 0xffffu, a, qmax, u_lo);
+                const uint32_t hi = requant_elem<DT, STEP, OP>(bf16_hi(w[k]), p[k] >> 16, a, qmax, u_hi);
                 o[k] = lo | (hi << 16);
             }
         }
@@ -119,11 +148,11 @@ __device__ __forceinline__ void requant_scalar(const RequantArgs& a, int64_t e, 
     if constexpr (DT == DT_F32) {
         const float x = __ldg(reinterpret_cast<const float*>(a.in) + e);
         uint32_t* o = reinterpret_cast<uint32_t*>(a.out) + e;
-        *o = requant_elem<DT, STEP, OP>(x, OP == OP_ADD ? *o : 0u, a, qmax);
+        *o = requant_elem<DT, STEP, OP>(x, OP == OP_ADD ? *o : 0u, a, qmax, STEP == STEP_SRPE ? requant_one_plus_u(a, e) : 0.0f);
     } else {
         const float x = bf16_bits_to_f32(__ldg(reinterpret_cast<const unsigned short*>(a.in) + e));
         uint16_t* o = reinterpret_cast<uint16_t*>(a.out) + e;
-        *o = static_cast<uint16_t>(requant_elem<DT, STEP, OP>(x, OP == OP_ADD ? *o : 0u, a, qmax));
+        *o = static_cast<uint16_t>(requant_elem<DT, STEP, OP>(x, OP == OP_ADD ? *o : 0u, a, qmax, STEP == STEP_SRPE ? requant_one_plus_u(a, e) : 0.0f));
     }
 }
 
@@ -158,7 +187,7 @@ __global__ void __launch_bounds__(kThreads) requant_stream_kernel(const RequantA
             const int64_t item = first + static_cast<int64_t>(u) * kThreads;
             if (item < a.n_items) {
                 uint32_t o[8];
-                requant_vector<DT, STEP, OP>(w[u], p[u], a, qmax, o);
+                requant_vector<DT, STEP, OP>(w[u], p[u], a, qmax, o, (a.sr_base + a.head + item * EPI) >> 3);
                 stg_stream(out + item * 32, o);
             }
         }
@@ -207,7 +236,10 @@ static void launch_cell(RequantArgs a, int32_t qmax, bool vec, const LaunchCfg& 
 
 template <int DT>
 static void launch_dt(const RequantArgs& a, int32_t qmax, int mode, int op, bool vec, const LaunchCfg& cfg) {
-    if (mode == 1) {
+    if (mode == 2) {
+        if (op == OP_ADD) launch_cell<DT, STEP_SRPE, OP_ADD>(a, qmax, vec, cfg);
+        else launch_cell<DT, STEP_SRPE, OP_SET>(a, qmax, vec, cfg);
+    } else if (mode == 1) {
         if (op == OP_ADD) launch_cell<DT, STEP_STOCH, OP_ADD>(a, qmax, vec, cfg);
         else launch_cell<DT, STEP_STOCH, OP_SET>(a, qmax, vec, cfg);
     } else {
@@ -242,7 +274,13 @@ int launch_requantize(const void* in, int dt_inout, void* out, int dt_quant, int
     if (head > numel) head = numel;
     a.head = head;
     a.n_items = (numel - head) / (32 / isz);
-    const bool vec = ((ia & 31u) == (oa & 31u)) && a.n_items > 0;
+    bool vec = ((ia & 31u) == (oa & 31u)) && a.n_items > 0;
+    a.sr_key = PhiloxKey{static_cast<uint32_t>(cfg.sr_key), static_cast<uint32_t>(cfg.sr_key >> 32)};
+    a.sr_base = cfg.sr_base;
+    if (mode == 2) {        // per-element stochastic rounding: a 32-byte item must start on a multiple of 8 elements of the tensor
+        pq_assert((cfg.sr_base & 7) == 0, "sr_base must be a multiple of 8");
+        if (head % 8 != 0) vec = false;
+    }
     const int32_t qmax = (1 << dtype_bits(dt_quant)) - 1;
     if (dt_inout == DT_F32) launch_dt<DT_F32>(a, qmax, mode, op, vec, cfg);
     else launch_dt<DT_BF16>(a, qmax, mode, op, vec, cfg);

@@ -37,7 +37,7 @@ _TORCH_DTYPE_MAP: dict = {
 _QUANT_TYPES = {torch.quint2x4, torch.quint4x2, torch.quint8, torch.uint8, torch.qint8, torch.int8}
 _DEQUANT_TYPES = {torch.float32, torch.bfloat16}
 _ROUND_MODES = {"nearest": RoundMode.NEAREST, "stochastic": RoundMode.STOCHASTIC,
-                "stochastic_per_element": RoundMode.STOCHASTIC_PER_ELEMENT}     # the last one: extension, quantize only
+                "stochastic_per_element": RoundMode.STOCHASTIC_PER_ELEMENT}     # the last one: extension (quantize, requantize)
 _REDUCE_OPS = {"set": ReduceOp.SET, "add": ReduceOp.ADD}
 
 
@@ -117,8 +117,6 @@ def requantize(tensor: torch.Tensor, *, scale: float, zero_point: int, dtype: to
     assert dtype in _QUANT_TYPES, f"Unsupported quantized dtype: {dtype}. Must be one of {list(_QUANT_TYPES)}"
     if tensor.dtype not in _DEQUANT_TYPES:
         raise ValueError(f"Unsupported input dtype: {tensor.dtype}. Must be one of {list(_DEQUANT_TYPES)}")
-    if round_mode == "stochastic_per_element":
-        raise ValueError("requantize supports round_mode 'nearest' and 'stochastic' only")
     tensor = _contiguous(tensor)
     if out is None:
         alloc = torch.zeros if reduce_op == "add" else torch.empty

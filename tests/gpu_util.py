@@ -101,6 +101,14 @@ class Gpu:
         check_canary(d_out)
         return to_host(d_out, x.dtype)
 
+    def requantize_sr(self, x: np.ndarray, dt_q: int, scale: float, zp: int, key: int, op: int = 0, prev: np.ndarray | None = None,
+                      in_off: int = 0, out_off: int = 0) -> np.ndarray:
+        self.ctx.set_sr_key(key)
+        try:
+            return self.requantize(x, dt_q, scale, zp, mode=2, op=op, prev=prev, in_off=in_off, out_off=out_off)
+        finally:
+            self.ctx.set_sr_key(None)
+
     def compute_quant_params(self, x: np.ndarray, dt_q: int, in_off: int = 0) -> tuple[float, int]:
         d_in = to_dev(x, in_off)
         if x.dtype == np.float32:

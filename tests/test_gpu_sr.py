@@ -134,5 +134,38 @@ def test_sr_torch_surface(gpu0):
     err = (y - x)
     assert err.abs().max().item() <= scale * (1 + 1e-5) + 1e-7          # never more than one step away
     assert abs(err.mean().item()) < 5 * scale * 0.41 / 1000              # and unbiased (sigma of U-shaped error <= 0.41 step, n = 1e6)
-    with pytest.raises(ValueError):
-        pt.requantize(x, scale=scale, zero_point=zp, dtype=torch.quint8, round_mode="stochastic_per_element")
+    r = pt.requantize(x, scale=scale, zero_point=zp, dtype=torch.quint8, round_mode="stochastic_per_element")
+    assert (r - x).abs().max().item() <= scale * (1 + 1e-5) + 1e-7 and abs((r - x).mean().item()) < 5 * scale * 0.41 / 1000
+
+
+@pytest.mark.parametrize("dt_io", (F32, BF16), ids=("f32", "bf16"))
+@pytest.mark.parametrize("op", (0, 1), ids=("set", "add"))
+def test_sr_requantize_bit_exact(gpu0, dt_io, op):
+    """Fused quantize -> dequantize with per-element stochastic rounding: the float-domain fast path (floor by two round-down
+    adds, no conversion), the exact fallback (special values), ragged sizes and the one-element-per-thread kernel (misaligned
+    buffers) against orc_requantize_sr, bit for bit."""
+    from oracle.port import INT4, UINT2
+    rng = np.random.default_rng(55)
+    isz = 4 if dt_io == F32 else 2
+    for dt_q in (UINT8, UINT4, UINT2, INT8, INT4):
+        bits = BITS[dt_q]
+        for n in (1, 7, 8, 9, 4099, 100_003, 1 << 18):
+            for scale, zp in ((2.0 / ((1 << bits) - 1), 1), (0.037, 0), (0.5, 300), (1.0, 2**40 + 7)):
+                x = make_input(rng, n, dt_io, -3.0, 3.0)
+                if n > 100:
+                    sp = special_values(scale)
+                    x[10:10 + sp.size] = sp if dt_io == F32 else f32_to_bf16_bits(sp)
+                prev = rng.uniform(-1, 1, n).astype(np.float32)
+                prev = prev if dt_io == F32 else f32_to_bf16_bits(prev)
+                key = int(rng.integers(0, 2**63))
+                for in_off, out_off in ((0, 0),) if n != 100_003 else ((0, 0), (isz, isz), (isz, 2 * isz), (0, 16)):
+                    with np.errstate(all="ignore"):
+                        want = port.requantize_sr(x, dt_q, scale, zp, key, op=op, out=prev.copy())
+                    got = gpu0.requantize_sr(x, dt_q, scale, zp, key, op=op, prev=prev, in_off=in_off, out_off=out_off)
+                    what = f"dt_q={dt_q} n={n} scale={scale} zp={zp} offs=({in_off},{out_off})"
+                    if dt_io == F32:
+                        bad = np.flatnonzero(got.view(np.uint32) != want.view(np.uint32))
+                        assert bad.size == 0, f"{what}: x={x[bad[:4]]} got={got[bad[:4]]} want={want[bad[:4]]}"
+                    else:
+                        an, bn = (got & 0x7FFF) > 0x7F80, (want & 0x7FFF) > 0x7F80
+                        assert np.array_equal(an, bn) and np.array_equal(got[~an], want[~bn]), what

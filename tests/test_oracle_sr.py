@@ -87,3 +87,17 @@ def test_sr_signed_and_special_values():
     a = port.quantize_sr(y, INT8, 2 / 255, -1, 11)
     b = port.quantize_sr(y, UINT8, 2 / 255, 127, 11)
     assert np.array_equal(a, b ^ 0x80)
+
+
+def test_sr_requantize_is_quantize_then_generic_dequantize():
+    """orc_requantize_sr = per-element quantize followed by the generic dequant_step of orc_requantize (f32: one multiply)."""
+    rng = np.random.default_rng(44)
+    x = rng.uniform(-1.5, 1.5, 3001).astype(np.float32)
+    for dt, scale, zp in ((UINT8, 2 / 255, 128), (UINT4, 0.2, 7), (INT8, 0.01, -3)):
+        q = port.quantize_sr(x, dt, scale, zp, 31337, base=64)
+        y = port.requantize_sr(x, dt, scale, zp, 31337, base=64)
+        assert np.array_equal(y.view(np.uint32), port.dequantize(q, dt, x.size, F32, scale, zp).view(np.uint32))
+    acc = rng.uniform(-1, 1, x.size).astype(np.float32)
+    y = port.requantize_sr(x, UINT8, 2 / 255, 128, 7, op=1, out=acc.copy())
+    q = port.quantize_sr(x, UINT8, 2 / 255, 128, 7)
+    assert np.array_equal(y.view(np.uint32), port.dequantize(q, UINT8, x.size, F32, 2 / 255, 128, 1, out=acc.copy()).view(np.uint32))
