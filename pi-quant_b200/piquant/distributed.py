@@ -126,7 +126,7 @@ def _p2p_slots(nbytes: int, device: torch.device, group):
 
 
 def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.quint8, group: Optional[dist.ProcessGroup] = None,
-                          ctx: Context = Context.get(), transport: str = "nccl") -> torch.Tensor:
+                          ctx: Context = Context.get(), transport: str = "nccl", round_mode: str = "nearest") -> torch.Tensor:
     """In-place SUM all-reduce of a contiguous CUDA float32 / bfloat16 tensor with quantized transport.
 
     Ring reduce-scatter + ring all-gather over NVLink; every hop carries ``[64-byte parameter block | packed
@@ -136,6 +136,9 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
     collective is enqueued without a single synchronisation.  In the all-gather phase the owner of a reduced
     chunk dequantizes its own packed bytes too, so every rank ends with bit-identical values.
     The result is the sum up to quantization error (<= 0.5 * scale per hop and element).
+    ``round_mode="stochastic_per_element"`` rounds every element with its own Philox random number instead (extension,
+    ``piquant_cuda.h``): the error per hop is then <= 1 * scale but has zero mean, so it averages out over steps and ranks
+    instead of accumulating as a bias -- what gradient compression wants; each rank draws its own key per hop.
 
     ``transport="nccl"``: each hop is an NCCL send/recv of the packed buffer.  ``transport="p2p"``: the sender's
     quantize kernel stores its packed output (and the parameter kernel its 64-byte block) DIRECTLY into the
@@ -143,6 +146,7 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
     there is no send/recv and no staging copy; a stream-ordered barrier per hop publishes the slot."""
     assert tensor.is_cuda and tensor.is_contiguous() and tensor.dtype in (torch.float32, torch.bfloat16)
     assert dtype in _QUANT_TYPES
+    rmode = {"nearest": RoundMode.NEAREST, "stochastic_per_element": RoundMode.STOCHASTIC_PER_ELEMENT}[round_mode]
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if world == 1:
         return tensor
@@ -164,7 +168,7 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
         c = chunk(i)
         if c.numel():
             ctx.compute_meta_async_ptr(c.data_ptr(), fdt, c.numel(), qdt, buf.data_ptr())
-            ctx.quantize_meta_async_ptr(c.data_ptr(), fdt, buf.data_ptr() + meta, qdt, c.numel(), RoundMode.NEAREST, buf.data_ptr())
+            ctx.quantize_meta_async_ptr(c.data_ptr(), fdt, buf.data_ptr() + meta, qdt, c.numel(), rmode, buf.data_ptr())
 
     def unpack(i, buf, op):    # [meta | packed] in buf -> (op) chunk i, one kernel
         c = chunk(i)
@@ -188,7 +192,7 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
             c = chunk(i)
             if c.numel():
                 ctx.compute_meta_async_ptr(c.data_ptr(), fdt, c.numel(), qdt, base_ptr)
-                ctx.quantize_meta_async_ptr(c.data_ptr(), fdt, base_ptr + meta, qdt, c.numel(), RoundMode.NEAREST, base_ptr)
+                ctx.quantize_meta_async_ptr(c.data_ptr(), fdt, base_ptr + meta, qdt, c.numel(), rmode, base_ptr)
 
         def unpack_from(i, base_ptr, op):
             c = chunk(i)

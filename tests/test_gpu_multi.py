@@ -66,14 +66,17 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
         res["sharded_meta"] = (pt.meta_to_host(meta) == orc.compute_quant_params(x, orc.UINT8),)
         pd.destroy_native_comm(ctx)
         # quantized ring all-reduce: every rank ends with bit-identical values, close to the exact sum
-        for tdt, qdt, transport in ((torch.float32, torch.quint8, "nccl"), (torch.bfloat16, torch.quint8, "nccl"), (torch.float32, torch.quint4x2, "nccl"),
-                                    (torch.float32, torch.quint8, "p2p"), (torch.bfloat16, torch.quint4x2, "p2p"), (torch.float32, torch.quint8, "p2p")):
-            tol_steps = 1.0
+        for tdt, qdt, transport, rmode in ((torch.float32, torch.quint8, "nccl", "nearest"), (torch.bfloat16, torch.quint8, "nccl", "nearest"),
+                                           (torch.float32, torch.quint4x2, "nccl", "nearest"), (torch.float32, torch.quint8, "p2p", "nearest"),
+                                           (torch.bfloat16, torch.quint4x2, "p2p", "nearest"), (torch.float32, torch.quint8, "p2p", "nearest"),
+                                           (torch.float32, torch.quint8, "p2p", "stochastic_per_element"),
+                                           (torch.float32, torch.quint8, "nccl", "stochastic_per_element")):
+            tol_steps = 1.0 if rmode == "nearest" else 2.0          # per-element SR: up to one step per hop instead of half a step
             g = torch.Generator(device="cuda").manual_seed(100 + rank)
             t = (torch.rand(1_000_003, device="cuda", generator=g) * 2 - 1).to(tdt)
             exact = t.double().clone()
             dist.all_reduce(exact)
-            pd.quantized_all_reduce_(t, dtype=qdt, ctx=ctx, transport=transport)
+            pd.quantized_all_reduce_(t, dtype=qdt, ctx=ctx, transport=transport, round_mode=rmode)
             gathered = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(gathered, t)
             identical = all(torch.equal(gathered[0].view(torch.uint8), gi.view(torch.uint8)) for gi in gathered)
@@ -81,7 +84,10 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
             step = 2.0 * world / qmax                     # |sum| <= world, so every hop's scale is <= 2*world/qmax
             err = (t.double() - exact).abs().max().item()
             bound = step * (0.5 * world + 0.5) * tol_steps + (0.02 * world if tdt == torch.bfloat16 else 1e-5)
-            res[f"ring_{transport}_{tdt}_{qdt}_{len(res)}"] = (identical, err <= bound)
+            ok = (identical, err <= bound)
+            if rmode != "nearest":      # unbiased: the mean error over 1e6 elements is far below one step
+                ok += (abs((t.double() - exact).mean().item()) < 0.01 * step,)
+            res[f"ring_{transport}_{tdt}_{qdt}_{rmode}_{len(res)}"] = ok
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
