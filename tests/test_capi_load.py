@@ -9,6 +9,7 @@ import subprocess
 import sys
 from pathlib import Path
 
+import numpy as np
 import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -115,6 +116,29 @@ def test_invalid_dtype_combination_aborts_like_the_reference(lib):
     buf = "b = ctypes.create_string_buffer(64)\n"
     r = run_snippet(buf + "lib.piquant_quantize(ctypes.c_void_p(ctx), b, 4, b, 0, ctypes.c_size_t(8), ctypes.c_float(1.0), ctypes.c_int64(0), 0)")
     assert r.returncode == -6 and "must be a dequantized type" in r.stderr and "survived" not in r.stdout
+
+
+def test_extension_values_are_validated_before_any_cuda_call(lib):
+    """Round mode 2 (per-element SR) and dtypes 5..7 (signed) are accepted, anything beyond aborts -- checked with numel == 0
+    calls, which return before touching CUDA, so this runs without a GPU."""
+    buf = "b = ctypes.create_string_buffer(64)\n"
+    ok = run_snippet(buf + "\n".join([
+        "lib.piquant_quantize(ctypes.c_void_p(ctx), b, 0, b, 7, ctypes.c_size_t(0), ctypes.c_float(1.0), ctypes.c_int64(0), 2)",
+        "lib.piquant_dequantize(ctypes.c_void_p(ctx), b, 6, b, 1, ctypes.c_size_t(0), ctypes.c_float(1.0), ctypes.c_int64(0), 1)",
+        "lib.piquant_cuda_requantize(ctypes.c_void_p(ctx), b, 0, b, 5, ctypes.c_size_t(0), ctypes.c_float(1.0), ctypes.c_int64(0), 2, 0)",
+        "lib.piquant_cuda_set_sr_key(ctypes.c_void_p(ctx), ctypes.c_uint64(5))",
+        "lib.piquant_cuda_last_sr_key.restype = ctypes.c_uint64",
+        "assert lib.piquant_cuda_last_sr_key(ctypes.c_void_p(ctx)) == 0",
+    ]))
+    assert ok.returncode == 0 and "survived" in ok.stdout, ok.stderr
+    bad_mode = run_snippet(buf + "lib.piquant_quantize(ctypes.c_void_p(ctx), b, 0, b, 4, ctypes.c_size_t(8), ctypes.c_float(1.0), ctypes.c_int64(0), 3)")
+    assert bad_mode.returncode == -6 and "invalid round mode" in bad_mode.stderr
+    bad_dtype = run_snippet(buf + "lib.piquant_quantize(ctypes.c_void_p(ctx), b, 0, b, 8, ctypes.c_size_t(8), ctypes.c_float(1.0), ctypes.c_int64(0), 0)")
+    assert bad_dtype.returncode == -6 and "must be a quantized type" in bad_dtype.stderr
+    # signed parameter arithmetic on the host: the reference's formula with q_min = -2^(N-1)
+    from oracle import port
+    from piquant import Context, DataType
+    assert Context.params_from_minmax(-1.0, 1.0, DataType.INT8) == port.params_from_minmax(-1.0, 1.0, port.INT8) == (np.float32(2 / 255), -1)
 
 
 def test_compute_without_a_gpu_aborts_loudly(lib):
