@@ -274,7 +274,7 @@ __device__ __forceinline__ int32_t quant_step(float x, const QuantParams& P, int
 //   {c0, c1, c2, c3} <- {hi(M1*c2) ^ c1 ^ k0, lo(M1*c2), hi(M0*c0) ^ c3 ^ k1, lo(M0*c0)},  key += {W0, W1} per round.
 // 2 IMAD.WIDE + 2 LOP3 per round; the round keys are uniform (key + r * W), so they cost nothing per element.
 struct PhiloxKey { uint32_t k0, k1; };
-__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, PhiloxKey key, uint32_t (&out)[4]) {
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, PhiloxKey key, uint32_t (&out)[4]) {
     constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
