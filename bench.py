@@ -15,7 +15,11 @@ Printed JSON keys beyond the base contract:
   roofline      dominant kernel vs the measured HBM copy peak (MEASURED_PEAKS.json); algorithmic 5 B/elem
   e2e           same metric through piquant_quantize with PINNED HOST buffers: H2D + kernel + D2H per step
   cpu_baseline  the unmodified reference (oracle/_ref/libpiquant_ref.so) on this box's host cores, N=1 only
-  extra         the other BASELINE configs, timed the same way (kernel-only, per GPU)
+  extra         the other BASELINE configs, timed the same way (kernel-only, per GPU); the reference's own small-tensor
+                benchmark recipe; pageable-host throughput; per-config byte comparison with the CPU reference
+  strong        run on ALL ranks at every N: the BASELINE configs as the contract spells them -- ONE tensor sharded over the
+                N GPUs (C3 f32[1e9] compute_quant_params incl. the cross-rank exchange, C5 u8[1e9]->f32 ADD, f32->u8 and
+                bf16->u4 at 27.264 M and 1e9 total) with per-rank parity against the CPU oracle in the same run
 --impl reference times the reference's own CPU implementation (all host threads) on the same workload.
 """
 from __future__ import annotations
@@ -248,16 +252,45 @@ def run_ours(args) -> None:
     torch.cuda.synchronize()
     d2h_gbps = 2 * n / (time.perf_counter() - t0) / 1e9
     e2e_ok = bool(torch.equal(qh[: 1 << 24], q[: 1 << 24].cpu()))
+    # ... and what the link does when both directions run at once on every rank (the pipeline's actual traffic pattern:
+    # 4 B/element up and 1 B/element down share the host's memory system with the other ranks' copies)
+    up, down = torch.cuda.Stream(), torch.cuda.Stream()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        with torch.cuda.stream(up):
+            x.copy_(xh, non_blocking=True)
+        with torch.cuda.stream(down):
+            for _ in range(4):
+                qh.copy_(q, non_blocking=True)
+    torch.cuda.synchronize()
+    bidir_s = max_over_ranks(time.perf_counter() - t0)
+    bidir_h2d_gbps = 2 * 4 * n / bidir_s / 1e9
+    barrier()
+    # the literal drop-in case: PAGEABLE host tensors (what piquant.torch callers of the reference pass, reference
+    # python/src/piquant/torch.py:87,117) -- copy workers <-> pinned bounce buffers <-> copy engines
+    n_pg = min(n, 1 << 28)
+    xp = torch.empty(n_pg, dtype=torch.float32)
+    xp.copy_(xh[:n_pg])
+    qp = torch.empty(n_pg, dtype=torch.uint8)
+    ctx.quantize_ptr(xp.data_ptr(), D.F32, qp.data_ptr(), D.UINT8, n_pg, scale, zp, RoundMode.NEAREST)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ctx.quantize_ptr(xp.data_ptr(), D.F32, qp.data_ptr(), D.UINT8, n_pg, scale, zp, RoundMode.NEAREST)
+    pageable_s = max_over_ranks((time.perf_counter() - t0) / 3)
+    pageable_ok = bool(torch.equal(qp[: 1 << 24], qh[: 1 << 24]))
+    barrier()
+    del xp, qp
     os.sched_setaffinity(0, affinity0)      # the CPU baseline below must see every host core again
 
     # ---- the other BASELINE configs, kernel-only, this rank's GPU -------------------------------
     extra = {}
     if rank == 0:
         extra = run_extra(torch, ctx, D, RoundMode, ReduceOp, x, q, scale, zp, dev)
+    barrier()
+    strong = strong_scaling_legs(torch, dist, piquant, D, RoundMode, ReduceOp, x, q, world, rank, dev, barrier, max_over_ranks)
     if world > 1:
-        extra_sharded = sharded_params(torch, dist, piquant, ctx, D, x, world, rank, dev)
-        if rank == 0:
-            extra["C3_sharded_compute_quant_params"] = extra_sharded
         ring = ring_allreduce_leg(torch, dist, ctx, world, rank, dev)
         if rank == 0:
             extra["quantized_ring_all_reduce"] = ring
@@ -266,7 +299,7 @@ def run_ours(args) -> None:
     cpu_baseline = None
     parity = None
     if rank == 0 and world == 1:
-        cpu_baseline, parity = cpu_reference_leg(xh.numpy(), qh.numpy(), scale, zp)
+        cpu_baseline, parity = cpu_reference_leg(xh.numpy(), qh.numpy(), scale, zp, ctx, D, RoundMode, ReduceOp)
 
     if sampler:
         sampler.stop()
@@ -293,11 +326,18 @@ def run_ours(args) -> None:
                 "steps": e2e_steps, "path": "piquant_quantize(host pinned in, host pinned out): chunked H2D | kernel | D2H pipeline",
                 "bound": "pcie", "h2d_GBps_achieved_per_gpu": round(4 * n / e2e_s / 1e9, 1), "h2d_GBps_plain_memcpy": round(h2d_gbps, 1),
                 "d2h_GBps_plain_memcpy": round(d2h_gbps, 1), "frac_of_link": round((4 * n / e2e_s / 1e9) / h2d_gbps, 4),
-                "output_matches_device_path": e2e_ok, "host_numa": numa},
+                "h2d_GBps_plain_memcpy_both_directions_busy": round(bidir_h2d_gbps, 1),
+                "frac_of_link_both_directions_busy": round((4 * n / e2e_s / 1e9) / bidir_h2d_gbps, 4),
+                "output_matches_device_path": e2e_ok, "host_numa": numa,
+                "pageable_host": {"value": round(world * n_pg / pageable_s / 1e9, 3), "unit": UNIT, "numel_per_gpu": n_pg,
+                                  "h2d_GBps_per_gpu": round(4 * n_pg / pageable_s / 1e9, 1), "output_matches_pinned_path": pageable_ok,
+                                  "path": "piquant_quantize(PAGEABLE host in, PAGEABLE host out): host copy workers <-> pinned bounce ring <-> H2D | kernel | D2H",
+                                  "note": "what a caller of the reference's piquant.torch passes (CPU torch tensors)"}},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(mark0, mark1, window),
         "cpu_baseline": cpu_baseline,
         "parity_vs_cpu_reference": parity,
+        "strong": strong,
         "extra": extra,
     }
     emit(line)
@@ -438,28 +478,207 @@ def run_extra(torch, ctx, D, RoundMode, ReduceOp, x, q, scale, zp, dev) -> dict:
     return out
 
 
-def sharded_params(torch, dist, piquant, ctx, D, x, world, rank, dev) -> dict:
-    """BASELINE config 3 on N GPUs: each rank reduces its shard, ONE ncclAllReduce(max) of {-min, max} inside
-    piquant_compute_quant_params_float32 (library-owned communicator, bootstrapped over torch.distributed)."""
-    uid = [piquant.Context.nccl_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
-    ctx.comm_init_rank(uid[0], world, rank)
-    n = x.numel()
-    for _ in range(3):
-        res = ctx.compute_quant_params_ptr_float32(x.data_ptr(), D.UINT8, n)
-    dist.barrier()
+def strong_scaling_legs(torch, dist, piquant, D, RoundMode, ReduceOp, x, q, world, rank, dev, barrier, max_over_ranks) -> dict:
+    """The BASELINE configs as the contract spells them -- ONE tensor of `total` elements sharded contiguously over the N GPUs
+    (piquant.distributed.shard_bounds; reference src/piquant.cpp:132-176 splits a tensor over threads the same way) -- on ALL
+    ranks, with parity against the CPU oracle in the same run.  The global tensor is the concatenation of every rank's
+    x[b:e] (rank-seeded U(-1,1)); shards are independent, the only exchange is {-min, max} inside compute_quant_params.
+    Per config: T_N = max over ranks of the per-rank time, T_1 = rank 0 alone on the whole tensor, efficiency = T_1 / (N T_N)."""
+    from piquant import distributed as pd
+
+    peak, _ = measured_peak()
+    out: dict = {"n_gpus": world, "sharding": "contiguous, boundaries at multiples of 64 elements (piquant.distributed.shard_bounds)"}
+    ctx = piquant.Context()
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    if world > 1:
+        uid = [piquant.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init_rank(uid[0], world, rank)
+    solo = piquant.Context()            # no communicator: rank 0 alone on the whole tensor (T_1)
+    solo.set_stream(stream.cuda_stream)
+    n_all = x.numel()
+
+    def flags_all(*flags) -> bool:
+        t = torch.tensor([1 if all(flags) else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def device_time(fn, reps, warm=3):
+        """CUDA-event time per call of fn(k) (k = launch index, for rotating windows), max over ranks"""
+        for k in range(warm):
+            fn(k)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(reps):
+            fn(warm + k)
+        e1.record()
+        torch.cuda.synchronize()
+        return max_over_ranks(e0.elapsed_time(e1) / reps * 1e-3)
+
+    def wall_time(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return max_over_ranks((time.perf_counter() - t0) / reps)
+
+    def only_rank0(measure):
+        """run `measure` on rank 0 while the other ranks wait; every rank gets the value"""
+        v = measure() if rank == 0 else 0.0
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def oracle_windows(n_r):
+        """4 Mi-element windows at both ends of this rank's shard (the shard boundaries of the global tensor)"""
+        w = min(n_r, 1 << 22)
+        return [(0, w)] if n_r <= (1 << 23) else [(0, w), (n_r - w, n_r)]
+
+    from oracle import port as orc      # the CPU oracle, here ONLY as the checker of the GPU results (never timed, never the product)
+
+    # ---- C3: compute_quant_params of f32[total] sharded, incl. the cross-rank exchange ----------------------------
+    total = n_all
+    b, e = pd.shard_bounds(total, world, rank)
+    shard = x[b:e]
+    n_r = e - b
+    res = ctx.compute_quant_params_ptr_float32(shard.data_ptr(), D.UINT8, n_r)
+    # parity: every rank must hold the parameters of the WHOLE tensor, bit for bit.  Independent route: torch reductions +
+    # torch.distributed + the oracle's restatement of the reference's double arithmetic.
+    mm = torch.stack([-shard.min(), shard.max()]) if n_r else torch.full((2,), -3.4028234663852886e38, device=dev)
+    if world > 1:
+        dist.all_reduce(mm, op=dist.ReduceOp.MAX)
+    want = orc.params_from_minmax(float(-mm[0].item()), float(mm[1].item()), orc.UINT8)
+    c3 = {"numel_total": total, "numel_per_gpu": n_r, "scale": res[0], "zero_point": res[1],
+          "parity_params_bit_equal_on_every_rank": flags_all(res == want)}
+    transports = {}
+    if world > 1:
+        for name, tr in (("peer_memory_in_kernel", 2), ("nccl_allreduce", 1)):
+            if tr == 2 and ctx.comm_transport != 2:
+                transports[name] = "unavailable (ranks cannot map each other's memory)"
+                continue
+            ctx.comm_set_transport(tr)
+            t = wall_time(lambda: ctx.compute_quant_params_ptr_float32(shard.data_ptr(), D.UINT8, n_r), 30)
+            ok = flags_all(ctx.compute_quant_params_ptr_float32(shard.data_ptr(), D.UINT8, n_r) == want)
+            transports[name] = {"ms": round(t * 1e3, 4), "parity": ok}
+        ctx.comm_set_transport(0)
+        c3["exchange"] = transports
+    t_n = wall_time(lambda: ctx.compute_quant_params_ptr_float32(shard.data_ptr(), D.UINT8, n_r), 30)
+    t_1 = only_rank0(lambda: wall_time_local(torch, lambda: solo.compute_quant_params_ptr_float32(x.data_ptr(), D.UINT8, total), 20))
+    c3.update({"ms": round(t_n * 1e3, 4), "ms_one_gpu_whole_tensor": round(t_1 * 1e3, 4), "Gelem/s": round(total / t_n / 1e9, 1),
+               "strong_scaling_efficiency": round(t_1 / (world * t_n), 4), "transport": {0: "none", 1: "nccl_allreduce", 2: "peer_memory_in_kernel"}[ctx.comm_transport],
+               "roofline_ms_per_gpu_at_measured_peak": round(4 * n_r / (peak * 1e9) * 1e3, 4),
+               "note": "wall clock of the synchronous call (returns host scalars): min/max kernel with the exchange inside + stream sync; max over ranks"})
+    out["C3_compute_quant_params_f32_1e9_sharded"] = c3
+    scale_g, zp_g = res
+
+    # ---- quantize: f32->u8 and bf16->u4, 27.264 M and 1e9 total, sharded ----------------------------------------
+    xb_all = x.to(torch.bfloat16)
+    for dt_name, src, DIN, DQ, odq, bpe, per in (("f32_u8", x, D.F32, D.UINT8, orc.UINT8, 5.0, 1), ("bf16_u4", xb_all, D.BF16, D.UINT4, orc.UINT4, 2.5, 2)):
+        for total in (27_264_000, n_all):
+            b, e = pd.shard_bounds(total, world, rank)
+            n_r = e - b
+            # whole-tensor parameters through the communicator (bf16: its own min/max)
+            if DIN == D.F32:
+                s_g, z_g = ctx.compute_quant_params_ptr_float32(src[b:e].data_ptr(), DQ, n_r)
+            else:
+                s_g, z_g = ctx.compute_quant_params_ptr_bfloat16(src[b:e].data_ptr(), DQ, n_r)
+            # rotating windows over the rank's 1e9-element buffer, so that L2 (126 MB) never serves a small shard twice
+            windows = max(1, min(64, n_all // max(n_r, 1)))
+            offs = [(b + j * n_r) if (b + (j + 1) * n_r) <= n_all else b for j in range(windows)] if total < n_all else [b]
+            offs = [o - o % 64 for o in offs]
+
+            def launch(k, n_r=n_r, offs=offs, src=src, DIN=DIN, DQ=DQ, s_g=s_g, z_g=z_g, per=per):
+                o = offs[k % len(offs)]
+                ctx.quantize_ptr(src[o:o + n_r].data_ptr(), DIN, q[o // per:].data_ptr(), DQ, n_r, s_g, z_g, RoundMode.NEAREST)
+            reps = 200 if total < n_all else 20
+            t_n = device_time(launch, reps)
+            o1 = [j * total for j in range(max(1, min(32, n_all // total)))]
+            t_1 = only_rank0(lambda: device_time_local(torch, lambda k: solo.quantize_ptr(src[o1[k % len(o1)]:].data_ptr(), DIN, q[o1[k % len(o1)] // per:].data_ptr(), DQ, total, s_g, z_g, RoundMode.NEAREST), reps))
+            # parity: the shard's packed bytes at both shard boundaries == the oracle on the same elements with the global parameters
+            launch(0)
+            torch.cuda.synchronize()
+            o = offs[0]
+            ok = True
+            for w0, w1 in oracle_windows(n_r):
+                w0 -= w0 % 64
+                xin = src[o + w0:o + w1]
+                host = xin.cpu().numpy() if DIN == D.F32 else xin.view(torch.int16).cpu().numpy().view("uint16")
+                got = q[(o + w0) // per:(o + w0) // per + orc.packed_bytes(odq, w1 - w0)].cpu().numpy()
+                ok = ok and bool((orc.quantize(host, odq, s_g, z_g) == got).all())
+            gbs = bpe * total / t_n / 1e9
+            out[f"quantize_{dt_name}_{'27.264M' if total < n_all else '1e9'}_sharded"] = {
+                "numel_total": total, "numel_per_gpu": n_r, "us": round(t_n * 1e6, 2), "us_one_gpu_whole_tensor": round(t_1 * 1e6, 2),
+                "Gelem/s": round(total / t_n / 1e9, 1), "GB/s_aggregate": round(gbs, 1), "frac_of_measured_peak_x_N": round(gbs / (peak * world), 4),
+                "strong_scaling_efficiency": round(t_1 / (world * t_n), 4), "parity_sharded": flags_all(ok),
+                "note": "CUDA events over back-to-back launches on rotating windows, max over ranks; parity = packed bytes of both shard-boundary windows vs the CPU oracle on every rank"}
+    del xb_all
+
+    # ---- C5: u8[total] -> f32 dequantize with the ADD store op, sharded ------------------------------------------
+    total = n_all
+    b, e = pd.shard_bounds(total, world, rank)
+    n_r = e - b
+    acc = torch.zeros(n_r, dtype=torch.float32, device=dev)
+    ctx.quantize_ptr(x[b:e].data_ptr(), D.F32, q[b:e].data_ptr(), D.UINT8, n_r, scale_g, zp_g, RoundMode.NEAREST)
+
+    def add(_k=0):
+        ctx.dequantize_ptr(q[b:e].data_ptr(), D.UINT8, acc.data_ptr(), D.F32, n_r, scale_g, zp_g, ReduceOp.ADD)
+    t_n = device_time(add, 20)
+    acc.zero_()
+    add()
+    add()
+    torch.cuda.synchronize()
+    ok = True
+    for w0, w1 in oracle_windows(n_r):
+        qw = q[b + w0:b + w1].cpu().numpy()
+        wantw = orc.dequantize(qw, orc.UINT8, w1 - w0, orc.F32, scale_g, zp_g, orc.ADD,
+                               out=orc.dequantize(qw, orc.UINT8, w1 - w0, orc.F32, scale_g, zp_g, orc.ADD))
+        ok = ok and bool((acc[w0:w1].cpu().numpy().view("uint32") == wantw.view("uint32")).all())
+    del acc
+
+    def solo_c5():
+        acc1 = torch.zeros(total, dtype=torch.float32, device=dev)
+        t = device_time_local(torch, lambda k: solo.dequantize_ptr(q.data_ptr(), D.UINT8, acc1.data_ptr(), D.F32, total, scale_g, zp_g, ReduceOp.ADD), 10)
+        del acc1
+        return t
+    t_1 = only_rank0(solo_c5)
+    gbs = 9.0 * total / t_n / 1e9
+    out["C5_u8_f32_dequantize_add_1e9_sharded"] = {
+        "numel_total": total, "numel_per_gpu": n_r, "ms": round(t_n * 1e3, 4), "ms_one_gpu_whole_tensor": round(t_1 * 1e3, 4),
+        "Gelem/s": round(total / t_n / 1e9, 1), "GB/s_aggregate": round(gbs, 1), "frac_of_measured_peak_x_N": round(gbs / (peak * world), 4),
+        "strong_scaling_efficiency": round(t_1 / (world * t_n), 4), "parity_sharded": flags_all(ok),
+        "note": "all ranks concurrently, 9 B/element; parity = two ADD passes into zeros vs the oracle, both shard-boundary windows, every rank"}
+    if world > 1:
+        ctx.comm_destroy()
+    return out
+
+
+def wall_time_local(torch, fn, reps, warm=3) -> float:
+    for _ in range(warm):
+        fn()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    reps = 10
     for _ in range(reps):
-        res = ctx.compute_quant_params_ptr_float32(x.data_ptr(), D.UINT8, n)
-    t = (time.perf_counter() - t0) / reps
-    tt = torch.tensor([t], dtype=torch.float64, device=dev)
-    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ctx.comm_destroy()
-    t = float(tt.item())
-    return {"numel_total": n * world, "ms": round(t * 1e3, 4), "Gelem/s": round(n * world / t / 1e9, 1), "scale": res[0], "zero_point": res[1],
-            "note": "wall clock max over ranks; shard min/max kernel + one 2-float NCCL max all-reduce + sync"}
+        fn()
+    return (time.perf_counter() - t0) / reps
+
+
+def device_time_local(torch, fn, reps, warm=3) -> float:
+    for k in range(warm):
+        fn(k)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(reps):
+        fn(warm + k)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
 
 
 def ring_allreduce_leg(torch, dist, ctx, world, rank, dev) -> dict:
@@ -491,27 +710,45 @@ def ring_allreduce_leg(torch, dist, ctx, world, rank, dev) -> dict:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def identical_on_every_rank() -> bool:
+        """two wrapping checksums of the result's bit pattern, compared across ranks"""
+        v = work.view(torch.int32).to(torch.int64)
+        c = torch.stack([v.sum(), (v * (torch.arange(n, device=dev, dtype=torch.int64) % 8191 + 1)).sum()])
+        lo, hi = c.clone(), c.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        return bool(torch.equal(lo, hi))
+
+    def error_stats(exact):
+        d = (work - exact).double()
+        st = torch.stack([d.abs().max(), d.mean().abs()])
+        dist.all_reduce(st, op=dist.ReduceOp.MAX)
+        return round(float(st[0].item()), 5), float(f"{st[1].item():.3e}")
+
     ms_nccl = timed(lambda: dist.all_reduce(work))
     exact = work.clone()
-    ms_q8 = timed(lambda: pd.quantized_all_reduce_(work, dtype=torch.quint8, ctx=ctx))
-    err = (work - exact).abs().max()
-    try:        # same ring, the quantize kernel storing straight into the neighbour's slot over NVLink peer memory
-        ms_p2p = round(timed(lambda: pd.quantized_all_reduce_(work, dtype=torch.quint8, ctx=ctx, transport="p2p")), 3)
-        err = torch.maximum(err, (work - exact).abs().max())
-    except Exception as e:      # noqa: BLE001  (symmetric memory not available on this box)
-        ms_p2p = f"unavailable: {type(e).__name__}"
-    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    res = {"numel": n, "ms_nccl_f32": round(ms_nccl, 3)}
     bus = 2 * (world - 1) / world * n * 4 / 1e9
-    return {"numel": n, "ms_nccl_f32": round(ms_nccl, 3), "ms_quantized_u8": round(ms_q8, 3), "ms_quantized_u8_p2p_fused": ms_p2p, "speedup": round(ms_nccl / ms_q8, 3),
-            "nccl_busbw_GBps": round(bus / (ms_nccl * 1e-3), 1), "effective_busbw_GBps": round(bus / (ms_q8 * 1e-3), 1),
-            "speedup_p2p_fused": round(ms_nccl / ms_p2p, 3) if isinstance(ms_p2p, float) else None,
-            "max_abs_err": round(float(err.item()), 5),
-            "note": "ring reduce-scatter + all-gather, [64 B params | u8 payload] per hop, no host sync; p2p_fused = the quantize kernel stores into the neighbour's slot over NVLink peer memory"}
+    res["nccl_busbw_GBps"] = round(bus / (ms_nccl * 1e-3), 1)
+    for key, kw in (("quantized_u8_nccl_sendrecv", dict(transport="nccl")), ("quantized_u8_p2p_fused", dict(transport="p2p")),
+                    ("quantized_u8_p2p_fused_stochastic_per_element", dict(transport="p2p", round_mode="stochastic_per_element"))):
+        try:
+            ms = timed(lambda: pd.quantized_all_reduce_(work, dtype=torch.quint8, ctx=ctx, **kw))
+            mx, mean = error_stats(exact)
+            res[key] = {"ms": round(ms, 3), "speedup_vs_nccl_f32": round(ms_nccl / ms, 3), "effective_busbw_GBps": round(bus / (ms * 1e-3), 1),
+                        "max_abs_err": mx, "abs_mean_err": mean, "bit_identical_on_every_rank": identical_on_every_rank()}
+        except Exception as e:      # noqa: BLE001  (symmetric memory not available on this box)
+            res[key] = f"unavailable: {type(e).__name__}: {str(e)[:120]}"
+    res["note"] = ("ring reduce-scatter + all-gather, [64 B params | u8 payload] per hop, no host sync; a reduce-scatter hop = quantize + ONE fused "
+                   "dequantize-ADD/min-max/params kernel; p2p_fused = kernels store into / forward to the neighbour's slot over NVLink peer memory, "
+                   "nothing is sent; abs_mean_err shows the bias nearest rounding accumulates per hop and per-element stochastic rounding does not")
+    return res
 
 
-def cpu_reference_leg(x_host, q_gpu_host, scale, zp):
+def cpu_reference_leg(x_host, q_gpu_host, scale, zp, ctx, D, RoundMode, ReduceOp):
     """The unmodified reference on this box's host cores (oracle/_ref), bounded to ~10 s, and a full-size
-    bit comparison of its output with the GPU library's."""
+    bit comparison of its output with the GPU library's -- for the headline and for every other BASELINE config
+    (the GPU side of those comparisons runs through the same C ABI on the same host arrays)."""
     import numpy as np
 
     try:
@@ -573,11 +810,56 @@ def cpu_reference_leg(x_host, q_gpu_host, scale, zp):
             others[name] = {"numel": m, "ms": round(tt * 1e3, 3), "Gelem/s": round(m / tt / 1e9, 3), "passes": k}
     except Exception as e:      # noqa: BLE001
         others["error"] = repr(e)[:200]
+    per_config = {"headline_f32_u8_nearest_1e9": {"numel": n, "mismatches": mism}}
+    try:
+        from oracle import port as orc
+        bf = orc.bf16_bits_to_f32
+        # C2: bf16 -> u4 bytes, u4 -> bf16 bits, and the round-trip error of BOTH implementations on the same data
+        q4g = np.empty_like(q4)
+        ctx.quantize_ptr(xb.ctypes.data, D.BF16, q4g.ctypes.data, D.UINT4, n2, s4, z4, RoundMode.NEAREST)
+        ybg = np.empty_like(yb)
+        ctx.dequantize_ptr(q4.ctypes.data, D.UINT4, ybg.ctypes.data, D.BF16, n2, s4, z4, ReduceOp.SET)
+        per_config["C2_bf16_u4_quantize_1e8"] = {"numel": n2, "mismatches": int(np.count_nonzero(q4g != q4))}
+        per_config["C2_u4_bf16_dequantize_1e8"] = {"numel": n2, "mismatches": int(np.count_nonzero(ybg != yb))}
+        xf = bf(xb)
+        per_config["C2_round_trip_max_abs_err_over_scale"] = {
+            "gpu": round(float(np.abs(bf(ybg) - xf).max()) / s4, 4), "cpu_reference": round(float(np.abs(bf(yb) - xf).max()) / s4, 4),
+            "note": "above 0.5 on both: the excess is the bf16 rounding of the dequantized output, not the quantizer"}
+        del xf, q4g, ybg
+        # C3: parameters of the whole tensor
+        per_config["C3_compute_quant_params_f32"] = {
+            "gpu": list(ctx.compute_quant_params_ptr_float32(x_host.ctypes.data, D.UINT8, n)), "cpu_reference": list(c.compute_quant_params(x_host, ref_dt("UINT8")))}
+        per_config["C3_compute_quant_params_f32"]["equal"] = per_config["C3_compute_quant_params_f32"]["gpu"] == per_config["C3_compute_quant_params_f32"]["cpu_reference"]
+        # C4: the reference's stochastic output (its threshold cannot be set: one value per call from an unreachable RNG,
+        # src/piquant.cpp:194-201) brackets that threshold; the GPU is run with a threshold from the bracket and must match bytewise
+        m4 = min(n, 200_000_000)
+        ref4 = c.quantize(x_host[:m4], ref_dt("UINT8"), scale, zp, 1)
+        xi = orc.infer_stochastic_threshold(x_host[:m4], scale, zp, 255, ref4)
+        if xi is None:
+            per_config["C4_f32_u8_stochastic"] = {"numel": m4, "error": "no single threshold explains the reference's output"}
+        else:
+            g4 = np.empty_like(ref4)
+            ctx.set_stochastic_threshold(xi)
+            ctx.quantize_ptr(x_host[:m4].ctypes.data, D.F32, g4.ctypes.data, D.UINT8, m4, scale, zp, RoundMode.STOCHASTIC)
+            ctx.set_stochastic_threshold(None)
+            per_config["C4_f32_u8_stochastic"] = {"numel": m4, "threshold_inferred_from_reference_output": xi, "mismatches": int(np.count_nonzero(g4 != ref4))}
+            del g4
+        del ref4
+        # C5: one ADD pass into a non-zero accumulator
+        n5 = n // 8
+        prev = x_host[n5:2 * n5].copy()
+        acc_r, acc_g = prev.copy(), prev.copy()
+        c.dequantize(out[:n5], ref_dt("UINT8"), n5, ref_dt("F32"), scale, zp, 1, out=acc_r)
+        ctx.dequantize_ptr(out[:n5].ctypes.data, D.UINT8, acc_g.ctypes.data, D.F32, n5, scale, zp, ReduceOp.ADD)
+        per_config["C5_u8_f32_dequantize_add_shard"] = {"numel": n5, "mismatches": int(np.count_nonzero(acc_g.view(np.uint32) != acc_r.view(np.uint32)))}
+    except Exception as e:      # noqa: BLE001
+        per_config["error"] = repr(e)[:300]
     c.close()
     return ({"value": round(n / t / 1e9, 3), "unit": UNIT, "cores": cores, "kind": "reference", "isa": ref.cpu_isa(),
              "sample": f"numel={n} (the full workload), {passes} passes, {cores} threads, mean",
              "other_configs_same_cores": others},
-            {"numel": n, "mismatches": mism, "what": "GPU e2e output vs reference CPU output, byte for byte"})
+            {"numel": n, "mismatches": mism, "what": "GPU output vs reference CPU output on the same host arrays, byte for byte (bf16 / f32 results: bit patterns)",
+             "per_config": per_config})
 
 
 def ref_dt(name: str) -> int:

@@ -108,6 +108,15 @@ PIQUANT_EXPORT int  piquant_cuda_nccl_unique_id(void* out128);
 PIQUANT_EXPORT void piquant_cuda_comm_init_rank(piquant_context_t* ctx, const void* unique_id128, int nranks, int rank);
 /* Leave the communicator; compute_quant_params is local again. */
 PIQUANT_EXPORT void piquant_cuda_comm_destroy(piquant_context_t* ctx);
+/* How the ranks combine {-min, max}.  comm_init_rank also has every rank map a 512-byte mailbox of every other rank
+ * (CUDA IPC over NVLink / NVSwitch); when that succeeds on all ranks the exchange happens INSIDE the min/max kernel
+ * (8-byte peer stores + a sequence tag, polled by the kernel's last CTA): one launch per compute_quant_params, no
+ * NCCL call.  transport: 0 = peer memory when available (default), 1 = ncclAllReduce, 2 = peer memory (abort if it
+ * is not available).  All ranks must choose the same.  Collectives of one context must be issued in the same order
+ * on every rank (as with any communicator). */
+PIQUANT_EXPORT void piquant_cuda_comm_set_transport(piquant_context_t* ctx, int transport);
+/* The transport in use: 0 = no communicator, 1 = ncclAllReduce, 2 = peer memory. */
+PIQUANT_EXPORT int  piquant_cuda_comm_transport(piquant_context_t* ctx);
 
 /* ---- device-resident parameters: no host round trip between min/max, (scale, zero_point) and quantize ----
  * The reference's callers do  params = compute_quant_params(x); q = quantize(x, params)  with a join after
@@ -143,6 +152,86 @@ PIQUANT_EXPORT void piquant_cuda_dequantize_meta_async(piquant_context_t* ctx, c
 PIQUANT_EXPORT void piquant_cuda_quantize_auto(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
                                                piquant_dtype_t dtype_out, size_t numel, piquant_round_mode_t mode,
                                                float* out_scale, int64_t* out_zero_point);
+
+/* ---- explicit device and stream per call --------------------------------------------------------------------
+ * piquant_cuda_set_stream is context state: two threads sharing a context would have to serialise "bind, then call".
+ * Every function below has the meaning of the function it is named after, with two trailing arguments instead of that
+ * state, so that no call mutates anything another thread depends on (the reference tolerates concurrent calls on one
+ * context, reference src/piquant.cpp:194-211 -- so does this library: scratch memory is per stream):
+ *   device >= 0 : the caller vouches that every pointer of the call is device-accessible memory of that CUDA device
+ *                 (what a torch CUDA tensor knows about itself): no pointer classification, no driver query per call;
+ *   device == PIQUANT_CUDA_DEVICE_AUTO : find out from the pointers like the piquant.h functions do (host pointers are
+ *                 accepted wherever they are there);
+ *   stream      : the cudaStream_t the work is ordered on (NULL = legacy default stream). */
+#define PIQUANT_CUDA_DEVICE_AUTO (-1)
+/* flags */
+#define PIQUANT_CUDA_FLAG_LOCAL      1u   /* min/max of THIS tensor only, even if the context has a communicator */
+#define PIQUANT_CUDA_FLAG_KEEP_IN_L2 2u   /* min/max: read with L2::evict_last, a pass over the same tensor follows */
+#define PIQUANT_CUDA_FLAG_REVERSE    4u   /* quantize: process the tensor from its end (what the previous pass left in L2) */
+
+PIQUANT_EXPORT void piquant_cuda_quantize_on_stream(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                                    piquant_dtype_t dtype_out, size_t numel, float scale, int64_t zero_point,
+                                                    piquant_round_mode_t mode, int device, void* stream);
+PIQUANT_EXPORT void piquant_cuda_dequantize_on_stream(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                                      piquant_dtype_t dtype_out, size_t numel, float scale, int64_t zero_point,
+                                                      piquant_reduce_op_t op, int device, void* stream);
+PIQUANT_EXPORT void piquant_cuda_requantize_on_stream(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in_out, void* out,
+                                                      piquant_dtype_t quant_dtype, size_t numel, float scale, int64_t zero_point,
+                                                      piquant_round_mode_t mode, piquant_reduce_op_t op, int device, void* stream);
+/* piquant_compute_quant_params_float32 / _bfloat16 (dtype says which); synchronises `stream`. */
+PIQUANT_EXPORT void piquant_cuda_compute_quant_params_on_stream(piquant_context_t* ctx, const void* x, piquant_dtype_t dtype, size_t n,
+                                                                piquant_dtype_t target_quant_dtype, float* out_scale,
+                                                                int64_t* out_zero_point, int device, void* stream);
+PIQUANT_EXPORT void piquant_cuda_minmax_on_stream(piquant_context_t* ctx, const void* x, piquant_dtype_t dtype, size_t n, float* out4,
+                                                  unsigned flags, int device, void* stream);
+PIQUANT_EXPORT void piquant_cuda_compute_meta_on_stream(piquant_context_t* ctx, const void* x, piquant_dtype_t dtype, size_t n,
+                                                        piquant_dtype_t target_quant_dtype, piquant_cuda_meta_t* d_meta, unsigned flags,
+                                                        int device, void* stream);
+PIQUANT_EXPORT void piquant_cuda_quantize_meta_on_stream(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                                         piquant_dtype_t dtype_out, size_t numel, piquant_round_mode_t mode,
+                                                         const piquant_cuda_meta_t* d_meta, unsigned flags, int device, void* stream);
+PIQUANT_EXPORT void piquant_cuda_dequantize_meta_on_stream(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                                           piquant_dtype_t dtype_out, size_t numel, piquant_reduce_op_t op,
+                                                           const piquant_cuda_meta_t* d_meta, int device, void* stream);
+PIQUANT_EXPORT void piquant_cuda_quantize_auto_on_stream(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                                         piquant_dtype_t dtype_out, size_t numel, piquant_round_mode_t mode,
+                                                         float* out_scale, int64_t* out_zero_point, int device, void* stream);
+
+/* ---- the two fused passes of a quantized ring reduction (the caller the ADD store op exists for, reference README.md:29) ----
+ *
+ * Reduce-scatter hop, receiver side:  out += dequantize(in; d_meta)   (piquant_dequantize with PIQUANT_REDUCE_OP_ADD)
+ * and, in the same launch, min/max of the sums just written -> the reference's (scale, zero_point) arithmetic for
+ * next_quant_dtype -> d_meta_next (and a second copy at d_meta_next_copy unless NULL, e.g. the header of the next
+ * receiver's slot in NVLink peer memory).  The chunk a rank accumulates at hop s is the chunk it quantizes and sends at
+ * hop s + 1, so the separate min/max pass over it -- a full HBM read -- disappears; results are bit-identical to
+ * dequantize-ADD followed by piquant_cuda_compute_meta (local).  Never uses the communicator. */
+PIQUANT_EXPORT void piquant_cuda_dequantize_add_minmax_on_stream(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                                                 piquant_dtype_t dtype_out, size_t numel, const piquant_cuda_meta_t* d_meta,
+                                                                 piquant_dtype_t next_quant_dtype, piquant_cuda_meta_t* d_meta_next,
+                                                                 piquant_cuda_meta_t* d_meta_next_copy, int device, void* stream);
+/* All-gather hop:  out = dequantize(in; d_meta)   (PIQUANT_REDUCE_OP_SET)  and, in the same launch, the packed bytes of
+ * `in` are stored unchanged to forward_to and the 64-byte block d_meta to forward_meta_to (NULL: not forwarded) --
+ * typically the next rank's receive slot in peer memory: the hop's dequantize IS its send. */
+PIQUANT_EXPORT void piquant_cuda_dequantize_forward_on_stream(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
+                                                              piquant_dtype_t dtype_out, size_t numel, const piquant_cuda_meta_t* d_meta,
+                                                              void* forward_to, piquant_cuda_meta_t* forward_meta_to, int device, void* stream);
+
+/* ---- many small tensors, one launch -----------------------------------------------------------------------------
+ * The reference's own Python benchmark quantizes a 1e6-element tensor 1000 times (reference python/benchmark/benchmark.py:16-23);
+ * on a GPU a launch costs more than 1e6 elements of data.  One call quantizes `count` independent tensors -- each with
+ * its own pointers, length, scale and zero point, all f32 or all bf16 into one quantized dtype -- in ONE kernel launch
+ * per 256 tensors; every tensor gets exactly the bytes a piquant_quantize call on it would produce.  Device memory
+ * only; mode: PIQUANT_NEAREST or PIQUANT_STOCHASTIC (one threshold for the whole batch). */
+typedef struct piquant_cuda_batch_item_t {
+    const void* in;
+    void*       out;
+    size_t      numel;
+    float       scale;
+    int64_t     zero_point;
+} piquant_cuda_batch_item_t;
+PIQUANT_EXPORT void piquant_cuda_quantize_batch(piquant_context_t* ctx, const piquant_cuda_batch_item_t* items, size_t count,
+                                                piquant_dtype_t dtype_in, piquant_dtype_t dtype_out, piquant_round_mode_t mode,
+                                                int device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,7 @@
 // HBM once in each direction.  U = 2 items per thread per tile keeps 128 B of stores (and, for ADD,
 // 128 B of loads) in flight per thread.  Ragged head/tail bytes are handled by the last CTA.
 #include "dequantize_common.cuh"
+#include "pq_reduce.cuh"
 
 namespace pq {
 
@@ -18,9 +19,25 @@ namespace pq {
 #endif
 constexpr int kDequantItemsPerThread = PQ_DEQUANT_U;
 
-template <int BITS, int OUT_DT, int OP, bool A32>
-__global__ void __launch_bounds__(kThreads) dequant_stream_kernel(const DequantArgs a_in) {
-    DequantArgs a = a_in;
+// What a fused launch does besides dequantizing (the two halves of a quantized ring reduction, reference README.md:29):
+//   FUSE_MINMAX  (with ADD): min/max of the values this launch WROTE, folded by the pq_reduce.cuh tail into the parameter
+//                block of the next hop -- the chunk a rank accumulates at hop s is exactly the chunk it quantizes and sends at
+//                hop s + 1, so the separate min/max pass over it (a full HBM read) disappears.  The sums are stored with
+//                L2::evict_last: the quantize pass that follows finds the end of the chunk still in the 126 MB L2.
+//   FUSE_FORWARD (with SET): the packed input words are also stored, unchanged, to `fwd` -- the next rank's receive slot in
+//                NVLink peer memory -- together with the 64-byte parameter block: one kernel is both the all-gather
+//                hop's dequantize and its send.
+enum : int { FUSE_NONE = 0, FUSE_MINMAX = 1, FUSE_FORWARD = 2 };
+
+struct DequantFuse {
+    ReduceTail        tail;           // FUSE_MINMAX
+    uint8_t*          fwd;            // FUSE_FORWARD: same byte phase (mod 32) as the packed input
+    const DeviceMeta* fwd_meta_src;   // FUSE_FORWARD: parameter block to pass on ...
+    DeviceMeta*       fwd_meta_dst;   // ... and where (nullptr: none)
+};
+
+template <int BITS, int OUT_DT, int OP, bool A32, int FUSE>
+__device__ __forceinline__ void dequant_stream_body(DequantArgs& a, [[maybe_unused]] const DequantFuse* f) {
     constexpr int PER = 8 / BITS;
     constexpr int V = OUT_DT == DT_F32 ? 16 : 32;       // elements per item (64 output bytes)
     constexpr int OSZ = OUT_DT == DT_F32 ? 4 : 2;
@@ -36,7 +53,19 @@ __global__ void __launch_bounds__(kThreads) dequant_stream_kernel(const DequantA
     const int64_t n_tiles = (a.n_items + TILE - 1) / TILE;
     pdl_launch_dependents();
     pdl_wait();
-    load_device_params<BITS, OUT_DT>(a);
+    if (!load_device_params<BITS, OUT_DT>(a)) {
+        // flagged parameters: nothing is dequantized; a fused min/max passes the flag on to the block it was to produce
+        if constexpr (FUSE == FUSE_MINMAX) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                if (f->tail.meta_out) f->tail.meta_out->error = 1;
+                if (f->tail.meta_out2) { f->tail.meta_out2->error = 1; __threadfence_system(); }
+            }
+        }
+        return;
+    }
+
+    [[maybe_unused]] float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+    [[maybe_unused]] uint32_t pmn = 0x7f807f80u, pmx = 0xff80ff80u;      // packed bf16x2 accumulators
 
     if (const int64_t tile = blockIdx.x; tile < n_tiles) {      // one tile per CTA, hardware-scheduled (see quantize.cu)
         const int64_t first = tile * TILE + threadIdx.x;
@@ -54,6 +83,7 @@ __global__ void __launch_bounds__(kThreads) dequant_stream_kernel(const DequantA
         for (int u = 0; u < U; ++u) {
             const int64_t item = first + static_cast<int64_t>(u) * kThreads;
             if (item < a.n_items) {
+                if constexpr (FUSE == FUSE_FORWARD) store_words<NWI, A32>(f->fwd + a.head_bytes + item * IB, wi[u]);
                 uint32_t wo[NWO];
 #pragma unroll
                 for (int k = 0; k < NWI; ++k) wi[u][k] ^= a.P.sign_xor;     // signed dtypes: two's complement -> offset binary
@@ -71,17 +101,70 @@ __global__ void __launch_bounds__(kThreads) dequant_stream_kernel(const DequantA
                         wo[e >> 1] = pack_bf16x2(lo, hi);
                     }
                 }
-                store_words<NWO, A32>(out + item * 64, wo);
+                if constexpr (FUSE == FUSE_MINMAX) {
+#pragma unroll
+                    for (int k = 0; k < NWO; ++k) {
+                        if constexpr (OUT_DT == DT_F32) {
+                            mn = fminf(mn, __uint_as_float(wo[k]));
+                            mx = fmaxf(mx, __uint_as_float(wo[k]));
+                        } else {            // of the ROUNDED bf16 values: what a min/max pass over the stored tensor would see
+                            pmn = min_bf16x2(pmn, wo[k]);
+                            pmx = max_bf16x2(pmx, wo[k]);
+                        }
+                    }
+                }
+                store_words<NWO, A32, FUSE == FUSE_MINMAX>(out + item * 64, wo);
             }
         }
     }
 
     if (blockIdx.x == gridDim.x - 1) {
         const int64_t total = (a.numel + PER - 1) / PER;
-        for (int64_t b = threadIdx.x; b < a.head_bytes; b += kThreads) dequant_one_byte<BITS, OUT_DT, OP>(a, b);
-        for (int64_t b = a.head_bytes + a.n_items * IB + threadIdx.x; b < total; b += kThreads)
+        auto ragged = [&](int64_t b) {
             dequant_one_byte<BITS, OUT_DT, OP>(a, b);
+            if constexpr (FUSE == FUSE_FORWARD) f->fwd[b] = a.in[b];
+            if constexpr (FUSE == FUSE_MINMAX) {        // fold what this thread has just stored
+#pragma unroll
+                for (int k = 0; k < PER; ++k) {
+                    const int64_t e = b * PER + k;
+                    if (e < a.numel) {
+                        float v;
+                        if constexpr (OUT_DT == DT_F32) v = reinterpret_cast<const float*>(a.out)[e];
+                        else v = bf16_bits_to_f32(reinterpret_cast<const uint16_t*>(a.out)[e]);
+                        mn = fminf(mn, v);
+                        mx = fmaxf(mx, v);
+                    }
+                }
+            }
+        };
+        for (int64_t b = threadIdx.x; b < a.head_bytes; b += kThreads) ragged(b);
+        for (int64_t b = a.head_bytes + a.n_items * IB + threadIdx.x; b < total; b += kThreads) ragged(b);
+        if constexpr (FUSE == FUSE_FORWARD) {
+            if (f->fwd_meta_dst && threadIdx.x < 16)       // 64 bytes = 16 words; the block was written by an earlier kernel on the stream
+                reinterpret_cast<uint32_t*>(f->fwd_meta_dst)[threadIdx.x] = reinterpret_cast<const uint32_t*>(f->fwd_meta_src)[threadIdx.x];
+        }
     }
+    if constexpr (FUSE == FUSE_MINMAX) {
+        if constexpr (OUT_DT == DT_BF16) {
+            mn = fminf(mn, fminf(bf16_lo(pmn), bf16_hi(pmn)));
+            mx = fmaxf(mx, fmaxf(bf16_lo(pmx), bf16_hi(pmx)));
+        }
+        cta_reduce_tail(mn, mx, f->tail);
+    }
+}
+
+template <int BITS, int OUT_DT, int OP, bool A32>
+__global__ void __launch_bounds__(kThreads) dequant_stream_kernel(const DequantArgs a_in) {
+    DequantArgs a = a_in;
+    dequant_stream_body<BITS, OUT_DT, OP, A32, FUSE_NONE>(a, nullptr);
+}
+
+// the same pass with one of the fused epilogues; `f` lives in the kernel's parameter space (constant bank)
+template <int BITS, int OUT_DT, int OP, bool A32, int FUSE>
+__global__ void __launch_bounds__(kThreads) dequant_fused_kernel(const DequantArgs a_in, const DequantFuse f) {
+    static_assert((FUSE == FUSE_MINMAX && OP == OP_ADD) || (FUSE == FUSE_FORWARD && OP == OP_SET));
+    DequantArgs a = a_in;
+    dequant_stream_body<BITS, OUT_DT, OP, A32, FUSE>(a, &f);
 }
 
 // Any alignment: one thread per packed input byte.
@@ -92,7 +175,7 @@ __global__ void __launch_bounds__(kThreads) dequant_bytes_kernel(const DequantAr
     const int64_t total = (a.numel + PER - 1) / PER;
     pdl_launch_dependents();
     pdl_wait();
-    load_device_params<BITS, OUT_DT>(a);
+    if (!load_device_params<BITS, OUT_DT>(a)) return;
     for (int64_t b = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; b < total;
          b += static_cast<int64_t>(gridDim.x) * kThreads)
         dequant_one_byte<BITS, OUT_DT, OP>(a, b);
@@ -103,9 +186,21 @@ __global__ void __launch_bounds__(kThreads) dequant_bytes_kernel(const DequantAr
 // ---------------------------------------------------------------------------------------------
 
 using DequantKernel = void (*)(const DequantArgs);
+using DequantFusedKernel = void (*)(const DequantArgs, const DequantFuse);
+
+// host-side request for a fused epilogue (see DequantFuse)
+struct FuseRequest {
+    int                  kind = FUSE_NONE;
+    const MinMaxScratch* scratch = nullptr;   // FUSE_MINMAX
+    const ReduceOut*     reduce = nullptr;    // FUSE_MINMAX
+    void*                fwd = nullptr;       // FUSE_FORWARD
+    const DeviceMeta*    fwd_meta_src = nullptr;
+    DeviceMeta*          fwd_meta_dst = nullptr;
+};
 
 template <int BITS, int OUT_DT, int OP>
-static void launch_cell(const void* in, void* out, int64_t numel, const QuantParams& P, const LaunchCfg& cfg, const QuantParams* dP) {
+static int launch_cell(const void* in, void* out, int64_t numel, const QuantParams& P, const LaunchCfg& cfg, const QuantParams* dP,
+                       const FuseRequest& fr) {
     constexpr int PER = 8 / BITS;
     constexpr int V = OUT_DT == DT_F32 ? 16 : 32;
     constexpr int OSZ = OUT_DT == DT_F32 ? 4 : 2;
@@ -142,11 +237,34 @@ static void launch_cell(const void* in, void* out, int64_t numel, const QuantPar
             }
         }
     }
+    const int64_t tile = static_cast<int64_t>(kThreads) * kDequantItemsPerThread;
+    // a fused epilogue rides on the vector kernel only; the caller splits the work when this returns 0
+    if (fr.kind != FUSE_NONE) {
+        if (!vec) return 0;
+        const int64_t grid = (a.n_items + tile - 1) / tile;
+        DequantFuse f{};
+        DequantFusedKernel fn = nullptr;
+        if constexpr (OP == OP_ADD) {
+            if (fr.kind != FUSE_MINMAX || grid > fr.scratch->max_blocks) return 0;
+            f.tail = make_reduce_tail(*fr.scratch, *fr.reduce);
+            fn = a32 ? dequant_fused_kernel<BITS, OUT_DT, OP_ADD, true, FUSE_MINMAX> : dequant_fused_kernel<BITS, OUT_DT, OP_ADD, false, FUSE_MINMAX>;
+        } else {
+            if (fr.kind != FUSE_FORWARD) return 0;
+            // the forwarded copy uses the input's vector stores: same phase modulo 32 bytes required
+            if ((reinterpret_cast<uintptr_t>(fr.fwd) & 31u) != (reinterpret_cast<uintptr_t>(in) & 31u)) return 0;
+            f.fwd = static_cast<uint8_t*>(fr.fwd);
+            f.fwd_meta_src = fr.fwd_meta_src;
+            f.fwd_meta_dst = fr.fwd_meta_dst;
+            fn = a32 ? dequant_fused_kernel<BITS, OUT_DT, OP_SET, true, FUSE_FORWARD> : dequant_fused_kernel<BITS, OUT_DT, OP_SET, false, FUSE_FORWARD>;
+        }
+        launch_kernel(fn, static_cast<unsigned>(grid < 1 ? 1 : grid), kThreads, 0, cfg.stream, a, f);
+        PQ_CUDA_CHECK(cudaGetLastError());
+        return 1;
+    }
     DequantKernel fn;
     int64_t blocks_needed;
     if (vec) {
         fn = a32 ? dequant_stream_kernel<BITS, OUT_DT, OP, true> : dequant_stream_kernel<BITS, OUT_DT, OP, false>;
-        const int64_t tile = static_cast<int64_t>(kThreads) * kDequantItemsPerThread;
         blocks_needed = (a.n_items + tile - 1) / tile;
     } else {
         fn = dequant_bytes_kernel<BITS, OUT_DT, OP>;
@@ -163,21 +281,30 @@ static void launch_cell(const void* in, void* out, int64_t numel, const QuantPar
     if (grid < 1) grid = 1;
     launch_kernel(fn, static_cast<unsigned>(grid), kThreads, 0, cfg.stream, a);
     PQ_CUDA_CHECK(cudaGetLastError());
+    return 1;
 }
 
 template <int BITS, int OUT_DT>
-static void launch_op(const void* in, void* out, int64_t numel, const QuantParams& P, int op, const LaunchCfg& cfg, const QuantParams* dP) {
-    if (op == OP_ADD) launch_cell<BITS, OUT_DT, OP_ADD>(in, out, numel, P, cfg, dP);
-    else launch_cell<BITS, OUT_DT, OP_SET>(in, out, numel, P, cfg, dP);
+static int launch_op(const void* in, void* out, int64_t numel, const QuantParams& P, int op, const LaunchCfg& cfg, const QuantParams* dP,
+                     const FuseRequest& fr) {
+    if (op == OP_ADD) return launch_cell<BITS, OUT_DT, OP_ADD>(in, out, numel, P, cfg, dP, fr);
+    return launch_cell<BITS, OUT_DT, OP_SET>(in, out, numel, P, cfg, dP, fr);
 }
 
 template <int OUT_DT>
-static void launch_in(const void* in, int dt_in, void* out, int64_t numel, const QuantParams& P, int op, const LaunchCfg& cfg, const QuantParams* dP) {
+static int launch_in(const void* in, int dt_in, void* out, int64_t numel, const QuantParams& P, int op, const LaunchCfg& cfg, const QuantParams* dP,
+                     const FuseRequest& fr) {
     switch (dt_in) {
-        case DT_U8: launch_op<8, OUT_DT>(in, out, numel, P, op, cfg, dP); break;
-        case DT_U4: launch_op<4, OUT_DT>(in, out, numel, P, op, cfg, dP); break;
-        default:    launch_op<2, OUT_DT>(in, out, numel, P, op, cfg, dP); break;
+        case DT_U8: return launch_op<8, OUT_DT>(in, out, numel, P, op, cfg, dP, fr);
+        case DT_U4: return launch_op<4, OUT_DT>(in, out, numel, P, op, cfg, dP, fr);
+        default:    return launch_op<2, OUT_DT>(in, out, numel, P, op, cfg, dP, fr);
     }
+}
+
+static int launch_direct(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int op,
+                         const LaunchCfg& cfg, const QuantParams* dP, const FuseRequest& fr) {
+    if (dt_out == DT_F32) return launch_in<DT_F32>(in, dt_in, out, numel, P, op, cfg, dP, fr);
+    return launch_in<DT_BF16>(in, dt_in, out, numel, P, op, cfg, dP, fr);
 }
 
 int launch_dequantize_tma(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int op,
@@ -186,16 +313,41 @@ int launch_dequantize_tma(const void* in, int dt_in, void* out, int dt_out, int6
 int launch_dequantize(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P, int op,
                       const LaunchCfg& cfg, const QuantParams* dP) {
     if (numel <= 0) return 0;
-    // variant 2: the TMA ring kernel whenever both streams can be 16-byte aligned; 1: direct kernels;
-    // 0 (auto): TMA for large tensors (measured crossover, see dequantize_prefers_tma)
-    const int64_t traffic = numel * (dtype_bits(dt_out) / 8) * (op == OP_ADD ? 2 : 1) + numel * dtype_bits(dt_in) / 8;
-    if (cfg.variant == 2 || (cfg.variant == 0 && dequantize_prefers_tma(traffic))) {
+    // variant 2: the TMA ring kernel whenever both streams can be 16-byte aligned; 0 (auto) and 1: the direct kernels
+    // (selection table: pq_kernels.h)
+    if (cfg.variant == 2) {
         const int n = launch_dequantize_tma(in, dt_in, out, dt_out, numel, P, op, cfg, dP);
         if (n) return n;
     }
-    if (dt_out == DT_F32) launch_in<DT_F32>(in, dt_in, out, numel, P, op, cfg, dP);
-    else launch_in<DT_BF16>(in, dt_in, out, numel, P, op, cfg, dP);
-    return 1;
+    return launch_direct(in, dt_in, out, dt_out, numel, P, op, cfg, dP, FuseRequest{});
+}
+
+int launch_dequantize_add_minmax(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P,
+                                 const LaunchCfg& cfg, const QuantParams* dP, const MinMaxScratch& scratch, const ReduceOut& ro) {
+    pq_assert(numel > 0, "dequantize-ADD + min/max of an empty tensor");
+    FuseRequest fr;
+    fr.kind = FUSE_MINMAX;
+    fr.scratch = &scratch;
+    fr.reduce = &ro;
+    if (const int n = launch_direct(in, dt_in, out, dt_out, numel, P, OP_ADD, cfg, dP, fr)) return n;
+    // buffers that cannot be vector-aligned (or more tiles than partial slots): the two passes, same results
+    const int n = launch_direct(in, dt_in, out, dt_out, numel, P, OP_ADD, cfg, dP, FuseRequest{});
+    return n + launch_minmax(out, dt_out, numel, scratch, ro, cfg, true);
+}
+
+int launch_dequantize_forward(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P,
+                              const LaunchCfg& cfg, const QuantParams* dP, void* fwd, const DeviceMeta* fwd_meta_src,
+                              DeviceMeta* fwd_meta_dst) {
+    pq_assert(numel > 0, "dequantize + forward of an empty tensor");
+    FuseRequest fr;
+    fr.kind = FUSE_FORWARD;
+    fr.fwd = fwd;
+    fr.fwd_meta_src = fwd_meta_src;
+    fr.fwd_meta_dst = fwd_meta_dst;
+    if (const int n = launch_direct(in, dt_in, out, dt_out, numel, P, OP_SET, cfg, dP, fr)) return n;
+    PQ_CUDA_CHECK(cudaMemcpyAsync(fwd, in, packed_bytes(dt_in, static_cast<size_t>(numel)), cudaMemcpyDeviceToDevice, cfg.stream));
+    if (fwd_meta_dst) PQ_CUDA_CHECK(cudaMemcpyAsync(fwd_meta_dst, fwd_meta_src, sizeof(DeviceMeta), cudaMemcpyDeviceToDevice, cfg.stream));
+    return launch_direct(in, dt_in, out, dt_out, numel, P, OP_SET, cfg, dP, FuseRequest{});
 }
 
 }  // namespace pq

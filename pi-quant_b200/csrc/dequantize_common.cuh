@@ -26,11 +26,13 @@ __host__ __device__ inline void set_dequant_fast(DequantArgs& a, int bits, int o
 
 // Parameters computed by an earlier kernel on the stream replace the by-value ones.  Call after pdl_wait().
 template <int BITS, int OUT_DT>
-__device__ __forceinline__ void load_device_params(DequantArgs& a) {
+__device__ __forceinline__ bool load_device_params(DequantArgs& a) {
     if (a.dP) {
+        if (device_params_failed(a.dP)) return false;      // flagged block: no work (see pq_device.cuh)
         a.P = *a.dP;
         set_dequant_fast(a, BITS, OUT_DT);
     }
+    return true;
 }
 
 // All elements of one packed input byte (elements past numel are skipped).

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kDqThreads) dequant_tma_kernel(const DequantAr
     __syncthreads();
     pdl_launch_dependents();
     pdl_wait();
-    load_device_params<BITS, OUT_DT>(a);
+    if (!load_device_params<BITS, OUT_DT>(a)) return;
 
     if (threadIdx.x < 32) {
         if (threadIdx.x == 0) {

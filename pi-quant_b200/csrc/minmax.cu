@@ -11,33 +11,17 @@
 // reference for any reduction order.  NaNs never win a comparison (the reference's scalar loops use
 // `<` / `>`); accumulators start at +-inf and are clamped to +-FLT_MAX at the end, which equals the
 // reference's +-FLT_MAX start for every input.
-#include <cfloat>
-
-#include "pq_kernels.h"
+#include "pq_reduce.cuh"
 
 namespace pq {
-
-__device__ __forceinline__ uint32_t min_bf16x2(uint32_t a, uint32_t b) {
-    uint32_t d;
-    asm("min.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
-__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
-    uint32_t d;
-    asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-    return d;
-}
 
 struct MinMaxArgs {
     const char* x;
     int64_t     numel;
     int64_t     head;       // elements in front of the 32-byte aligned region
     int64_t     n_items;    // 32-byte items in the aligned region
-    float2*     partials;
-    unsigned*   ticket;
-    float*      result;         // device: {min, max, -min, max}
-    float*      mapped_result;  // device-mapped pinned host copy of the same, or nullptr
     int64_t     tiles_per_cta;  // each CTA folds this many consecutive tiles
+    ReduceTail  tail;           // partials / ticket scratch, where the result goes, optional parameters and rank exchange
 };
 
 template <int IN_DT, bool KEEP>
@@ -110,61 +94,36 @@ __global__ void __launch_bounds__(kThreads) minmax_kernel(const MinMaxArgs a) {
         for (int64_t e = a.head + a.n_items * EPI + threadIdx.x; e < a.numel; e += kThreads) fold(e);
     }
 
-    __shared__ float s_mn[kThreads / 32], s_mx[kThreads / 32];
-    __shared__ bool s_last;
-    mn = warp_min(mn);
-    mx = warp_max(mx);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 1; i < kThreads / 32; ++i) { mn = fminf(mn, s_mn[i]); mx = fmaxf(mx, s_mx[i]); }
-        a.partials[blockIdx.x] = make_float2(mn, mx);
-        __threadfence();
-        const unsigned t = atomicAdd(a.ticket, 1u);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    mn = __int_as_float(0x7f800000);
-    mx = __int_as_float(0xff800000);
-    for (unsigned i = threadIdx.x; i < gridDim.x; i += kThreads) {
-        const float2 p = __ldcg(a.partials + i);
-        mn = fminf(mn, p.x);
-        mx = fmaxf(mx, p.y);
-    }
-    mn = warp_min(mn);
-    mx = warp_max(mx);
-    __syncthreads();
-    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 1; i < kThreads / 32; ++i) { mn = fminf(mn, s_mn[i]); mx = fmaxf(mx, s_mx[i]); }
-        mn = fminf(mn, FLT_MAX);       // nothing below FLT_MAX seen -> the reference's start value
-        mx = fmaxf(mx, -FLT_MAX);
-        a.result[0] = mn; a.result[1] = mx; a.result[2] = -mn; a.result[3] = mx;
-        if (a.mapped_result) {
-            a.mapped_result[0] = mn; a.mapped_result[1] = mx; a.mapped_result[2] = -mn; a.mapped_result[3] = mx;
-            __threadfence_system();
-        }
-        *a.ticket = 0u;                // ready for the next launch on this stream
-    }
+    cta_reduce_tail(mn, mx, a.tail);
 }
 
-int launch_minmax(const void* x, int dt, int64_t numel, const MinMaxScratch& scratch, float* result,
-                  float* mapped_result, const LaunchCfg& cfg, bool keep_in_l2) {
+ReduceTail make_reduce_tail(const MinMaxScratch& scratch, const ReduceOut& ro) {
+    ReduceTail t{};
+    t.partials = scratch.partials;
+    t.ticket = scratch.ticket;
+    t.result = ro.result;
+    t.mapped_result = ro.mapped_result;
+    t.meta_out = ro.meta_out;
+    t.meta_out2 = ro.meta_out2;
+    t.meta_mapped = ro.meta_mapped;
+    if (ro.meta_out) {
+        pq_assert(dtype_is_quant(ro.dt_quant), "type %s is not a quantization type", dtype_name(ro.dt_quant));
+        t.q_bits = dtype_bits(ro.dt_quant);
+        t.q_signed = dtype_is_signed_quant(ro.dt_quant) ? 1 : 0;
+        t.q_sign_xor = dtype_sign_xor(ro.dt_quant);
+    }
+    if (ro.px) t.px = *ro.px;
+    return t;
+}
+
+int launch_minmax(const void* x, int dt, int64_t numel, const MinMaxScratch& scratch, const ReduceOut& ro,
+                  const LaunchCfg& cfg, bool keep_in_l2) {
     const int isz = dt == DT_F32 ? 4 : 2;
     const int epi = 32 / isz;
     MinMaxArgs a;
     a.x = static_cast<const char*>(x);
     a.numel = numel;
-    a.partials = scratch.partials;
-    a.ticket = scratch.ticket;
-    a.result = result;
-    a.mapped_result = mapped_result;
+    a.tail = make_reduce_tail(scratch, ro);
     const uintptr_t addr = reinterpret_cast<uintptr_t>(x);
     int64_t head = static_cast<int64_t>(((32 - (addr & 31u)) & 31u) / isz);   // natural alignment of x is assumed
     if (head > numel) head = numel;
@@ -187,46 +146,10 @@ int launch_minmax(const void* x, int dt, int64_t numel, const MinMaxScratch& scr
 // (scale, zero_point) on the device
 // ---------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ long long dev_cvttsd_i64(double a) {     // x86 cvttsd2si: out of range / NaN -> INT64_MIN
-    return (a >= -9223372036854775808.0 && a < 9223372036854775808.0) ? __double2ll_rz(a) : LLONG_MIN;
-}
-
 __global__ void params_kernel(const float* minmax4, int bits, int is_signed, uint32_t sign_xor, DeviceMeta* out, DeviceMeta* mapped_out) {
     pdl_launch_dependents();
     pdl_wait();
-    // same expressions, same order, same IEEE double operations as params_from_minmax() in context.cu
-    const double r_min = -static_cast<double>(minmax4[2]), r_max = static_cast<double>(minmax4[3]);
-    const unsigned long long type_max = (1ull << (bits - (is_signed ? 1 : 0))) - 1;
-    const long long type_min = is_signed ? -static_cast<long long>(type_max) - 1 : 0;
-    float s;
-    long long z;
-    if (r_max == r_min) {
-        s = 1.0f;
-        z = is_signed ? -1 : static_cast<long long>(type_max >> 1);
-    } else {
-        const double q_min = static_cast<double>(type_min), q_max = static_cast<double>(type_max);
-        const double sd = __ddiv_rn(__dsub_rn(r_max, r_min), __dsub_rn(q_max, q_min));
-        double zp = __dsub_rn(q_min, __ddiv_rn(r_min, sd));
-        zp = fmax(fmin(static_cast<double>(dev_cvttsd_i64(round(zp))), q_max), q_min);
-        s = __double2float_rn(sd);
-        z = dev_cvttsd_i64(zp);
-    }
-    DeviceMeta m;
-    m.scale = s;
-    m.error = (isnan(s) || !(s >= 0.0f)) ? 1 : 0;
-    m.zero_point = z;
-    // the kernels work on the unsigned (offset-binary) view of a signed type: make_params() in context.cu
-    z = static_cast<long long>(static_cast<unsigned long long>(z) + (is_signed ? (1ull << (bits - 1)) : 0ull));
-    m.P.sign_xor = sign_xor;
-    m.P.scale = s;
-    m.P.inv_scale = __fdiv_rn(1.0f, s);
-    m.P.xi = 0.0f;
-    m.P.zp64 = z;
-    m.P.zp32 = static_cast<int32_t>(static_cast<uint32_t>(static_cast<unsigned long long>(z)));
-    m.P.bias = __fmul_rn(-static_cast<float>(m.P.zp32), s);
-    m.P.bigzp = (z > (1ll << 29) || z < -(1ll << 29)) ? 1 : 0;
-    m.P.spec_ok32 = (m.P.zp32 <= (1 << 29) && m.P.zp32 >= -(1 << 29)) ? 1 : 0;
-    for (int i = 0; i < static_cast<int>(sizeof(m.pad)); ++i) m.pad[i] = 0;
+    const DeviceMeta m = meta_from_minmax(minmax4[2], minmax4[3], bits, is_signed, sign_xor);
     *out = m;
     if (mapped_out) {
         *mapped_out = m;

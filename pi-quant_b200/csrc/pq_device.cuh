@@ -43,6 +43,14 @@ struct QuantParams {
     int64_t zp64;
 };
 
+// Parameters produced on the device live inside a 64-byte DeviceMeta block (pq_kernels.h): {scale, error, zero_point, P}.
+// `error` != 0 means the reference would have aborted in compute_quant_params (scale NaN or negative, src/piquant.cpp:373);
+// a kernel handed such a block does no work at all -- the host cannot abort for it without a synchronisation -- and the
+// flag stays in the block for whoever reads the parameters back (piquant_cuda_quantize_auto aborts on it like the reference).
+__device__ __forceinline__ bool device_params_failed(const QuantParams* dP) {
+    return *reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(dP) - 12) != 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // programmatic dependent launch (see launch_kernel in pq_kernels.h)
 // ------------------------------------------------------------------------------------------------
@@ -102,6 +110,13 @@ __device__ __forceinline__ void stg_stream(void* p, const uint32_t (&r)[4]) {
                  :: "l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
 }
 
+// stores of data that a following pass will read again: ask L2 to keep the lines (SASS: STG.E.NA.ELL2)
+__device__ __forceinline__ void stg_keep(void* p, const uint32_t (&r)[8]) {
+    asm volatile("st.global.L1::no_allocate.L2::evict_last.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+// (the modifier exists for 32-byte stores only; the 16-byte-aligned variant of a kernel stores normally)
+
 // Load NW 32-bit words from a NW*4-byte aligned address (A32: 32-byte LDG.256, else 16-byte LDG.128).
 template <int NW, bool A32>
 __device__ __forceinline__ void load_words(const void* p, uint32_t (&w)[NW]) {
@@ -154,7 +169,8 @@ __device__ __forceinline__ void load_words_rmw(const void* p, uint32_t (&w)[NW])
     }
 }
 
-template <int NW, bool A32>
+// KEEP: L2::evict_last (a following pass reads the data again) instead of the plain streaming store
+template <int NW, bool A32, bool KEEP = false>
 __device__ __forceinline__ void store_words(void* p, const uint32_t (&w)[NW]) {
     if constexpr (A32 && NW >= 8) {
         static_assert(NW % 8 == 0);
@@ -163,9 +179,10 @@ __device__ __forceinline__ void store_words(void* p, const uint32_t (&w)[NW]) {
             uint32_t t[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) t[k] = w[8 * i + k];
-            stg_stream(static_cast<char*>(p) + 32 * i, t);
+            if constexpr (KEEP) stg_keep(static_cast<char*>(p) + 32 * i, t);
+            else stg_stream(static_cast<char*>(p) + 32 * i, t);
         }
-    } else {
+    } else if constexpr (NW >= 4) {
         static_assert(NW % 4 == 0);
 #pragma unroll
         for (int i = 0; i < NW / 4; ++i) {
@@ -174,6 +191,11 @@ __device__ __forceinline__ void store_words(void* p, const uint32_t (&w)[NW]) {
             for (int k = 0; k < 4; ++k) t[k] = w[4 * i + k];
             stg_stream(static_cast<char*>(p) + 16 * i, t);
         }
+    } else if constexpr (NW == 2) {
+        asm volatile("st.global.L1::no_allocate.v2.b32 [%0], {%1,%2};" ::"l"(p), "r"(w[0]), "r"(w[1]) : "memory");
+    } else {
+        static_assert(NW == 1);
+        asm volatile("st.global.L1::no_allocate.b32 [%0], %1;" ::"l"(p), "r"(w[0]) : "memory");
     }
 }
 
@@ -525,6 +547,18 @@ __device__ __forceinline__ float dequant_bf16_pre(uint32_t q, float prev, const 
 // ------------------------------------------------------------------------------------------------
 // reductions
 // ------------------------------------------------------------------------------------------------
+// two bf16 lanes per instruction (SASS: HMNMX2.BF16); NaN never wins, like the f32 fminf / fmaxf
+__device__ __forceinline__ uint32_t min_bf16x2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("min.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -19,6 +19,8 @@ struct LaunchCfg {
     unsigned long long* sched;   // {next tile, finished CTAs}: work counter of the persistent TMA kernels, zero between launches
     uint64_t     sr_key = 0;     // per-element stochastic rounding (mode 2): Philox key of the call
     int64_t      sr_base = 0;    // ... and the index of this launch's element 0 in the caller's tensor (host-pointer chunks)
+    bool         reverse = false;   // quantize: deal the tiles from the END of the tensor -- the pass before (min/max, or the
+                                    // dequantize-ADD that produced the tensor) touched the end last, so that is what L2 still holds
 };
 
 // [[noreturn]] abort with a red message on stderr -- the reference's error convention
@@ -118,19 +120,12 @@ int launch_dequantize(const void* in, int dt_in, void* out, int dt_out, int64_t 
 int launch_requantize(const void* in, int dt_inout, void* out, int dt_quant, int64_t numel, const QuantParams& P,
                       int mode, int op, const LaunchCfg& cfg, const QuantParams* device_params = nullptr);
 
-// Scratch owned by the context, one set per device.
+// Scratch of the ticketed single-launch reductions: one set per (device, stream) -- two streams never share a ticket.
 struct MinMaxScratch {
     float2*   partials;   // [max_blocks]
     unsigned* ticket;     // last-block-done counter, self-resetting
     int       max_blocks;
 };
-// Writes result[0..3] = {min, max, -min, max} (device memory) and, if `mapped_result` is not null,
-// the same four floats to that device-mapped pinned host address.  min/max start from +-FLT_MAX and
-// NaNs never win, like the reference (src/kernels/kernels_specialized.inl:1418-1607).
-// keep_in_l2: read with the default cache policy instead of evict-first, so that a tensor smaller than the
-// 126 MB L2 is still resident when the quantize pass that follows reads it again.
-int launch_minmax(const void* x, int dt, int64_t numel, const MinMaxScratch& scratch, float* result,
-                  float* mapped_result, const LaunchCfg& cfg, bool keep_in_l2 = false);
 
 // Parameters of one quantized tensor, produced and consumed on the device (include/piquant_cuda.h:
 // piquant_cuda_meta_t has the same 64-byte layout: 16 public bytes, then the kernel-side parameters).
@@ -143,6 +138,81 @@ struct DeviceMeta {
 };
 static_assert(sizeof(QuantParams) == 40, "QuantParams must keep fitting the opaque part of piquant_cuda_meta_t");
 static_assert(sizeof(DeviceMeta) == 64 && offsetof(DeviceMeta, P) == 16, "piquant_cuda_meta_t layout");
+
+// ---- whole-tensor {-min, max} across ranks, inside the kernel -----------------------------------------------------
+// Every rank owns a small mailbox in its own HBM, mapped into every other rank's address space (CUDA IPC over
+// NVLink / NVSwitch).  Exchange number `seq` (the same on every rank: collectives of one context are issued in the
+// same order everywhere): rank r stores its pair into slot [seq & 1][r] of EVERY rank's mailbox as two 8-byte words
+// {seq : value bits} -- an aligned 8-byte store is single-copy atomic, so a reader sees either the old or the new
+// word, never a torn one -- then polls its own mailbox until all `nranks` slots of this parity carry `seq`, and folds
+// them.  Two parities are enough: a rank cannot finish exchange s before every peer has written its s-word, which a
+// peer only does after it has finished READING exchange s - 1, so slot [s & 1] is never overwritten (by s + 2)
+// while someone still waits on it.
+constexpr int kMaxPeers = 16;
+constexpr int kMailboxWords = 2 * kMaxPeers * 2;      // [parity][rank][{-min, max}] x u64
+
+struct PeerExchange {
+    unsigned long long* box[kMaxPeers];   // box[r]: rank r's mailbox as mapped here (box[rank] is this GPU's own)
+    int      nranks;                      // <= 1: no exchange
+    int      rank;
+    unsigned seq;                         // >= 1
+};
+
+// What the tail writes and where.
+struct ReduceTail {
+    float2*     partials;        // [gridDim.x] per-CTA {min, max}
+    unsigned*   ticket;          // last-CTA-done counter, self-resetting
+    float*      result;          // device: {min, max, -min, max}
+    float*      mapped_result;   // pinned-mapped host copy of the same, or nullptr
+    DeviceMeta* meta_out;        // not null: also evaluate (scale, zero_point) for the quantized type below
+    DeviceMeta* meta_out2;       // second copy (e.g. the receiver's slot on a peer GPU), or nullptr
+    DeviceMeta* meta_mapped;     // pinned-mapped host copy, or nullptr
+    int         q_bits;          // 2 / 4 / 8
+    int         q_signed;
+    uint32_t    q_sign_xor;
+    PeerExchange px;
+};
+
+// Host-side description of what a reduction launch has to deliver (ReduceTail without the scratch).
+struct ReduceOut {
+    float*      result = nullptr;         // device {min, max, -min, max}; required
+    float*      mapped_result = nullptr;  // pinned-mapped host copy, optional
+    DeviceMeta* meta_out = nullptr;       // quantization parameters for dt_quant, optional
+    DeviceMeta* meta_out2 = nullptr;
+    DeviceMeta* meta_mapped = nullptr;
+    int         dt_quant = -1;            // quantized dtype the parameters are for (may be a signed extension type)
+    const PeerExchange* px = nullptr;     // whole-tensor result over the ranks of a communicator, optional
+};
+ReduceTail make_reduce_tail(const MinMaxScratch& scratch, const ReduceOut& ro);
+
+// One launch: result (+ optional parameter block, + optional cross-rank exchange) of x.  min/max start from +-FLT_MAX
+// and NaNs never win, like the reference (src/kernels/kernels_specialized.inl:1418-1607).
+// keep_in_l2: read with L2::evict_last instead of evict_first, so that a tensor smaller than the 126 MB L2 is still
+// resident when the quantize pass that follows reads it again.
+int launch_minmax(const void* x, int dt, int64_t numel, const MinMaxScratch& scratch, const ReduceOut& ro,
+                  const LaunchCfg& cfg, bool keep_in_l2 = false);
+
+// Fused passes of a quantized ring reduction (dequantize.cu).  Both return the number of kernels launched and fall back
+// to separate launches with identical results when the buffers cannot be vector-aligned.
+//   ADD + min/max: out += dequantize(in), and `ro` receives min/max (+ parameters, + rank exchange) of the sums written.
+//   SET + forward: out = dequantize(in), and the packed bytes of `in` (+ the 64-byte block fwd_meta_src) are also stored to
+//   fwd (+ fwd_meta_dst) -- typically the next rank's receive slot in NVLink peer memory.
+int launch_dequantize_add_minmax(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P,
+                                 const LaunchCfg& cfg, const QuantParams* device_params, const MinMaxScratch& scratch, const ReduceOut& ro);
+int launch_dequantize_forward(const void* in, int dt_in, void* out, int dt_out, int64_t numel, const QuantParams& P,
+                              const LaunchCfg& cfg, const QuantParams* device_params, void* fwd, const DeviceMeta* fwd_meta_src,
+                              DeviceMeta* fwd_meta_dst);
+
+// Many small tensors, ONE launch (quantize.cu): tensors[i] = {in, out, numel, scale, zero_point}, all with the same
+// (dt_in, dt_out, mode).  Returns the number of kernels launched (one per 256 tensors).
+struct BatchItem {
+    const void* in;
+    void*       out;
+    int64_t     numel;
+    float       scale;
+    int64_t     zero_point;
+};
+int launch_quantize_batch(const BatchItem* items, int count, int dt_in, int dt_out_view, int dt_out, int mode, float xi, const LaunchCfg& cfg);
 
 // One-thread kernel: the double-precision scale / zero-point arithmetic of the reference
 // (src/piquant.cpp:245-258) on the {-min, max} pair at minmax4[2..3], bit-identical to the host version,

@@ -75,11 +75,9 @@ __device__ __forceinline__ void quant_vector(const QuantArgs& a, int64_t group, 
 }
 }  // namespace
 
-// 8 CTAs per SM = 32 registers per thread: what the speculative path of every cell needs (bf16 stochastic wanted 39-40
-// for its exact fallback and ran at 6 CTAs per SM); the Philox cells (4 vectors per thread) get what keeps their hot path free of spills: <= 85 (f32) / <= 128 (bf16).
+// One tile (kThreads * J vectors) of the vectorised region, and -- for the CTA flagged `last` -- the ragged head / tail bytes.
 template <int IN_DT, int BITS, int STEP>
-__global__ void __launch_bounds__(kThreads, STEP != STEP_SRPE ? 8 : (IN_DT == DT_F32 ? 3 : 2)) quant_stream_kernel(const QuantArgs a_in) {
-    QuantArgs a = a_in;
+__device__ __forceinline__ void quant_tile(const QuantArgs& a, uint32_t tile, bool last) {
     constexpr int PER = 8 / BITS;                       // elements per packed byte
     constexpr int ISZ = IN_DT == DT_F32 ? 4 : 2;
     constexpr int EV = 32 / ISZ;                        // elements per 32-byte vector
@@ -91,16 +89,9 @@ __global__ void __launch_bounds__(kThreads, STEP != STEP_SRPE ? 8 : (IN_DT == DT
     uint8_t* out = a.out_body;
     // STEP_SRPE: Philox counter (= element index / 8) of vector 0; the host guarantees that vectors start on multiples of 8
     [[maybe_unused]] const int64_t vec_group0 = (a.sr_base + a.head_bytes * PER) >> 3;
-    pdl_launch_dependents();
-    pdl_wait();
-    load_device_params(a);
-
-    // ONE tile per CTA (grid == number of tiles): the hardware CTA scheduler deals tiles to whichever SM is free.  (A
-    // persistent grid with a static tile -> CTA map waits for its slowest SM -- the two dies differ by ~10 % -- and measured
-    // 7 % slower: profiles/r1_sched_probe_static_vs_dynamic_tiles.txt.)
-    const int64_t first = static_cast<int64_t>(blockIdx.x) * TILE + threadIdx.x;
+    const int64_t first = static_cast<int64_t>(tile) * TILE + threadIdx.x;
     uint32_t w[J][8];
-    if (blockIdx.x < a.n_full_tiles) {
+    if (tile < a.n_full_tiles) {
 #pragma unroll
         for (int j = 0; j < J; ++j) ldg_stream(in + (first + static_cast<int64_t>(j) * kThreads) * 32, w[j]);
 #pragma unroll
@@ -122,11 +113,132 @@ __global__ void __launch_bounds__(kThreads, STEP != STEP_SRPE ? 8 : (IN_DT == DT
         }
     }
 
-    if (blockIdx.x == gridDim.x - 1) {
+    if (last) {
         const int64_t total = (a.numel + PER - 1) / PER;
         for (int64_t b = threadIdx.x; b < a.head_bytes; b += kThreads) quant_one_byte<IN_DT, BITS, STEP>(a, b);
         for (int64_t b = a.head_bytes + a.n_items * 16 + threadIdx.x; b < total; b += kThreads)
             quant_one_byte<IN_DT, BITS, STEP>(a, b);
+    }
+}
+
+// 8 CTAs per SM = 32 registers per thread: what the speculative path of every cell needs (bf16 stochastic wanted 39-40
+// for its exact fallback and ran at 6 CTAs per SM); the Philox cells (4 vectors per thread) get what keeps their hot path free of spills: <= 85 (f32) / <= 128 (bf16).
+template <int IN_DT, int BITS, int STEP>
+__global__ void __launch_bounds__(kThreads, STEP != STEP_SRPE ? 8 : (IN_DT == DT_F32 ? 3 : 2)) quant_stream_kernel(const QuantArgs a_in) {
+    QuantArgs a = a_in;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (!load_device_params(a)) return;
+    // ONE tile per CTA (grid == number of tiles): the hardware CTA scheduler deals tiles to whichever SM is free.  (A
+    // persistent grid with a static tile -> CTA map waits for its slowest SM -- the two dies differ by ~10 % -- and measured
+    // 7 % slower: profiles/r1_sched_probe_static_vs_dynamic_tiles.txt.)  a.reverse: last tile first (LaunchCfg::reverse).
+    const uint32_t tile = a.reverse ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
+    quant_tile<IN_DT, BITS, STEP>(a, tile, blockIdx.x == gridDim.x - 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Many small tensors in ONE launch.
+//
+// The reference's own Python benchmark quantizes a 1e6-element tensor 1000 times (python/benchmark/benchmark.py:16-23): at
+// that size one tensor is 0.7 us of HBM time and a launch costs more than the data.  Here up to kBatchMax tensors -- each
+// with its own pointers, length, scale and zero point -- travel in the kernel's parameter space (40 bytes per tensor, no
+// staging copy, no device-side table to keep alive), a prefix sum of tiles maps blockIdx.x to (tensor, tile) with a
+// 9-step uniform binary search, and every CTA then runs exactly the single-tensor tile code above on a QuantArgs it
+// derives from the descriptor: same head / body / tail split, same bytes as a piquant_quantize call per tensor.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBatchMax = 256;
+
+struct BatchDesc {
+    const char* in;
+    uint8_t*    out;
+    int64_t     numel;
+    int64_t     zp64;        // kernel view (signed dtypes: + 2^(bits-1))
+    float       inv_scale;
+    float       scale;
+};
+
+struct BatchArgs {
+    int       count;
+    float     xi;
+    uint32_t  sign_xor;
+    uint32_t  tile_start[kBatchMax + 1];    // tile_start[i] .. tile_start[i+1]: CTAs of tensor i
+    BatchDesc t[kBatchMax];
+};
+
+// what launch_quantize() derives on the host for one tensor, on the device (both must agree: same split, same bytes)
+template <int IN_DT, int BITS>
+__host__ __device__ inline void batch_split(const char* in, const uint8_t* out, int64_t numel, int64_t& head_bytes, int64_t& n_items, bool& vec) {
+    constexpr int PER = 8 / BITS;
+    constexpr int ISZ = IN_DT == DT_F32 ? 4 : 2;
+    const int64_t full_bytes = numel / PER;
+    int64_t head = static_cast<int64_t>((16 - (reinterpret_cast<uintptr_t>(out) & 15u)) & 15u);
+    if (head > full_bytes) head = full_bytes;
+    head_bytes = head;
+    n_items = (full_bytes - head) / 16;
+    const uintptr_t in_vec = reinterpret_cast<uintptr_t>(in) + static_cast<uintptr_t>(head) * PER * ISZ;
+    vec = n_items > 0 && (in_vec & 31u) == 0;
+}
+
+template <int IN_DT, int BITS>
+__host__ __device__ inline uint32_t batch_tiles(const char* in, const uint8_t* out, int64_t numel) {
+    constexpr int PER = 8 / BITS;
+    constexpr int OB = (32 / (IN_DT == DT_F32 ? 4 : 2)) * BITS / 8;
+    constexpr int64_t TILE = static_cast<int64_t>(kThreads) * kVecPerThread;
+    int64_t head_bytes, n_items;
+    bool vec;
+    batch_split<IN_DT, BITS>(in, out, numel, head_bytes, n_items, vec);
+    int64_t tiles;
+    if (vec) tiles = (n_items * 16 / OB + TILE - 1) / TILE;
+    else tiles = ((numel + PER - 1) / PER + TILE * OB - 1) / (TILE * OB);      // byte-granular: the same bytes per CTA
+    return static_cast<uint32_t>(tiles < 1 ? 1 : tiles);
+}
+
+template <int IN_DT, int BITS, int STEP>
+__global__ void __launch_bounds__(kThreads, 8) quant_batch_kernel(const __grid_constant__ BatchArgs b) {
+    static_assert(STEP != STEP_SRPE, "the batch entry point serves nearest and per-call stochastic rounding");
+    constexpr int PER = 8 / BITS;
+    constexpr int ISZ = IN_DT == DT_F32 ? 4 : 2;
+    constexpr int OB = (32 / ISZ) * BITS / 8;
+    constexpr int64_t TILE = static_cast<int64_t>(kThreads) * kVecPerThread;
+    pdl_launch_dependents();
+    // which tensor does this CTA serve?  largest i with tile_start[i] <= blockIdx.x (uniform across the CTA)
+    int lo = 0, hi = b.count;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (b.tile_start[mid] <= blockIdx.x) lo = mid; else hi = mid;
+    }
+    const BatchDesc& d = b.t[lo];
+    const uint32_t tile = blockIdx.x - b.tile_start[lo];
+    const bool last = blockIdx.x + 1 == b.tile_start[lo + 1];
+    QuantArgs a;
+    a.in = d.in;
+    a.out = d.out;
+    a.numel = d.numel;
+    a.P.inv_scale = d.inv_scale;
+    a.P.scale = d.scale;
+    a.P.xi = b.xi;
+    a.P.bias = 0.0f;
+    a.P.zp64 = d.zp64;
+    a.P.zp32 = static_cast<int32_t>(static_cast<uint32_t>(static_cast<unsigned long long>(d.zp64)));
+    a.P.bigzp = (d.zp64 > (1ll << 29) || d.zp64 < -(1ll << 29)) ? 1 : 0;
+    a.P.spec_ok32 = (a.P.zp32 <= (1 << 29) && a.P.zp32 >= -(1 << 29)) ? 1 : 0;
+    a.P.sign_xor = b.sign_xor;
+    a.dP = nullptr;
+    a.sr_base = 0;
+    bool vec;
+    batch_split<IN_DT, BITS>(d.in, d.out, d.numel, a.head_bytes, a.n_items, vec);
+    pdl_wait();
+    if (vec) {
+        a.n_vecs = a.n_items * 16 / OB;
+        a.n_full_tiles = static_cast<uint32_t>(a.n_vecs / TILE);
+        a.in_body = a.in + a.head_bytes * PER * ISZ;
+        a.out_body = a.out + a.head_bytes;
+        quant_tile<IN_DT, BITS, STEP>(a, tile, last);
+    } else {
+        const int64_t total = (d.numel + PER - 1) / PER;
+        const int64_t b0 = static_cast<int64_t>(tile) * TILE * OB;
+        const int64_t b1 = b0 + TILE * OB < total ? b0 + TILE * OB : total;
+        for (int64_t x = b0 + threadIdx.x; x < b1; x += kThreads) quant_one_byte<IN_DT, BITS, STEP>(a, x);
     }
 }
 
@@ -205,9 +317,10 @@ __global__ void __launch_bounds__(kThreads, 8) quant_bf16_u2_threshold_kernel(co
     uint8_t* out = a.out_body;
     pdl_launch_dependents();
     pdl_wait();
-    const int64_t first = static_cast<int64_t>(blockIdx.x) * TILE + threadIdx.x;
+    const uint32_t tile = a.reverse ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
+    const int64_t first = static_cast<int64_t>(tile) * TILE + threadIdx.x;
     uint32_t w[J][8];
-    if (blockIdx.x < a.n_full_tiles) {
+    if (tile < a.n_full_tiles) {
 #pragma unroll
         for (int j = 0; j < J; ++j) ldg_stream(in + (first + static_cast<int64_t>(j) * kThreads) * 32, w[j]);
 #pragma unroll
@@ -315,7 +428,7 @@ __global__ void __launch_bounds__(kThreads) quant_bytes_kernel(const QuantArgs a
     const int64_t total = (a.numel + PER - 1) / PER;
     pdl_launch_dependents();
     pdl_wait();
-    load_device_params(a);
+    if (!load_device_params(a)) return;
     for (int64_t b = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; b < total;
          b += static_cast<int64_t>(gridDim.x) * kThreads)
         quant_one_byte<IN_DT, BITS, STEP>(a, b);
@@ -399,6 +512,7 @@ int launch_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t nu
     a.sched = nullptr;           // the direct kernels are scheduled by the hardware, one tile per CTA
     a.sr_key = PhiloxKey{static_cast<uint32_t>(cfg.sr_key), static_cast<uint32_t>(cfg.sr_key >> 32)};
     a.sr_base = cfg.sr_base;
+    a.reverse = cfg.reverse ? 1u : 0u;
     const int64_t full_bytes = numel / per;                      // bytes whose elements all exist
     int64_t head = static_cast<int64_t>((16 - (reinterpret_cast<uintptr_t>(out) & 15u)) & 15u);
     if (head > full_bytes) head = full_bytes;
@@ -426,6 +540,72 @@ int launch_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t nu
     if (dt_in == DT_F32) launch_out<DT_F32>(a, dt_out, mode, a32, cfg);
     else launch_out<DT_BF16>(a, dt_out, mode, a32, cfg);
     return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch launch
+// ---------------------------------------------------------------------------------------------
+
+template <int IN_DT, int BITS, int STEP>
+static int launch_batch_cell(const BatchItem* items, int count, int dt_out, float xi, const LaunchCfg& cfg) {
+    int launches = 0;
+    for (int base = 0; base < count;) {
+        BatchArgs b;
+        b.xi = xi;
+        b.sign_xor = dtype_sign_xor(dt_out);
+        int k = 0;
+        uint64_t tiles = 0;
+        while (base < count && k < kBatchMax) {
+            const BatchItem& it = items[base];
+            if (it.numel <= 0) { ++base; continue; }
+            const QuantParams P = make_params(it.scale, it.zero_point, xi, dt_out);
+            BatchDesc& d = b.t[k];
+            d.in = static_cast<const char*>(it.in);
+            d.out = static_cast<uint8_t*>(it.out);
+            d.numel = it.numel;
+            d.zp64 = P.zp64;
+            d.inv_scale = P.inv_scale;
+            d.scale = P.scale;
+            const uint32_t t = batch_tiles<IN_DT, BITS>(d.in, d.out, d.numel);
+            if (tiles + t >= (uint64_t{1} << 31)) {
+                pq_assert(k > 0, "tensor too large for the batch entry point (%llu tiles)", static_cast<unsigned long long>(t));
+                break;
+            }
+            b.tile_start[k] = static_cast<uint32_t>(tiles);
+            tiles += t;
+            ++k;
+            ++base;
+        }
+        if (k == 0) break;
+        b.count = k;
+        for (int i = k; i <= kBatchMax; ++i) b.tile_start[i] = static_cast<uint32_t>(tiles);
+        launch_kernel(quant_batch_kernel<IN_DT, BITS, STEP>, static_cast<unsigned>(tiles), kThreads, 0, cfg.stream, b);
+        PQ_CUDA_CHECK(cudaGetLastError());
+        ++launches;
+    }
+    return launches;
+}
+
+template <int IN_DT, int BITS>
+static int launch_batch_mode(const BatchItem* items, int count, int dt_out, int mode, float xi, const LaunchCfg& cfg) {
+    if (mode == 1) return launch_batch_cell<IN_DT, BITS, STEP_STOCH>(items, count, dt_out, xi, cfg);
+    if constexpr (IN_DT == DT_F32 && BITS == 2) return launch_batch_cell<IN_DT, BITS, STEP_ROUND64>(items, count, dt_out, xi, cfg);   // quantize.inl:132-148
+    else return launch_batch_cell<IN_DT, BITS, STEP_BODY>(items, count, dt_out, xi, cfg);
+}
+
+template <int IN_DT>
+static int launch_batch_out(const BatchItem* items, int count, int dt_out_view, int dt_out, int mode, float xi, const LaunchCfg& cfg) {
+    switch (dt_out_view) {
+        case DT_U8: return launch_batch_mode<IN_DT, 8>(items, count, dt_out, mode, xi, cfg);
+        case DT_U4: return launch_batch_mode<IN_DT, 4>(items, count, dt_out, mode, xi, cfg);
+        default:    return launch_batch_mode<IN_DT, 2>(items, count, dt_out, mode, xi, cfg);
+    }
+}
+
+int launch_quantize_batch(const BatchItem* items, int count, int dt_in, int dt_out_view, int dt_out, int mode, float xi, const LaunchCfg& cfg) {
+    pq_assert(mode == 0 || mode == 1, "the batch entry point serves nearest and per-call stochastic rounding, not mode %d", mode);
+    if (dt_in == DT_F32) return launch_batch_out<DT_F32>(items, count, dt_out_view, dt_out, mode, xi, cfg);
+    return launch_batch_out<DT_BF16>(items, count, dt_out_view, dt_out, mode, xi, cfg);
 }
 
 }  // namespace pq

@@ -20,6 +20,7 @@ struct QuantArgs {
     uint8_t*    out_body;    // out + head_bytes
     int64_t     n_vecs;      // 32-byte input vectors in the region
     uint32_t    n_full_tiles;
+    uint32_t    reverse;     // != 0: CTA b takes tile gridDim.x - 1 - b (LaunchCfg::reverse)
     // bf16 -> 2-bit threshold kernel (quantize.cu): q(x) = #{k : x >= thr[k]} while |x| <= thr_xlim
     uint32_t    thr[3];      // bf16 threshold k in both halves of the word
     uint32_t    thr_xlim;    // largest |x| (bf16 bits) for which the three compares are the exact result
@@ -34,12 +35,15 @@ __device__ __forceinline__ void srpe_words(const QuantArgs& a, int64_t g, uint32
 
 // Parameters computed by an earlier kernel on the stream replace the by-value ones (the per-call stochastic
 // threshold always comes from the host).  Call after pdl_wait().
-__device__ __forceinline__ void load_device_params(QuantArgs& a) {
+// Returns false when the block is flagged as failed: the kernel then returns without touching its output.
+__device__ __forceinline__ bool load_device_params(QuantArgs& a) {
     if (a.dP) {
+        if (device_params_failed(a.dP)) return false;
         const float xi = a.P.xi;
         a.P = *a.dP;
         a.P.xi = xi;
     }
+    return true;
 }
 
 template <int IN_DT>

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kTmaThreads) quant_tma_kernel(const QuantArgs 
     __syncthreads();
     pdl_launch_dependents();
     pdl_wait();                 // set-up above overlaps the previous kernel's tail; no global access before this line
-    load_device_params(a);
+    if (!load_device_params(a)) return;
 
     if (threadIdx.x < 32) {
         if (threadIdx.x == 0) {

@@ -43,13 +43,15 @@ __device__ __forceinline__ float requant_one_plus_u(const RequantArgs& a, int64_
     return srpe_one_plus_u(r[k >> 1], k & 1);
 }
 
-__device__ __forceinline__ void load_device_params(RequantArgs& a) {
+__device__ __forceinline__ bool load_device_params(RequantArgs& a) {
     if (a.dP) {
+        if (device_params_failed(a.dP)) return false;      // flagged block: no work (see pq_device.cuh)
         const float xi = a.P.xi;
         a.P = *a.dP;
         a.P.xi = xi;
         a.scale_bf16 = bf16_bits_to_f32(f32_to_bf16_bits(a.P.scale));
     }
+    return true;
 }
 
 template <int DT, int STEP, int OP>
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(kThreads) requant_stream_kernel(const RequantA
     const int64_t n_tiles = (a.n_items + TILE - 1) / TILE;
     pdl_launch_dependents();
     pdl_wait();
-    load_device_params(a);
+    if (!load_device_params(a)) return;
 
     if (const int64_t tile = blockIdx.x; tile < n_tiles) {      // one tile per CTA, hardware-scheduled (see quantize.cu)
         const int64_t first = tile * TILE + threadIdx.x;
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(kThreads) requant_scalar_kernel(const RequantA
     RequantArgs a = a_in;
     pdl_launch_dependents();
     pdl_wait();
-    load_device_params(a);
+    if (!load_device_params(a)) return;
     for (int64_t e = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; e < a.numel;
          e += static_cast<int64_t>(gridDim.x) * kThreads)
         requant_scalar<DT, STEP, OP>(a, e, qmax);

@@ -241,6 +241,87 @@ class Context:
         return scale[0], zero_point[0]
 
 
+    # ---- explicit device + stream per call (include/piquant_cuda.h: the *_on_stream family) ---------------------
+    # device >= 0: the caller vouches that every pointer is device memory of that device (no driver query per call);
+    # DEVICE_AUTO: classify the pointers like the reference-ABI calls do.  Nothing here touches context state, so
+    # threads may share one context freely.
+
+    DEVICE_AUTO = -1
+    FLAG_LOCAL, FLAG_KEEP_IN_L2, FLAG_REVERSE = 1, 2, 4
+
+    def quantize_on_stream(self, ptr_in: int, dtype_in: DataType, ptr_out: int, dtype_out: DataType, numel: int, scale: float,
+                           zero_point: int, round_mode: RoundMode, device: int, stream: int) -> None:
+        C.piquant_cuda_quantize_on_stream(self._ctx, ptr_in, dtype_in.value, ptr_out, dtype_out.value, numel, scale, zero_point,
+                                          round_mode.value, device, stream)
+
+    def dequantize_on_stream(self, ptr_in: int, dtype_in: DataType, ptr_out: int, dtype_out: DataType, numel: int, scale: float,
+                             zero_point: int, reduce_op: ReduceOp, device: int, stream: int) -> None:
+        C.piquant_cuda_dequantize_on_stream(self._ctx, ptr_in, dtype_in.value, ptr_out, dtype_out.value, numel, scale, zero_point,
+                                            reduce_op.value, device, stream)
+
+    def requantize_on_stream(self, ptr_in: int, dtype_in_out: DataType, ptr_out: int, quant_dtype: DataType, numel: int, scale: float,
+                             zero_point: int, round_mode: RoundMode, reduce_op: ReduceOp, device: int, stream: int) -> None:
+        C.piquant_cuda_requantize_on_stream(self._ctx, ptr_in, dtype_in_out.value, ptr_out, quant_dtype.value, numel, scale, zero_point,
+                                            round_mode.value, reduce_op.value, device, stream)
+
+    def compute_quant_params_on_stream(self, ptr: int, dtype: DataType, numel: int, target_quant_dtype: DataType, device: int,
+                                       stream: int) -> Tuple[float, int]:
+        scale, zero_point = ffi.new("float*"), ffi.new("int64_t*")
+        C.piquant_cuda_compute_quant_params_on_stream(self._ctx, ptr, dtype.value, numel, target_quant_dtype.value, scale, zero_point,
+                                                      device, stream)
+        return scale[0], zero_point[0]
+
+    def minmax_on_stream(self, ptr: int, dtype: DataType, numel: int, ptr_out4: int, flags: int, device: int, stream: int) -> None:
+        C.piquant_cuda_minmax_on_stream(self._ctx, ptr, dtype.value, numel, ptr_out4, flags, device, stream)
+
+    def compute_meta_on_stream(self, ptr: int, dtype: DataType, numel: int, target_quant_dtype: DataType, ptr_meta: int, flags: int,
+                               device: int, stream: int) -> None:
+        C.piquant_cuda_compute_meta_on_stream(self._ctx, ptr, dtype.value, numel, target_quant_dtype.value, ptr_meta, flags, device, stream)
+
+    def quantize_meta_on_stream(self, ptr_in: int, dtype_in: DataType, ptr_out: int, dtype_out: DataType, numel: int,
+                                round_mode: RoundMode, ptr_meta: int, flags: int, device: int, stream: int) -> None:
+        C.piquant_cuda_quantize_meta_on_stream(self._ctx, ptr_in, dtype_in.value, ptr_out, dtype_out.value, numel, round_mode.value,
+                                               ptr_meta, flags, device, stream)
+
+    def dequantize_meta_on_stream(self, ptr_in: int, dtype_in: DataType, ptr_out: int, dtype_out: DataType, numel: int,
+                                  reduce_op: ReduceOp, ptr_meta: int, device: int, stream: int) -> None:
+        C.piquant_cuda_dequantize_meta_on_stream(self._ctx, ptr_in, dtype_in.value, ptr_out, dtype_out.value, numel, reduce_op.value,
+                                                 ptr_meta, device, stream)
+
+    def quantize_auto_on_stream(self, ptr_in: int, dtype_in: DataType, ptr_out: int, dtype_out: DataType, numel: int,
+                                round_mode: RoundMode, device: int, stream: int) -> Tuple[float, int]:
+        scale, zero_point = ffi.new("float*"), ffi.new("int64_t*")
+        C.piquant_cuda_quantize_auto_on_stream(self._ctx, ptr_in, dtype_in.value, ptr_out, dtype_out.value, numel, round_mode.value,
+                                               scale, zero_point, device, stream)
+        return scale[0], zero_point[0]
+
+    def dequantize_add_minmax_on_stream(self, ptr_in: int, dtype_in: DataType, ptr_out: int, dtype_out: DataType, numel: int,
+                                        ptr_meta: int, next_quant_dtype: DataType, ptr_meta_next: int, ptr_meta_next_copy: int,
+                                        device: int, stream: int) -> None:
+        """out += dequantize(in) and, in the same launch, the parameters of the sums for the next hop (ring reduce-scatter)."""
+        C.piquant_cuda_dequantize_add_minmax_on_stream(self._ctx, ptr_in, dtype_in.value, ptr_out, dtype_out.value, numel, ptr_meta,
+                                                       next_quant_dtype.value, ptr_meta_next, ptr_meta_next_copy, device, stream)
+
+    def dequantize_forward_on_stream(self, ptr_in: int, dtype_in: DataType, ptr_out: int, dtype_out: DataType, numel: int,
+                                     ptr_meta: int, ptr_forward: int, ptr_forward_meta: int, device: int, stream: int) -> None:
+        """out = dequantize(in) and, in the same launch, the packed bytes (+ parameter block) stored on to the next rank (ring all-gather)."""
+        C.piquant_cuda_dequantize_forward_on_stream(self._ctx, ptr_in, dtype_in.value, ptr_out, dtype_out.value, numel, ptr_meta,
+                                                    ptr_forward, ptr_forward_meta, device, stream)
+
+    def quantize_batch(self, items, dtype_in: DataType, dtype_out: DataType, round_mode: RoundMode, device: int, stream: int) -> None:
+        """items: sequence of (ptr_in, ptr_out, numel, scale, zero_point); ONE kernel launch per 256 tensors."""
+        arr = ffi.new("piquant_cuda_batch_item_t[]", items if isinstance(items, list) else list(items))     # tuples initialise the structs
+        C.piquant_cuda_quantize_batch(self._ctx, arr, len(arr), dtype_in.value, dtype_out.value, round_mode.value, device, stream)
+
+    def comm_set_transport(self, transport: int) -> None:
+        """0 = peer-memory exchange inside the min/max kernel when available (default), 1 = ncclAllReduce, 2 = peer memory or abort."""
+        C.piquant_cuda_comm_set_transport(self._ctx, transport)
+
+    @property
+    def comm_transport(self) -> int:
+        return int(C.piquant_cuda_comm_transport(self._ctx))
+
+
 def cuda_device_count() -> int:
     return int(C.piquant_cuda_device_count())
 

@@ -72,6 +72,36 @@ void  piquant_cuda_dequantize_meta_async(piquant_context_t* ctx, const void* in,
 void  piquant_cuda_quantize_auto(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
                                  piquant_dtype_t dtype_out, size_t numel, piquant_round_mode_t mode,
                                  float* out_scale, int64_t* out_zero_point);
+void  piquant_cuda_comm_set_transport(piquant_context_t* ctx, int transport);
+int   piquant_cuda_comm_transport(piquant_context_t* ctx);
+
+/* The *_on_stream family (include/piquant_cuda.h).  Data pointers are declared uintptr_t HERE: on x86-64 that is the same
+   ABI as `const void*`, and Python ints (tensor.data_ptr()) then pass without an ffi.cast per argument. */
+void  piquant_cuda_quantize_on_stream(piquant_context_t* ctx, uintptr_t in, int dtype_in, uintptr_t out, int dtype_out, size_t numel,
+                                      float scale, int64_t zero_point, int mode, int device, uintptr_t stream);
+void  piquant_cuda_dequantize_on_stream(piquant_context_t* ctx, uintptr_t in, int dtype_in, uintptr_t out, int dtype_out, size_t numel,
+                                        float scale, int64_t zero_point, int op, int device, uintptr_t stream);
+void  piquant_cuda_requantize_on_stream(piquant_context_t* ctx, uintptr_t in, int dtype_in_out, uintptr_t out, int quant_dtype, size_t numel,
+                                        float scale, int64_t zero_point, int mode, int op, int device, uintptr_t stream);
+void  piquant_cuda_compute_quant_params_on_stream(piquant_context_t* ctx, uintptr_t x, int dtype, size_t n, int target_quant_dtype,
+                                                  float* out_scale, int64_t* out_zero_point, int device, uintptr_t stream);
+void  piquant_cuda_minmax_on_stream(piquant_context_t* ctx, uintptr_t x, int dtype, size_t n, uintptr_t out4, unsigned flags, int device, uintptr_t stream);
+void  piquant_cuda_compute_meta_on_stream(piquant_context_t* ctx, uintptr_t x, int dtype, size_t n, int target_quant_dtype, uintptr_t d_meta,
+                                          unsigned flags, int device, uintptr_t stream);
+void  piquant_cuda_quantize_meta_on_stream(piquant_context_t* ctx, uintptr_t in, int dtype_in, uintptr_t out, int dtype_out, size_t numel, int mode,
+                                           uintptr_t d_meta, unsigned flags, int device, uintptr_t stream);
+void  piquant_cuda_dequantize_meta_on_stream(piquant_context_t* ctx, uintptr_t in, int dtype_in, uintptr_t out, int dtype_out, size_t numel, int op,
+                                             uintptr_t d_meta, int device, uintptr_t stream);
+void  piquant_cuda_quantize_auto_on_stream(piquant_context_t* ctx, uintptr_t in, int dtype_in, uintptr_t out, int dtype_out, size_t numel, int mode,
+                                           float* out_scale, int64_t* out_zero_point, int device, uintptr_t stream);
+void  piquant_cuda_dequantize_add_minmax_on_stream(piquant_context_t* ctx, uintptr_t in, int dtype_in, uintptr_t out, int dtype_out, size_t numel,
+                                                   uintptr_t d_meta, int next_quant_dtype, uintptr_t d_meta_next, uintptr_t d_meta_next_copy,
+                                                   int device, uintptr_t stream);
+void  piquant_cuda_dequantize_forward_on_stream(piquant_context_t* ctx, uintptr_t in, int dtype_in, uintptr_t out, int dtype_out, size_t numel,
+                                                uintptr_t d_meta, uintptr_t forward_to, uintptr_t forward_meta_to, int device, uintptr_t stream);
+typedef struct piquant_cuda_batch_item_t { uintptr_t in; uintptr_t out; size_t numel; float scale; int64_t zero_point; } piquant_cuda_batch_item_t;
+void  piquant_cuda_quantize_batch(piquant_context_t* ctx, const piquant_cuda_batch_item_t* items, size_t count, int dtype_in, int dtype_out,
+                                  int mode, int device, uintptr_t stream);
 """
 
 

@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 
 from . import Context, DataType, ReduceOp, RoundMode
-from .torch import _QUANT_TYPES, _bind_stream, torch_to_piquant_dtype
+from .torch import _QUANT_TYPES, _site, torch_to_piquant_dtype
 
 SHARD_ALIGN = 64    # elements: a multiple of every pack width (4 for uint2); 128 B of bf16, 16 B of packed uint2
 
@@ -57,8 +57,9 @@ def local_neg_min_max(shard: torch.Tensor, ctx: Context = Context.get()) -> torc
         fmax = torch.finfo(torch.float32).max
         return torch.full((2,), -fmax, dtype=torch.float32, device=shard.device)
     shard = shard if shard.is_contiguous() else shard.contiguous()
-    _bind_stream(ctx, shard)
-    ctx.minmax_async_ptr(shard.data_ptr(), torch_to_piquant_dtype(shard.dtype), shard.numel(), out4.data_ptr())
+    device, stream = _site(shard)
+    ctx.minmax_on_stream(shard.data_ptr(), torch_to_piquant_dtype(shard.dtype), shard.numel(), out4.data_ptr(), Context.FLAG_LOCAL,
+                         device, stream)
     return out4[2:4]
 
 
@@ -130,20 +131,25 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
     """In-place SUM all-reduce of a contiguous CUDA float32 / bfloat16 tensor with quantized transport.
 
     Ring reduce-scatter + ring all-gather over NVLink; every hop carries ``[64-byte parameter block | packed
-    payload]`` -- 1, 1/2 or 1/4 byte per element instead of 4 (or 2).  Each hop is
-    ``min/max -> parameters (on the device) -> quantize`` on the sender and ONE ``dequantize`` with the ADD
-    store op into the accumulator chunk on the receiver; parameters never visit the host, so the whole
-    collective is enqueued without a single synchronisation.  In the all-gather phase the owner of a reduced
-    chunk dequantizes its own packed bytes too, so every rank ends with bit-identical values.
-    The result is the sum up to quantization error (<= 0.5 * scale per hop and element).
+    payload]`` -- 1, 1/2 or 1/4 byte per element instead of 4 (or 2).  A reduce-scatter hop is TWO passes over the
+    chunk: the sender quantizes it with parameters that are already on the device, the receiver runs ONE fused kernel --
+    dequantize with the ADD store op into its accumulator chunk AND min/max of the sums AND the reference's
+    scale / zero-point arithmetic for the next hop (``piquant_cuda_dequantize_add_minmax_on_stream``): the chunk a rank
+    accumulates at hop s is exactly the chunk it sends at hop s + 1, so no separate min/max pass ever reads it.
+    Parameters never visit the host; the whole collective is enqueued without a single synchronisation.  In the
+    all-gather phase the owner of a reduced chunk dequantizes its own packed bytes too, so every rank ends with
+    bit-identical values.  The result is the sum up to quantization error (<= 0.5 * scale per hop and element).
     ``round_mode="stochastic_per_element"`` rounds every element with its own Philox random number instead (extension,
     ``piquant_cuda.h``): the error per hop is then <= 1 * scale but has zero mean, so it averages out over steps and ranks
     instead of accumulating as a bias -- what gradient compression wants; each rank draws its own key per hop.
 
-    ``transport="nccl"``: each hop is an NCCL send/recv of the packed buffer.  ``transport="p2p"``: the sender's
-    quantize kernel stores its packed output (and the parameter kernel its 64-byte block) DIRECTLY into the
-    receiver's slot through NVLink peer memory (torch symmetric memory) -- compute and transfer are one kernel,
-    there is no send/recv and no staging copy; a stream-ordered barrier per hop publishes the slot."""
+    ``transport="nccl"``: each hop is an NCCL send/recv of the packed buffer.  ``transport="p2p"``: nothing is ever
+    sent -- the sender's quantize kernel stores its packed output DIRECTLY into the receiver's slot through NVLink peer
+    memory (torch symmetric memory), the fused receiver kernel drops the next hop's parameter block into the next
+    receiver's slot, and in the all-gather phase the kernel that dequantizes a received chunk also stores its packed
+    bytes on to the next rank (``piquant_cuda_dequantize_forward_on_stream``): compute and transfer are one kernel per
+    direction, with one stream-ordered barrier per hop publishing the slot.  ``transport="auto"``: p2p when symmetric
+    memory is available, else nccl."""
     assert tensor.is_cuda and tensor.is_contiguous() and tensor.dtype in (torch.float32, torch.bfloat16)
     assert dtype in _QUANT_TYPES
     rmode = {"nearest": RoundMode.NEAREST, "stochastic_per_element": RoundMode.STOCHASTIC_PER_ELEMENT}[round_mode]
@@ -155,82 +161,103 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
     bounds = [shard_bounds(flat.numel(), world, i) for i in range(world)]
     qbytes = [qdt.storage_bytes(e - b) for b, e in bounds]
     meta = Context.META_BYTES
-    bufs = [torch.empty(meta + max(qbytes), dtype=torch.uint8, device=tensor.device) for _ in range(3)]
-    nxt = dist.get_global_rank(group, (rank + 1) % world) if group is not None else (rank + 1) % world
-    prv = dist.get_global_rank(group, (rank - 1) % world) if group is not None else (rank - 1) % world
-    _bind_stream(ctx, tensor)
+    slot_bytes = (meta + max(qbytes) + 255) // 256 * 256
+    device, stream = _site(tensor)
+    LOCAL, REVERSE = Context.FLAG_LOCAL, Context.FLAG_REVERSE
+    hdl = None
+    if transport in ("p2p", "auto"):
+        try:
+            local_slots, hdl = _p2p_slots(slot_bytes, tensor.device, group)
+        except Exception:      # noqa: BLE001 -- no symmetric memory on this box / build
+            if transport == "p2p":
+                raise
+    elif transport != "nccl":
+        raise ValueError(f"unknown transport {transport!r}")
 
     def chunk(i):
         b, e = bounds[i]
         return flat[b:e]
 
-    def pack(i, buf):          # chunk i -> [meta | packed] in buf, three kernels, no sync
+    def first_params(i, meta_ptr):      # min/max + parameter arithmetic of chunk i in ONE launch; never the communicator's whole-tensor path
         c = chunk(i)
         if c.numel():
-            ctx.compute_meta_async_ptr(c.data_ptr(), fdt, c.numel(), qdt, buf.data_ptr())
-            ctx.quantize_meta_async_ptr(c.data_ptr(), fdt, buf.data_ptr() + meta, qdt, c.numel(), rmode, buf.data_ptr())
+            ctx.compute_meta_on_stream(c.data_ptr(), fdt, c.numel(), qdt, meta_ptr, LOCAL, device, stream)
 
-    def unpack(i, buf, op):    # [meta | packed] in buf -> (op) chunk i, one kernel
+    def quantize_to(i, payload_ptr, meta_ptr, flags=0):
         c = chunk(i)
         if c.numel():
-            ctx.dequantize_meta_async_ptr(buf.data_ptr() + meta, qdt, c.data_ptr(), fdt, c.numel(), op, buf.data_ptr())
+            ctx.quantize_meta_on_stream(c.data_ptr(), fdt, payload_ptr, qdt, c.numel(), rmode, meta_ptr, flags, device, stream)
+
+    def accumulate(i, base_ptr, next_meta_ptr, next_meta_copy_ptr):      # chunk i += [meta | packed] at base_ptr; parameters of the sums out
+        c = chunk(i)
+        if c.numel():
+            ctx.dequantize_add_minmax_on_stream(base_ptr + meta, qdt, c.data_ptr(), fdt, c.numel(), base_ptr, qdt, next_meta_ptr,
+                                                next_meta_copy_ptr, device, stream)
+
+    def scatter(i, base_ptr):           # chunk i = dequantize([meta | packed] at base_ptr)
+        c = chunk(i)
+        if c.numel():
+            ctx.dequantize_meta_on_stream(base_ptr + meta, qdt, c.data_ptr(), fdt, c.numel(), ReduceOp.SET, base_ptr, device, stream)
+
+    def scatter_forward(i, base_ptr, fwd_base_ptr):      # ... and store the same [meta | packed] on to fwd_base_ptr (peer memory)
+        c = chunk(i)
+        if c.numel():
+            ctx.dequantize_forward_on_stream(base_ptr + meta, qdt, c.data_ptr(), fdt, c.numel(), base_ptr, fwd_base_ptr + meta, fwd_base_ptr,
+                                             device, stream)
+
+    reduce_scatter, all_gather = ring_schedule(world, rank)
+    own = (rank + 1) % world
+    keep = torch.empty(slot_bytes, dtype=torch.uint8, device=tensor.device)      # [meta | packed] of the chunk this rank owns
+    if hdl is not None:
+        my_base, nxt_base = local_slots.data_ptr(), int(hdl.buffer_ptrs[(rank + 1) % world])
+        peer_hdr0 = hdl.get_buffer((rank + 1) % world, (meta,), torch.uint8)       # header of the neighbour's slot 0
+        cur = torch.empty(meta, dtype=torch.uint8, device=tensor.device)           # parameters of the chunk to send next
+        hdl.barrier(channel=0)               # nobody is still reading the slots of a previous call
+        first_params(reduce_scatter[0][0], cur.data_ptr())
+        peer_hdr0.copy_(cur, non_blocking=True)
+        step = 0
+        for send_i, recv_i in reduce_scatter:
+            off, nxt_off = (step % 2) * slot_bytes, ((step + 1) % 2) * slot_bytes
+            # quantize straight into the neighbour's slot over NVLink (its header is there already); from hop 1 on the chunk
+            # was just written by `accumulate`, so it is read from its end -- the part L2 still holds
+            quantize_to(send_i, nxt_base + off + meta, cur.data_ptr(), REVERSE if step else 0)
+            hdl.barrier(channel=0)                           # my slot `off` now holds chunk recv_i from my predecessor
+            # ONE kernel: chunk += dequantize(slot); parameters of the sums -> `cur` and -> the header of the neighbour's NEXT slot
+            accumulate(recv_i, my_base + off, cur.data_ptr(), nxt_base + nxt_off)
+            step += 1
+        # the owner keeps exactly what everybody else will receive: quantize the reduced chunk once, dequantize that
+        keep[:meta].copy_(cur, non_blocking=True)
+        quantize_to(own, keep.data_ptr() + meta, cur.data_ptr(), REVERSE)
+        src = keep.data_ptr()
+        for hop, (send_i, recv_i) in enumerate(all_gather):
+            off = (step % 2) * slot_bytes
+            scatter_forward(send_i, src, nxt_base + off)     # dequantize what I hold of chunk send_i AND store its packed bytes into the neighbour's slot
+            hdl.barrier(channel=0)
+            src = my_base + off                              # chunk recv_i has arrived; it is dequantized (and forwarded) by the next iteration
+            step += 1
+        scatter(all_gather[-1][1], src)
+        return tensor
+
+    nxt = dist.get_global_rank(group, (rank + 1) % world) if group is not None else (rank + 1) % world
+    prv = dist.get_global_rank(group, (rank - 1) % world) if group is not None else (rank - 1) % world
+    bufs = [torch.empty(slot_bytes, dtype=torch.uint8, device=tensor.device) for _ in range(3)]
 
     def exchange(send_buf, send_i, recv_buf, recv_i):
         ops = [dist.P2POp(dist.isend, send_buf[: meta + qbytes[send_i]], nxt, group=group),
                dist.P2POp(dist.irecv, recv_buf[: meta + qbytes[recv_i]], prv, group=group)]
         for req in dist.batch_isend_irecv(ops):
-            req.wait()
+            req.wait()                                       # stream-ordered: the current stream waits, the host does not
 
-    reduce_scatter, all_gather = ring_schedule(world, rank)
-    if transport == "p2p":
-        slot_bytes = (meta + max(qbytes) + 255) // 256 * 256
-        local_slots, hdl = _p2p_slots(slot_bytes, tensor.device, group)
-        nxt_rank, my_base, nxt_base = (rank + 1) % world, local_slots.data_ptr(), int(hdl.buffer_ptrs[(rank + 1) % world])
-        step = 0
-
-        def pack_to(i, base_ptr):            # chunk i -> [meta | packed] at base_ptr (local or peer memory)
-            c = chunk(i)
-            if c.numel():
-                ctx.compute_meta_async_ptr(c.data_ptr(), fdt, c.numel(), qdt, base_ptr)
-                ctx.quantize_meta_async_ptr(c.data_ptr(), fdt, base_ptr + meta, qdt, c.numel(), rmode, base_ptr)
-
-        def unpack_from(i, base_ptr, op):
-            c = chunk(i)
-            if c.numel():
-                ctx.dequantize_meta_async_ptr(base_ptr + meta, qdt, c.data_ptr(), fdt, c.numel(), op, base_ptr)
-
-        hdl.barrier(channel=0)               # nobody is still reading the slots of a previous call
-        for send_i, recv_i in reduce_scatter:
-            off = (step % 2) * slot_bytes
-            pack_to(send_i, nxt_base + off)                  # quantize straight into the neighbour's slot over NVLink
-            hdl.barrier(channel=0)                           # my slot `off` now holds chunk recv_i from my predecessor
-            unpack_from(recv_i, my_base + off, ReduceOp.ADD)
-            step += 1
-        own = (rank + 1) % world
-        keep = bufs[0]                                       # the owner's packed copy: what everybody else will receive
-        pack_to(own, keep.data_ptr())
-        unpack_from(own, keep.data_ptr(), ReduceOp.SET)
-        src_ptr, src_tensor = keep.data_ptr(), keep
-        peer_slots = hdl.get_buffer(nxt_rank, (2 * slot_bytes,), torch.uint8)
-        for send_i, recv_i in all_gather:
-            off = (step % 2) * slot_bytes
-            nbytes = meta + qbytes[send_i]
-            peer_slots[off: off + nbytes].copy_(src_tensor[:nbytes], non_blocking=True)      # NVLink peer store of the packed bytes
-            hdl.barrier(channel=0)
-            unpack_from(recv_i, my_base + off, ReduceOp.SET)
-            src_tensor = local_slots[off: off + slot_bytes]  # forward what was just received
-            step += 1
-        return tensor
     send_buf, recv_buf, spare = bufs
-    for send_i, recv_i in reduce_scatter:
-        pack(send_i, send_buf)
+    first_params(reduce_scatter[0][0], send_buf.data_ptr())
+    for hop, (send_i, recv_i) in enumerate(reduce_scatter):
+        quantize_to(send_i, send_buf.data_ptr() + meta, send_buf.data_ptr(), REVERSE if hop else 0)
         exchange(send_buf, send_i, recv_buf, recv_i)
-        unpack(recv_i, recv_buf, ReduceOp.ADD)
-    own = (rank + 1) % world
-    pack(own, send_buf)
-    unpack(own, send_buf, ReduceOp.SET)          # the owner keeps exactly what everybody else will receive
+        accumulate(recv_i, recv_buf.data_ptr(), send_buf.data_ptr(), 0)     # next hop's parameters land in the send buffer's header
+    quantize_to(own, send_buf.data_ptr() + meta, send_buf.data_ptr(), REVERSE)
+    scatter(own, send_buf.data_ptr())            # the owner keeps exactly what everybody else will receive
     for send_i, recv_i in all_gather:
         exchange(send_buf, send_i, recv_buf, recv_i)
-        unpack(recv_i, recv_buf, ReduceOp.SET)
+        scatter(recv_i, recv_buf.data_ptr())
         send_buf, recv_buf, spare = recv_buf, spare, send_buf     # forward what was just received
     return tensor

@@ -7,7 +7,9 @@ Same three functions, keyword names, accepted dtypes and return conventions as t
   reference torch.py:87,117);
 * for CUDA tensors the work is enqueued on PyTorch's *current* stream of that device, so calls
   compose with surrounding torch ops without extra synchronisation; ``compute_quant_params``
-  returns Python scalars and therefore synchronises;
+  returns Python scalars and therefore synchronises.  Device index and stream travel WITH each call
+  (``piquant_cuda_*_on_stream``): nothing is stored in the context, so threads can share one context, and
+  the native side skips its per-call pointer classification;
 * ``dequantize`` takes an optional ``out=`` so that ``reduce_op='add'`` has a defined accumulator
   (the reference accumulates into an uninitialised ``torch.empty``, reference torch.py:117);
 * ``requantize`` exposes the fused quantize->dequantize pass (C++-only in the reference).
@@ -54,10 +56,20 @@ def piquant_to_torch_dtype(dtype: DataType) -> torch.dtype:
     raise ValueError(f"Unsupported quantized dtype: {dtype}")
 
 
-def _bind_stream(ctx: Context, tensor: torch.Tensor) -> None:
-    """Order the native call on torch's current stream of the tensor's device."""
+try:
+    _raw_stream = torch._C._cuda_getCurrentRawStream        # int handle without building a Stream object
+except AttributeError:                                     # pragma: no cover
+    def _raw_stream(index: int) -> int:
+        return torch.cuda.current_stream(index).cuda_stream
+
+
+def _site(tensor: torch.Tensor) -> Tuple[int, int]:
+    """(device, stream) of a native call on ``tensor``: a CUDA tensor runs on its own device and on torch's current stream
+    of that device; a CPU tensor is classified by the library (``DEVICE_AUTO``: staged through the GPU, synchronous)."""
     if tensor.is_cuda:
-        ctx.set_stream(torch.cuda.current_stream(tensor.device).cuda_stream)
+        index = tensor.device.index
+        return index, _raw_stream(index)
+    return Context.DEVICE_AUTO, 0
 
 
 def _contiguous(tensor: torch.Tensor) -> torch.Tensor:
@@ -68,12 +80,11 @@ def compute_quant_params(tensor: torch.Tensor, *, dtype: torch.dtype, ctx: Conte
     """(scale, zero_point) that map [min(tensor), max(tensor)] onto the range of ``dtype``."""
     assert dtype in _QUANT_TYPES, f"Unsupported quantized dtype: {dtype}. Must be one of {list(_QUANT_TYPES)}"
     tensor = _contiguous(tensor)
-    _bind_stream(ctx, tensor)
-    if tensor.dtype == torch.bfloat16:
-        return ctx.compute_quant_params_ptr_bfloat16(tensor.data_ptr(), torch_to_piquant_dtype(dtype), tensor.numel())
-    if tensor.dtype != torch.float32:
+    if tensor.dtype not in _DEQUANT_TYPES:
         raise ValueError(f"Unsupported input dtype: {tensor.dtype}. Must be one of {list(_DEQUANT_TYPES)}")
-    return ctx.compute_quant_params_ptr_float32(tensor.data_ptr(), torch_to_piquant_dtype(dtype), tensor.numel())
+    device, stream = _site(tensor)
+    return ctx.compute_quant_params_on_stream(tensor.data_ptr(), torch_to_piquant_dtype(tensor.dtype), tensor.numel(),
+                                              torch_to_piquant_dtype(dtype), device, stream)
 
 
 def quantize(tensor: torch.Tensor, *, scale: float, zero_point: int, dtype: torch.dtype, round_mode: str = "nearest",
@@ -87,9 +98,9 @@ def quantize(tensor: torch.Tensor, *, scale: float, zero_point: int, dtype: torc
         out = torch.empty(tensor.shape, dtype=dtype, device=tensor.device)
     else:
         assert out.dtype == dtype and out.shape == tensor.shape and out.device == tensor.device and out.is_contiguous()
-    _bind_stream(ctx, tensor)
-    ctx.quantize_ptr(tensor.data_ptr(), dtype_in, out.data_ptr(), dtype_out, numel=tensor.numel(), scale=scale,
-                     zero_point=zero_point, round_mode=_ROUND_MODES[round_mode])
+    device, stream = _site(tensor)
+    ctx.quantize_on_stream(tensor.data_ptr(), dtype_in, out.data_ptr(), dtype_out, tensor.numel(), scale, zero_point,
+                           _ROUND_MODES[round_mode], device, stream)
     return out
 
 
@@ -105,9 +116,9 @@ def dequantize(tensor: torch.Tensor, *, scale: float, zero_point: int, dtype: to
         out = alloc(tensor.shape, dtype=dtype, device=tensor.device)
     else:
         assert out.dtype == dtype and out.shape == tensor.shape and out.device == tensor.device and out.is_contiguous()
-    _bind_stream(ctx, tensor)
-    ctx.dequantize_ptr(tensor.data_ptr(), torch_to_piquant_dtype(tensor.dtype), out.data_ptr(), torch_to_piquant_dtype(out.dtype),
-                       numel=tensor.numel(), scale=scale, zero_point=zero_point, reduce_op=_REDUCE_OPS[reduce_op])
+    device, stream = _site(tensor)
+    ctx.dequantize_on_stream(tensor.data_ptr(), torch_to_piquant_dtype(tensor.dtype), out.data_ptr(), torch_to_piquant_dtype(out.dtype),
+                             tensor.numel(), scale, zero_point, _REDUCE_OPS[reduce_op], device, stream)
     return out
 
 
@@ -123,9 +134,9 @@ def requantize(tensor: torch.Tensor, *, scale: float, zero_point: int, dtype: to
         out = alloc(tensor.shape, dtype=tensor.dtype, device=tensor.device)
     else:
         assert out.dtype == tensor.dtype and out.shape == tensor.shape and out.device == tensor.device and out.is_contiguous()
-    _bind_stream(ctx, tensor)
-    ctx.requantize_ptr(tensor.data_ptr(), torch_to_piquant_dtype(tensor.dtype), out.data_ptr(), torch_to_piquant_dtype(dtype),
-                       tensor.numel(), scale, zero_point, _ROUND_MODES[round_mode], _REDUCE_OPS[reduce_op])
+    device, stream = _site(tensor)
+    ctx.requantize_on_stream(tensor.data_ptr(), torch_to_piquant_dtype(tensor.dtype), out.data_ptr(), torch_to_piquant_dtype(dtype),
+                             tensor.numel(), scale, zero_point, _ROUND_MODES[round_mode], _REDUCE_OPS[reduce_op], device, stream)
     return out
 
 
@@ -141,10 +152,37 @@ def quantize_auto(tensor: torch.Tensor, *, dtype: torch.dtype, round_mode: str =
         out = torch.empty(tensor.shape, dtype=dtype, device=tensor.device)
     else:
         assert out.dtype == dtype and out.shape == tensor.shape and out.device == tensor.device and out.is_contiguous()
-    _bind_stream(ctx, tensor)
-    scale, zero_point = ctx.quantize_auto_ptr(tensor.data_ptr(), torch_to_piquant_dtype(tensor.dtype), out.data_ptr(),
-                                              torch_to_piquant_dtype(dtype), tensor.numel(), _ROUND_MODES[round_mode])
+    device, stream = _site(tensor)
+    scale, zero_point = ctx.quantize_auto_on_stream(tensor.data_ptr(), torch_to_piquant_dtype(tensor.dtype), out.data_ptr(),
+                                                    torch_to_piquant_dtype(dtype), tensor.numel(), _ROUND_MODES[round_mode], device, stream)
     return out, scale, zero_point
+
+
+def quantize_batch(tensors, *, scales, zero_points, dtype: torch.dtype, round_mode: str = "nearest", ctx: Context = Context.get(),
+                   outs=None):
+    """Quantize many (small) CUDA tensors of one float dtype on one device in ONE kernel launch per 256 tensors.
+
+    The reference's own benchmark calls ``quantize`` a thousand times on 1e6 elements (reference python/benchmark/benchmark.py:16-23);
+    on a GPU the launch costs more than that much data.  Every tensor gets exactly the bytes ``quantize(tensor, scale=..,
+    zero_point=..)`` would produce.  ``round_mode``: ``nearest`` or ``stochastic`` (one threshold for the whole batch).
+    Returns the list of quantized tensors."""
+    assert dtype in _QUANT_TYPES, f"Unsupported quantized dtype: {dtype}. Must be one of {list(_QUANT_TYPES)}"
+    tensors = [_contiguous(t) for t in tensors]
+    if not tensors:
+        return []
+    first = tensors[0]
+    assert first.is_cuda, "quantize_batch serves CUDA tensors (host tensors: call quantize per tensor)"
+    assert all(t.dtype == first.dtype and t.device == first.device for t in tensors), "one float dtype and one device per batch"
+    assert len(scales) == len(tensors) and len(zero_points) == len(tensors)
+    if outs is None:
+        outs = [torch.empty(t.shape, dtype=dtype, device=t.device) for t in tensors]
+    else:
+        assert len(outs) == len(tensors) and all(o.dtype == dtype and o.shape == t.shape and o.device == t.device and o.is_contiguous()
+                                                 for o, t in zip(outs, tensors))
+    items = [(t.data_ptr(), o.data_ptr(), t.numel(), float(s), int(z)) for t, o, s, z in zip(tensors, outs, scales, zero_points)]
+    device, stream = _site(first)
+    ctx.quantize_batch(items, torch_to_piquant_dtype(first.dtype), torch_to_piquant_dtype(dtype), _ROUND_MODES[round_mode], device, stream)
+    return outs
 
 
 def new_meta(device: torch.device) -> torch.Tensor:

@@ -65,22 +65,6 @@ def unpack(q: np.ndarray, dt: int, numel: int) -> np.ndarray:
 
 
 def infer_xi(x_f32: np.ndarray, scale: float, zero_point: int, qmax: int, q_elems: np.ndarray) -> float | None:
-    """The reference draws ONE stochastic threshold xi per call from a random_device-seeded RNG
-    (piquant.cpp:194-201), so its output cannot be reproduced from a seed.  It can still be pinned:
-    every element with dec > xi rounds away from zero and every element with dec <= xi truncates
-    (quantize.inl:8-19), so the output brackets xi.  Returns a xi consistent with q_elems, or None."""
-    inv = np.float32(1.0) / np.float32(scale)
-    with np.errstate(all="ignore"):
-        r = x_f32.astype(np.float32) * inv
-        tr = np.trunc(r)
-        dec = np.abs(r - tr)
-        trunc_q = np.clip(tr.astype(np.int64) + zero_point, 0, qmax)
-        away_q = np.clip((tr + np.where(r < 0, -1.0, 1.0).astype(np.float32)).astype(np.int64) + zero_point, 0, qmax)
-    informative = trunc_q != away_q
-    went_away = informative & (q_elems.astype(np.int64) == away_q)
-    stayed = informative & (q_elems.astype(np.int64) == trunc_q)
-    lo = float(dec[stayed].max()) if stayed.any() else 0.0       # xi >= dec of every truncated element
-    hi = float(dec[went_away].min()) if went_away.any() else 1.0  # xi <  dec of every rounded-away element
-    if not lo < hi:
-        return None
-    return float(np.float32(lo)) if lo > 0.0 else 0.0
+    """A per-call stochastic threshold consistent with the reference's output, or None (oracle.port.infer_stochastic_threshold)."""
+    from oracle.port import infer_stochastic_threshold
+    return infer_stochastic_threshold(x_f32, scale, zero_point, qmax, q_elems)

@@ -47,7 +47,22 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
             want = orc.compute_quant_params(x, odt)
             got_torch = pd.compute_quant_params_sharded(shard, dtype=tdt, ctx=ctx)
             pd.init_native_comm(ctx)
-            got_native = pt.compute_quant_params(shard, dtype=tdt, ctx=ctx)
+            # both transports of the native exchange: {-min, max} swapped inside the min/max kernel through peer-mapped
+            # mailboxes (default where the GPUs can map each other's memory), and ncclAllReduce
+            transports = []
+            got_native = None
+            for tr in ((2, 1) if ctx.comm_transport == 2 else (1,)):
+                ctx.comm_set_transport(tr)
+                assert ctx.comm_transport == tr
+                for _ in range(3):          # several exchanges in a row: the mailbox parity / sequence logic
+                    got = pt.compute_quant_params(shard, dtype=tdt, ctx=ctx)
+                    got_native = got if got_native is None or got_native == got else ("mismatch", got_native, got)
+                transports.append(tr)
+            res[name + "_transports"] = (len(transports) >= 1,)
+            # a host-resident shard goes through the same exchange
+            got_host = pt.compute_quant_params(shard.cpu(), dtype=tdt, ctx=ctx)
+            res[name + "_host_shard"] = (got_host == want,)
+            ctx.comm_set_transport(0)
             pd.destroy_native_comm(ctx)
             got_local = pt.compute_quant_params(shard, dtype=tdt, ctx=ctx)      # local again after destroy
             want_local = orc.compute_quant_params(x[b:e], odt)
@@ -64,19 +79,34 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         ctx.compute_meta_async_ptr(shard.data_ptr(), piquant.DataType.F32, shard.numel(), piquant.DataType.UINT8, meta.data_ptr())
         res["sharded_meta"] = (pt.meta_to_host(meta) == orc.compute_quant_params(x, orc.UINT8),)
+        # ... unless the caller asks for this shard only (what the ring reduction does per chunk)
+        ctx.compute_meta_on_stream(shard.data_ptr(), piquant.DataType.F32, shard.numel(), piquant.DataType.UINT8, meta.data_ptr(),
+                                   piquant.Context.FLAG_LOCAL, rank, torch.cuda.current_stream().cuda_stream)
+        res["local_meta_with_comm"] = (pt.meta_to_host(meta) == orc.compute_quant_params(x[b:e], orc.UINT8),)
+        # one-shot quantize of a shard with whole-tensor parameters: one reduction launch (exchange inside) + one quantize launch
+        q_auto, s_auto, z_auto = pt.quantize_auto(shard, dtype=torch.uint8, ctx=ctx)
+        whole8 = orc.quantize(x, orc.UINT8, *orc.compute_quant_params(x, orc.UINT8))
+        res["sharded_quantize_auto"] = ((s_auto, z_auto) == orc.compute_quant_params(x, orc.UINT8), bool(np.array_equal(q_auto.cpu().numpy(), whole8[b:e])))
         pd.destroy_native_comm(ctx)
         # quantized ring all-reduce: every rank ends with bit-identical values, close to the exact sum
         for tdt, qdt, transport, rmode in ((torch.float32, torch.quint8, "nccl", "nearest"), (torch.bfloat16, torch.quint8, "nccl", "nearest"),
                                            (torch.float32, torch.quint4x2, "nccl", "nearest"), (torch.float32, torch.quint8, "p2p", "nearest"),
                                            (torch.bfloat16, torch.quint4x2, "p2p", "nearest"), (torch.float32, torch.quint8, "p2p", "nearest"),
                                            (torch.float32, torch.quint8, "p2p", "stochastic_per_element"),
+                                           (torch.float32, torch.quint4x2, "auto", "nearest"), (torch.bfloat16, torch.quint8, "auto", "nearest"),
                                            (torch.float32, torch.quint8, "nccl", "stochastic_per_element")):
             tol_steps = 1.0 if rmode == "nearest" else 2.0          # per-element SR: up to one step per hop instead of half a step
             g = torch.Generator(device="cuda").manual_seed(100 + rank)
             t = (torch.rand(1_000_003, device="cuda", generator=g) * 2 - 1).to(tdt)
             exact = t.double().clone()
             dist.all_reduce(exact)
+            inputs = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(inputs, t)
             pd.quantized_all_reduce_(t, dtype=qdt, ctx=ctx, transport=transport, round_mode=rmode)
+            if rmode == "nearest":
+                # the whole collective replayed on the CPU with the oracle, hop by hop: the GPU result must be bit-identical
+                want = _ring_on_the_oracle(orc, pd, [i.cpu() for i in inputs], qdt)
+                res[f"ring_bit_exact_{transport}_{tdt}_{qdt}_{len(res)}"] = (bool(np.array_equal(_bits(t.cpu()), want)),)
             gathered = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(gathered, t)
             identical = all(torch.equal(gathered[0].view(torch.uint8), gi.view(torch.uint8)) for gi in gathered)
@@ -91,6 +121,37 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
+
+
+def _bits(t):
+    import torch
+    return t.contiguous().view(torch.uint8).numpy().copy()
+
+
+def _ring_on_the_oracle(orc, pd, inputs, qdt):
+    """What quantized_all_reduce_ computes, restated with the CPU oracle: chunk c starts on rank c, is quantized with the
+    parameters of the running sum at every hop and accumulated with dequantize-ADD on the next rank; the rank that holds
+    the complete sum quantizes it once more and EVERY rank takes the dequantized values of those packed bytes."""
+    import torch
+    world = len(inputs)
+    odt = {torch.quint8: orc.UINT8, torch.quint4x2: orc.UINT4, torch.quint2x4: orc.UINT2}[qdt]
+    is_bf16 = inputs[0].dtype == torch.bfloat16
+    fdt = orc.BF16 if is_bf16 else orc.F32
+    host = [(i.view(torch.int16).numpy().view(np.uint16).copy() if is_bf16 else i.numpy().copy()) for i in inputs]
+    n = host[0].size
+    out = np.empty_like(host[0])
+    for c in range(world):
+        b, e = pd.shard_bounds(n, world, c)
+        if e == b:
+            continue
+        acc = host[c][b:e].copy()
+        for k in range(1, world):
+            s, z = orc.compute_quant_params(acc, odt)
+            q = orc.quantize(acc, odt, s, z)
+            acc = orc.dequantize(q, odt, e - b, fdt, s, z, orc.ADD, out=host[(c + k) % world][b:e].copy())
+        s, z = orc.compute_quant_params(acc, odt)
+        out[b:e] = orc.dequantize(orc.quantize(acc, odt, s, z), odt, e - b, fdt, s, z, orc.SET)
+    return out.view(np.uint8)
 
 
 def test_sharded_params_and_quantize_two_gpus():

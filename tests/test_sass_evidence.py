@@ -64,7 +64,7 @@ def test_no_kernel_uses_local_memory_outside_the_cold_fallbacks():
     out = subprocess.run([exe, "-res-usage", str(LIB)], capture_output=True, text=True, check=True).stdout
     frames = dict(re.findall(r"Function (\S+):\s*\n\s*REG:\d+ STACK:(\d+)", out))
     assert len(frames) > 100, "cuobjdump -res-usage output not understood"
-    allowed = re.compile(r"quant_stream_kernelILi1ELi[248]ELi2E|quant_bf16_u2_threshold_kernelILi2E")   # <bf16, *, stochastic>
+    allowed = re.compile(r"quant_(stream|batch)_kernelILi1ELi[248]ELi2E|quant_bf16_u2_threshold_kernelILi2E")   # <bf16, *, stochastic> (the batch kernel runs the same tile code)
     for fn, stack in frames.items():
         if allowed.search(fn):
             assert int(stack) <= 64, (fn, stack)
