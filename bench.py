@@ -261,8 +261,7 @@ def run_ours(args) -> None:
         with torch.cuda.stream(up):
             x.copy_(xh, non_blocking=True)
         with torch.cuda.stream(down):
-            for _ in range(4):
-                qh.copy_(q, non_blocking=True)
+            qh.copy_(q, non_blocking=True)          # 1 byte down per 4 bytes up, the pipeline's own ratio
     torch.cuda.synchronize()
     bidir_s = max_over_ranks(time.perf_counter() - t0)
     bidir_h2d_gbps = 2 * 4 * n / bidir_s / 1e9
@@ -460,7 +459,19 @@ def run_extra(torch, ctx, D, RoundMode, ReduceOp, x, q, scale, zp, dev) -> dict:
     torch.cuda.synchronize()
     t_total = (time.perf_counter() - t0) / 2000
     out["call_overhead_us_numel_4096"] = {"host_issue": round(t_issue * 1e6, 2), "throughput_back_to_back": round(t_total * 1e6, 2),
-                                         "note": "cffi call + pointer classification + cudaLaunchKernelEx (PDL)"}
+                                         "note": "reference ABI (piquant_quantize): cffi call + pointer classification (2 driver queries) + cudaLaunchKernelEx (PDL)"}
+    # the same call with device and stream passed along (piquant_cuda_quantize_on_stream: what piquant.torch uses): no classification
+    dev_i, st_i = dev.index, torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(2000):
+        ctx.quantize_on_stream(x.data_ptr(), D.F32, q.data_ptr(), D.UINT8, tiny, scale, zp, RoundMode.NEAREST, dev_i, st_i)
+    t_issue = (time.perf_counter() - t0) / 2000
+    torch.cuda.synchronize()
+    t_total = (time.perf_counter() - t0) / 2000
+    out["call_overhead_us_numel_4096_on_stream"] = {"host_issue": round(t_issue * 1e6, 2), "throughput_back_to_back": round(t_total * 1e6, 2),
+                                                   "note": "piquant_cuda_quantize_on_stream from Python: cffi call + slot lookup + cudaLaunchKernelEx (PDL)"}
+    out["small_tensor_regime"] = small_tensor_leg(torch, ctx, dev)
     # C4: stochastic rounding
     rec("C4_f32_u8_stochastic", n, 5, time_launches(torch, lambda: ctx.quantize_ptr(x.data_ptr(), D.F32, q.data_ptr(), D.UINT8, n, scale, zp, RoundMode.STOCHASTIC), 10))
     # C4 as BASELINE.json spells it ("f32->int8"): the reference has no signed dtype at this commit (mapped to
@@ -658,6 +669,50 @@ def strong_scaling_legs(torch, dist, piquant, D, RoundMode, ReduceOp, x, q, worl
     return out
 
 
+def small_tensor_leg(torch, ctx, dev) -> dict:
+    """The reference's own Python benchmark (reference python/benchmark/benchmark.py:16-23): NUMEL = 1e6 f32, 1000 runs of
+    piquant.torch.quantize per quantized dtype (each run allocates its output, like the reference's), total seconds -- here on CUDA
+    tensors, next to the SAME thousand tensors handed over as one batch (piquant.torch.quantize_batch: one launch per 256)."""
+    import piquant.torch as pt
+
+    runs, numel = 1000, 1_000_000
+    res = {"numel": numel, "runs": runs, "recipe": "reference python/benchmark/benchmark.py: torch.rand(NUMEL), compute_quant_params once, quantize x 1000"}
+    for tdt, name, bpe in ((torch.quint8, "quint8", 5.0), (torch.quint4x2, "quint4x2", 4.5), (torch.quint2x4, "quint2x4", 4.25)):
+        try:
+            t1 = torch.rand(numel, dtype=torch.float32, device=dev)
+            s_, z_ = pt.compute_quant_params(t1, dtype=tdt, ctx=ctx)
+            keep: list = []
+
+            def per_call():
+                keep.clear()
+                for _ in range(runs):
+                    keep.append(pt.quantize(t1, scale=s_, zero_point=z_, dtype=tdt, ctx=ctx))
+
+            def batched():
+                keep.clear()
+                keep.extend(pt.quantize_batch([t1] * runs, scales=[s_] * runs, zero_points=[z_] * runs, dtype=tdt, ctx=ctx))
+
+            row = {}
+            for label, fn in (("per_call", per_call), ("one_batch", batched)):
+                fn()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                t = time.perf_counter() - t0
+                row[label] = {"total_s": round(t, 5), "us_per_tensor": round(t / runs * 1e6, 2), "Gelem/s": round(runs * numel / t / 1e9, 1),
+                              "GB/s": round(bpe * runs * numel / t / 1e9, 1)}
+            a, b = keep[0], pt.quantize(t1, scale=s_, zero_point=z_, dtype=tdt, ctx=ctx)
+            row["batch_equals_per_call"] = bool(torch.equal(torch.empty(0, dtype=torch.uint8, device=dev).set_(a.untyped_storage()),
+                                                            torch.empty(0, dtype=torch.uint8, device=dev).set_(b.untyped_storage())))
+            res[name] = row
+            keep.clear()
+        except Exception as e:      # noqa: BLE001
+            res[name] = {"error": repr(e)[:200]}
+    res["note"] = "the same 4 MB tensor every run, as in the reference's script: L2-resident on the GPU (and cache-resident on the CPU)"
+    return res
+
+
 def wall_time_local(torch, fn, reps, warm=3) -> float:
     for _ in range(warm):
         fn()
@@ -731,7 +786,9 @@ def ring_allreduce_leg(torch, dist, ctx, world, rank, dev) -> dict:
     bus = 2 * (world - 1) / world * n * 4 / 1e9
     res["nccl_busbw_GBps"] = round(bus / (ms_nccl * 1e-3), 1)
     for key, kw in (("quantized_u8_nccl_sendrecv", dict(transport="nccl")), ("quantized_u8_p2p_fused", dict(transport="p2p")),
-                    ("quantized_u8_p2p_fused_stochastic_per_element", dict(transport="p2p", round_mode="stochastic_per_element"))):
+                    ("quantized_u8_p2p_fused_2_lanes", dict(transport="p2p", lanes=2)),
+                    ("quantized_u8_p2p_fused_4_lanes", dict(transport="p2p", lanes=4)),
+                    ("quantized_u8_p2p_fused_2_lanes_stochastic_per_element", dict(transport="p2p", lanes=2, round_mode="stochastic_per_element"))):
         try:
             ms = timed(lambda: pd.quantized_all_reduce_(work, dtype=torch.quint8, ctx=ctx, **kw))
             mx, mean = error_stats(exact)
@@ -810,6 +867,21 @@ def cpu_reference_leg(x_host, q_gpu_host, scale, zp, ctx, D, RoundMode, ReduceOp
             others[name] = {"numel": m, "ms": round(tt * 1e3, 3), "Gelem/s": round(m / tt / 1e9, 3), "passes": k}
     except Exception as e:      # noqa: BLE001
         others["error"] = repr(e)[:200]
+    try:        # the reference's own small-tensor recipe on these cores: 1e6 elements x 1000 runs per dtype (benchmark.py:16-23)
+        small = {}
+        x1 = np.ascontiguousarray(np.abs(x_host[:1_000_000]))
+        for name, dtn in (("quint8", "UINT8"), ("quint4x2", "UINT4"), ("quint2x4", "UINT2")):
+            s1, z1 = c.compute_quant_params(x1, ref_dt(dtn))
+            o1 = np.empty(orc_packed(ref_dt(dtn), x1.size), dtype=np.uint8)
+            c.quantize(x1, ref_dt(dtn), s1, z1, 0, out=o1)
+            t1 = time.perf_counter()
+            for _ in range(1000):
+                c.quantize(x1, ref_dt(dtn), s1, z1, 0, out=o1)
+            tt = time.perf_counter() - t1
+            small[name] = {"total_s": round(tt, 5), "us_per_tensor": round(tt * 1e3, 2), "Gelem/s": round(1e9 / tt / 1e9, 2)}
+        others["small_tensor_regime_1e6_x_1000"] = small
+    except Exception as e:      # noqa: BLE001
+        others["small_tensor_regime_1e6_x_1000"] = {"error": repr(e)[:200]}
     per_config = {"headline_f32_u8_nearest_1e9": {"numel": n, "mismatches": mism}}
     try:
         from oracle import port as orc
@@ -865,6 +937,11 @@ def cpu_reference_leg(x_host, q_gpu_host, scale, zp, ctx, D, RoundMode, ReduceOp
 def ref_dt(name: str) -> int:
     from oracle import port
     return getattr(port, name)
+
+
+def orc_packed(dt: int, numel: int) -> int:
+    from oracle import port
+    return port.packed_bytes(dt, numel)
 
 
 # ------------------------------------------------------------------------------------------------

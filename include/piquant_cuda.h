@@ -216,6 +216,12 @@ PIQUANT_EXPORT void piquant_cuda_dequantize_forward_on_stream(piquant_context_t*
                                                               piquant_dtype_t dtype_out, size_t numel, const piquant_cuda_meta_t* d_meta,
                                                               void* forward_to, piquant_cuda_meta_t* forward_meta_to, int device, void* stream);
 
+/* Stream-ordered copy of nbytes between any two device-accessible buffers (local, peer-mapped, pinned host) by a COPY
+ * ENGINE (cudaMemcpyAsync): the SM-free way to move a packed payload into a neighbour's slot.  A kernel that stores into
+ * peer memory is link-bound (NVLink sustains ~0.6 TB/s against ~7 TB/s of HBM) and holds every SM it occupies for the
+ * whole transfer; a DMA transfer leaves the SMs to the kernels of other streams. */
+PIQUANT_EXPORT void piquant_cuda_copy_on_stream(piquant_context_t* ctx, void* dst, const void* src, size_t nbytes, int device, void* stream);
+
 /* ---- many small tensors, one launch -----------------------------------------------------------------------------
  * The reference's own Python benchmark quantizes a 1e6-element tensor 1000 times (reference python/benchmark/benchmark.py:16-23);
  * on a GPU a launch costs more than 1e6 elements of data.  One call quantizes `count` independent tensors -- each with

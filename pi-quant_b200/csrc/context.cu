@@ -789,6 +789,7 @@ void reduce_on_device(Context& c, Lease& lease, const void* x, int dt_in, size_t
         first.result = s.d_result;
         c.launches += launch_minmax(x, dt_in, static_cast<int64_t>(n), s.scratch, first, cfg, keep_in_l2);
         PQ_NCCL_CHECK(Nccl::get().AllReduce(s.d_result + 2, s.d_result + 2, 2, kNcclFloat32, kNcclMax, c.comm.nccl, cfg.stream));
+        if (ro.result != s.d_result) c.launches += launch_minmax_publish(s.d_result, cfg);      // a caller's block gets all four values
         if (ro.meta_out) {
             c.launches += launch_params(s.d_result, ro.dt_quant, ro.meta_out, ro.meta_mapped, cfg);
             if (ro.meta_out2) PQ_CUDA_CHECK(cudaMemcpyAsync(ro.meta_out2, ro.meta_out, sizeof(DeviceMeta), cudaMemcpyDeviceToDevice, cfg.stream));
@@ -823,8 +824,8 @@ void compute_params(Context& c, const void* x, int dt_in, size_t n, int dt_quant
         ro.mapped_result = s.h_result_dev;
         reduce_on_device(c, lease, xp, dt_in, n, ro, false, false);
         PQ_CUDA_CHECK(cudaStreamSynchronize(site.stream));        // the slot stays leased: h_result is this call's until it is read
-        mn = s.h_result[0];
-        mx = s.h_result[1];
+        mn = -s.h_result[2];                                      // {-min, max}: the pair every transport of the exchange combines
+        mx = s.h_result[3];
     } else {
         // host tensor: chunks through the ring, one mapped result block per chunk, folded on the host
         DeviceState* d;
@@ -886,8 +887,8 @@ void compute_params(Context& c, const void* x, int dt_in, size_t n, int dt_quant
             ro.mapped_result = s.h_result_dev;
             reduce_on_device(c, lease, d->d_in[0], DT_F32, 2, ro, false, false);
             PQ_CUDA_CHECK(cudaStreamSynchronize(d->s_run));
-            mn = s.h_result[0];
-            mx = s.h_result[1];
+            mn = -s.h_result[2];
+            mx = s.h_result[3];
         }
     }
     params_from_minmax(static_cast<double>(mn), static_cast<double>(mx), dt_quant, out_scale, out_zp);
@@ -1384,6 +1385,17 @@ extern "C" void piquant_cuda_dequantize_forward_on_stream(piquant_context_t* ctx
     c->launches += launch_dequantize_forward(in, dtype_kernel_view(dtype_in), out, dtype_out, static_cast<int64_t>(numel), make_params(1.0f, 0, 0.0f, dtype_in),
                                              lease.cfg(*c), &reinterpret_cast<const DeviceMeta*>(d_meta)->P, forward_to,
                                              reinterpret_cast<const DeviceMeta*>(d_meta), reinterpret_cast<DeviceMeta*>(forward_meta_to));
+}
+
+extern "C" void piquant_cuda_copy_on_stream(piquant_context_t* ctx, void* dst, const void* src, size_t nbytes, int device, void* stream) {
+    as_ctx(ctx);
+    if (nbytes == 0) return;
+    pq_assert(dst != nullptr && src != nullptr, "copy pointers must not be NULL");
+    const Site site = call_site(device, stream);
+    const int cur = require_device();
+    const int dev = device_of(site, {src}, "piquant_cuda_copy");
+    DeviceGuard guard(cur, dev);
+    PQ_CUDA_CHECK(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDefault, site.stream));
 }
 
 extern "C" void piquant_cuda_quantize_auto_on_stream(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,

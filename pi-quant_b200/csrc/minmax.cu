@@ -157,6 +157,20 @@ __global__ void params_kernel(const float* minmax4, int bits, int is_signed, uin
     }
 }
 
+// after an all-reduce of {-min, max} (NCCL transport): bring {min, max} in line with the combined pair
+__global__ void minmax_publish_kernel(float* r4) {
+    pdl_launch_dependents();
+    pdl_wait();
+    r4[0] = -r4[2];
+    r4[1] = r4[3];
+}
+
+int launch_minmax_publish(float* minmax4, const LaunchCfg& cfg) {
+    launch_kernel(minmax_publish_kernel, 1u, 1u, 0, cfg.stream, minmax4);
+    PQ_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
 int launch_params(const float* minmax4, int dt_quant, DeviceMeta* out, DeviceMeta* mapped_out, const LaunchCfg& cfg) {
     launch_kernel(params_kernel, 1u, 1u, 0, cfg.stream, minmax4, dtype_bits(dt_quant), dtype_is_signed_quant(dt_quant) ? 1 : 0,
                   dtype_sign_xor(dt_quant), out, mapped_out);

@@ -220,17 +220,18 @@ int launch_quantize_batch(const BatchItem* items, int count, int dt_in, int dt_o
 // dt_quant may be a signed extension type: the public (scale, zero_point) are then the signed ones
 // (reference src/piquant.cpp:245-258 with type_min = -type_max - 1) and P is the unsigned kernel view.
 int launch_params(const float* minmax4, int dt_quant, DeviceMeta* out, DeviceMeta* mapped_out, const LaunchCfg& cfg);
+// minmax4[0..1] = {-minmax4[2], minmax4[3]}: after {-min, max} was combined across ranks by an all-reduce
+int launch_minmax_publish(float* minmax4, const LaunchCfg& cfg);
 
-// variant 0 ("auto"): which cells go to the TMA ring kernels.  Every entry is a measurement on B200, not a guess.
-// With one-tile-per-CTA hardware scheduling the direct LDG.256/STG kernels run at the traffic ceiling of the chip
-// (f32->u8: 7.19 TB/s = 110 % of the measured copy peak, against 7.23 TB/s for the same read:write mix with no
-// arithmetic at all, profiles/r1_sched_probe_static_vs_dynamic_tiles.txt), at every size and for every cell
-// (profiles/r1_cellbench_1e9_dynamic_tiles.txt), so "auto" currently selects the TMA ring nowhere; it stays
-// selectable (variant 2), tested to the same bit-exact bar, and serves inputs that are only 16-byte aligned.
-inline bool quantize_prefers_tma(int dt_in, int dt_out, int mode, int64_t algorithmic_bytes) {
-    (void)dt_in; (void)dt_out; (void)mode; (void)algorithmic_bytes;
-    return false;
-}
-inline bool dequantize_prefers_tma(int64_t algorithmic_bytes) { (void)algorithmic_bytes; return false; }
+// Kernel families.  The direct LDG.256 / STG kernels are the product default (variant 0 = variant 1): with one tile per
+// CTA dealt by the hardware scheduler they run at the traffic ceiling of the chip at every size and in every cell (f32->u8:
+// 7.19 TB/s against 7.23 TB/s for the same read:write mix with no arithmetic at all, profiles/r1_sched_probe_static_vs_dynamic_tiles.txt).
+// The TMA (cp.async.bulk + mbarrier ring) family is an opt-in variant (2): it ties the direct kernels on f32 inputs at
+// >= 0.25 GB per launch and trails them everywhere else -- bf16 inputs 82-90 % vs 103-106 % at 1e9 because 768 consumer
+// threads per SM convert what the direct kernel spreads over 2048, and a 4-stage ring fill per CTA dominates short launches
+// (profiles/r1_sizebench_final_direct_vs_tma.txt, profiles/r2_ncu_bf16_u4_direct_vs_tma.txt).  It is kept tested to the same
+// bit-exact bar, is selectable per context (piquant_cuda_set_kernel_variant), and serves by default exactly one case the
+// direct kernels cannot: inputs that are 16- but not 32-byte aligned (LDG.256 needs 32, bulk copies need 16).
+// There is deliberately no size- or cell-dependent switch: no measured point favours the TMA family.
 
 }  // namespace pq

@@ -530,9 +530,9 @@ int launch_quantize(const void* in, int dt_in, void* out, int dt_out, int64_t nu
         else launch_out<DT_BF16>(a, dt_out, mode, a32, cfg);
         return 1;
     }
-    // variant 0 = per-cell choice from measurements on B200 (profiles/); 1 = direct, 2 = TMA where alignment allows
-    const int64_t traffic = numel * isz + numel / per;
-    const bool want_tma = cfg.variant == 2 || (cfg.variant == 0 && quantize_prefers_tma(dt_in, dt_out, mode, traffic)) || !a32;
+    // variants 0 / 1 = direct kernels, 2 = TMA ring where alignment allows (selection notes: pq_kernels.h); an input that is
+    // 16- but not 32-byte aligned goes to the TMA ring in every variant (bulk copies need 16, LDG.256 needs 32)
+    const bool want_tma = cfg.variant == 2 || !a32;
     if (a16 && want_tma) {
         const int n = launch_quantize_tma(in, dt_in, out, dt_out, numel, P, mode, cfg, dP);
         if (n) return n;

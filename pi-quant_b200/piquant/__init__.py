@@ -308,6 +308,10 @@ class Context:
         C.piquant_cuda_dequantize_forward_on_stream(self._ctx, ptr_in, dtype_in.value, ptr_out, dtype_out.value, numel, ptr_meta,
                                                     ptr_forward, ptr_forward_meta, device, stream)
 
+    def copy_on_stream(self, ptr_dst: int, ptr_src: int, nbytes: int, device: int, stream: int) -> None:
+        """Stream-ordered copy by a copy engine (cudaMemcpyAsync): local, peer-mapped or pinned memory on either side."""
+        C.piquant_cuda_copy_on_stream(self._ctx, ptr_dst, ptr_src, nbytes, device, stream)
+
     def quantize_batch(self, items, dtype_in: DataType, dtype_out: DataType, round_mode: RoundMode, device: int, stream: int) -> None:
         """items: sequence of (ptr_in, ptr_out, numel, scale, zero_point); ONE kernel launch per 256 tensors."""
         arr = ffi.new("piquant_cuda_batch_item_t[]", items if isinstance(items, list) else list(items))     # tuples initialise the structs

@@ -110,15 +110,16 @@ def ring_schedule(world_size: int, rank: int):
 
 
 _P2P_SLOTS: dict = {}
+_SIDE_STREAMS: dict = {}
 
 
-def _p2p_slots(nbytes: int, device: torch.device, group):
+def _p2p_slots(nbytes: int, device: torch.device, group, lane: int = 0):
     """Two receive slots per rank in symmetric memory (every rank can address every other rank's slots over
-    NVLink).  Cached per (group, device, size): the rendezvous is a collective and costs milliseconds."""
+    NVLink).  Cached per (group, device, size, lane): the rendezvous is a collective and costs milliseconds."""
     import torch.distributed._symmetric_memory as symm_mem
 
     grp = group if group is not None else dist.group.WORLD
-    key = (grp.group_name, device.index, nbytes)
+    key = (grp.group_name, device.index, nbytes, lane)
     if key not in _P2P_SLOTS:
         buf = symm_mem.empty(2 * nbytes, dtype=torch.uint8, device=device)
         hdl = symm_mem.rendezvous(buf, grp)
@@ -126,8 +127,15 @@ def _p2p_slots(nbytes: int, device: torch.device, group):
     return _P2P_SLOTS[key]
 
 
+def _side_stream(device: torch.device, lane: int) -> "torch.cuda.Stream":
+    key = (device.index, lane)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.quint8, group: Optional[dist.ProcessGroup] = None,
-                          ctx: Context = Context.get(), transport: str = "nccl", round_mode: str = "nearest") -> torch.Tensor:
+                          ctx: Context = Context.get(), transport: str = "nccl", round_mode: str = "nearest", lanes: int = 1) -> torch.Tensor:
     """In-place SUM all-reduce of a contiguous CUDA float32 / bfloat16 tensor with quantized transport.
 
     Ring reduce-scatter + ring all-gather over NVLink; every hop carries ``[64-byte parameter block | packed
@@ -149,115 +157,153 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
     receiver's slot, and in the all-gather phase the kernel that dequantizes a received chunk also stores its packed
     bytes on to the next rank (``piquant_cuda_dequantize_forward_on_stream``): compute and transfer are one kernel per
     direction, with one stream-ordered barrier per hop publishing the slot.  ``transport="auto"``: p2p when symmetric
-    memory is available, else nccl."""
+    memory is available, else nccl.
+
+    ``lanes`` (p2p only): the tensor is cut into that many contiguous parts, each reduced by its own ring on its own
+    stream, the hops enqueued alternately.  A hop alternates between an NVLink-bound kernel (the quantize that stores into
+    peer memory) and an HBM-bound one (the fused accumulate); with two lanes one lane's link phase overlaps the other's
+    memory phase.  Every lane is an independent all-reduce of its part: the result is a sum with per-part, per-chunk scales."""
     assert tensor.is_cuda and tensor.is_contiguous() and tensor.dtype in (torch.float32, torch.bfloat16)
     assert dtype in _QUANT_TYPES
     rmode = {"nearest": RoundMode.NEAREST, "stochastic_per_element": RoundMode.STOCHASTIC_PER_ELEMENT}[round_mode]
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if world == 1:
         return tensor
-    fdt, qdt = torch_to_piquant_dtype(tensor.dtype), torch_to_piquant_dtype(dtype)
-    flat = tensor.view(-1)
-    bounds = [shard_bounds(flat.numel(), world, i) for i in range(world)]
-    qbytes = [qdt.storage_bytes(e - b) for b, e in bounds]
-    meta = Context.META_BYTES
-    slot_bytes = (meta + max(qbytes) + 255) // 256 * 256
-    device, stream = _site(tensor)
-    LOCAL, REVERSE = Context.FLAG_LOCAL, Context.FLAG_REVERSE
-    hdl = None
-    if transport in ("p2p", "auto"):
-        try:
-            local_slots, hdl = _p2p_slots(slot_bytes, tensor.device, group)
-        except Exception:      # noqa: BLE001 -- no symmetric memory on this box / build
-            if transport == "p2p":
-                raise
-    elif transport != "nccl":
+    if transport not in ("nccl", "p2p", "auto"):
         raise ValueError(f"unknown transport {transport!r}")
-
-    def chunk(i):
-        b, e = bounds[i]
-        return flat[b:e]
-
-    def first_params(i, meta_ptr):      # min/max + parameter arithmetic of chunk i in ONE launch; never the communicator's whole-tensor path
-        c = chunk(i)
-        if c.numel():
-            ctx.compute_meta_on_stream(c.data_ptr(), fdt, c.numel(), qdt, meta_ptr, LOCAL, device, stream)
-
-    def quantize_to(i, payload_ptr, meta_ptr, flags=0):
-        c = chunk(i)
-        if c.numel():
-            ctx.quantize_meta_on_stream(c.data_ptr(), fdt, payload_ptr, qdt, c.numel(), rmode, meta_ptr, flags, device, stream)
-
-    def accumulate(i, base_ptr, next_meta_ptr, next_meta_copy_ptr):      # chunk i += [meta | packed] at base_ptr; parameters of the sums out
-        c = chunk(i)
-        if c.numel():
-            ctx.dequantize_add_minmax_on_stream(base_ptr + meta, qdt, c.data_ptr(), fdt, c.numel(), base_ptr, qdt, next_meta_ptr,
-                                                next_meta_copy_ptr, device, stream)
-
-    def scatter(i, base_ptr):           # chunk i = dequantize([meta | packed] at base_ptr)
-        c = chunk(i)
-        if c.numel():
-            ctx.dequantize_meta_on_stream(base_ptr + meta, qdt, c.data_ptr(), fdt, c.numel(), ReduceOp.SET, base_ptr, device, stream)
-
-    def scatter_forward(i, base_ptr, fwd_base_ptr):      # ... and store the same [meta | packed] on to fwd_base_ptr (peer memory)
-        c = chunk(i)
-        if c.numel():
-            ctx.dequantize_forward_on_stream(base_ptr + meta, qdt, c.data_ptr(), fdt, c.numel(), base_ptr, fwd_base_ptr + meta, fwd_base_ptr,
-                                             device, stream)
-
+    fdt, qdt = torch_to_piquant_dtype(tensor.dtype), torch_to_piquant_dtype(dtype)
+    meta = Context.META_BYTES
+    device = tensor.device.index
+    LOCAL, REVERSE = Context.FLAG_LOCAL, Context.FLAG_REVERSE
     reduce_scatter, all_gather = ring_schedule(world, rank)
     own = (rank + 1) % world
-    keep = torch.empty(slot_bytes, dtype=torch.uint8, device=tensor.device)      # [meta | packed] of the chunk this rank owns
-    if hdl is not None:
-        my_base, nxt_base = local_slots.data_ptr(), int(hdl.buffer_ptrs[(rank + 1) % world])
-        peer_hdr0 = hdl.get_buffer((rank + 1) % world, (meta,), torch.uint8)       # header of the neighbour's slot 0
-        cur = torch.empty(meta, dtype=torch.uint8, device=tensor.device)           # parameters of the chunk to send next
-        hdl.barrier(channel=0)               # nobody is still reading the slots of a previous call
-        first_params(reduce_scatter[0][0], cur.data_ptr())
-        peer_hdr0.copy_(cur, non_blocking=True)
-        step = 0
-        for send_i, recv_i in reduce_scatter:
-            off, nxt_off = (step % 2) * slot_bytes, ((step + 1) % 2) * slot_bytes
-            # quantize straight into the neighbour's slot over NVLink (its header is there already); from hop 1 on the chunk
-            # was just written by `accumulate`, so it is read from its end -- the part L2 still holds
-            quantize_to(send_i, nxt_base + off + meta, cur.data_ptr(), REVERSE if step else 0)
-            hdl.barrier(channel=0)                           # my slot `off` now holds chunk recv_i from my predecessor
-            # ONE kernel: chunk += dequantize(slot); parameters of the sums -> `cur` and -> the header of the neighbour's NEXT slot
-            accumulate(recv_i, my_base + off, cur.data_ptr(), nxt_base + nxt_off)
-            step += 1
-        # the owner keeps exactly what everybody else will receive: quantize the reduced chunk once, dequantize that
-        keep[:meta].copy_(cur, non_blocking=True)
-        quantize_to(own, keep.data_ptr() + meta, cur.data_ptr(), REVERSE)
-        src = keep.data_ptr()
-        for hop, (send_i, recv_i) in enumerate(all_gather):
-            off = (step % 2) * slot_bytes
-            scatter_forward(send_i, src, nxt_base + off)     # dequantize what I hold of chunk send_i AND store its packed bytes into the neighbour's slot
-            hdl.barrier(channel=0)
-            src = my_base + off                              # chunk recv_i has arrived; it is dequantized (and forwarded) by the next iteration
-            step += 1
-        scatter(all_gather[-1][1], src)
+
+    def ring(flat, stream, lane, use_p2p):
+        """generator: enqueues one ring all-reduce of `flat` on `stream`, yielding after every hop"""
+        bounds = [shard_bounds(flat.numel(), world, i) for i in range(world)]
+        qbytes = [qdt.storage_bytes(e - b) for b, e in bounds]
+        slot_bytes = (meta + max(qbytes) + 255) // 256 * 256
+
+        def chunk(i):
+            b, e = bounds[i]
+            return flat[b:e]
+
+        def first_params(i, meta_ptr):      # min/max + parameter arithmetic of chunk i in ONE launch; never the communicator's whole-tensor path
+            c = chunk(i)
+            if c.numel():
+                ctx.compute_meta_on_stream(c.data_ptr(), fdt, c.numel(), qdt, meta_ptr, LOCAL, device, stream)
+
+        def quantize_to(i, payload_ptr, meta_ptr, flags=0):
+            c = chunk(i)
+            if c.numel():
+                ctx.quantize_meta_on_stream(c.data_ptr(), fdt, payload_ptr, qdt, c.numel(), rmode, meta_ptr, flags, device, stream)
+
+        def accumulate(i, base_ptr, next_meta_ptr, next_meta_copy_ptr):      # chunk i += [meta | packed] at base_ptr; parameters of the sums out
+            c = chunk(i)
+            if c.numel():
+                ctx.dequantize_add_minmax_on_stream(base_ptr + meta, qdt, c.data_ptr(), fdt, c.numel(), base_ptr, qdt, next_meta_ptr,
+                                                    next_meta_copy_ptr, device, stream)
+
+        def scatter(i, base_ptr):           # chunk i = dequantize([meta | packed] at base_ptr)
+            c = chunk(i)
+            if c.numel():
+                ctx.dequantize_meta_on_stream(base_ptr + meta, qdt, c.data_ptr(), fdt, c.numel(), ReduceOp.SET, base_ptr, device, stream)
+
+        def scatter_forward(i, base_ptr, fwd_base_ptr):      # ... and store the same [meta | packed] on to fwd_base_ptr (peer memory)
+            c = chunk(i)
+            if c.numel():
+                ctx.dequantize_forward_on_stream(base_ptr + meta, qdt, c.data_ptr(), fdt, c.numel(), base_ptr, fwd_base_ptr + meta, fwd_base_ptr,
+                                                 device, stream)
+
+        keep = torch.empty(slot_bytes, dtype=torch.uint8, device=flat.device)      # [meta | packed] of the chunk this rank owns
+        if use_p2p:
+            local_slots, hdl = _p2p_slots(slot_bytes, flat.device, group, lane)
+            my_base, nxt_base = local_slots.data_ptr(), int(hdl.buffer_ptrs[(rank + 1) % world])
+            peer_hdr0 = hdl.get_buffer((rank + 1) % world, (meta,), torch.uint8)       # header of the neighbour's slot 0
+            cur = torch.empty(meta, dtype=torch.uint8, device=flat.device)             # parameters of the chunk to send next
+            hdl.barrier(channel=0)               # nobody is still reading the slots of a previous call
+            first_params(reduce_scatter[0][0], cur.data_ptr())
+            peer_hdr0.copy_(cur, non_blocking=True)
+            step = 0
+            for send_i, recv_i in reduce_scatter:
+                off, nxt_off = (step % 2) * slot_bytes, ((step + 1) % 2) * slot_bytes
+                # quantize straight into the neighbour's slot over NVLink (its header is there already); from hop 1 on the chunk
+                # was just written by `accumulate`, so it is read from its end -- the part L2 still holds
+                quantize_to(send_i, nxt_base + off + meta, cur.data_ptr(), REVERSE if step else 0)
+                hdl.barrier(channel=0)                           # my slot `off` now holds chunk recv_i from my predecessor
+                yield
+                # ONE kernel: chunk += dequantize(slot); parameters of the sums -> `cur` and -> the header of the neighbour's NEXT slot
+                accumulate(recv_i, my_base + off, cur.data_ptr(), nxt_base + nxt_off)
+                step += 1
+                yield
+            # the owner keeps exactly what everybody else will receive: quantize the reduced chunk once, dequantize that
+            keep[:meta].copy_(cur, non_blocking=True)
+            quantize_to(own, keep.data_ptr() + meta, cur.data_ptr(), REVERSE)
+            src = keep.data_ptr()
+            for send_i, recv_i in all_gather:
+                off = (step % 2) * slot_bytes
+                scatter_forward(send_i, src, nxt_base + off)     # dequantize what I hold of chunk send_i AND store its packed bytes into the neighbour's slot
+                hdl.barrier(channel=0)
+                src = my_base + off                              # chunk recv_i has arrived; it is dequantized (and forwarded) by the next iteration
+                step += 1
+                yield
+            scatter(all_gather[-1][1], src)
+            return
+
+        nxt = dist.get_global_rank(group, (rank + 1) % world) if group is not None else (rank + 1) % world
+        prv = dist.get_global_rank(group, (rank - 1) % world) if group is not None else (rank - 1) % world
+        send_buf, recv_buf, spare = keep, torch.empty_like(keep), torch.empty_like(keep)
+
+        def exchange(send_buf, send_i, recv_buf, recv_i):
+            ops = [dist.P2POp(dist.isend, send_buf[: meta + qbytes[send_i]], nxt, group=group),
+                   dist.P2POp(dist.irecv, recv_buf[: meta + qbytes[recv_i]], prv, group=group)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()                                       # stream-ordered: the current stream waits, the host does not
+
+        first_params(reduce_scatter[0][0], send_buf.data_ptr())
+        for hop, (send_i, recv_i) in enumerate(reduce_scatter):
+            quantize_to(send_i, send_buf.data_ptr() + meta, send_buf.data_ptr(), REVERSE if hop else 0)
+            exchange(send_buf, send_i, recv_buf, recv_i)
+            accumulate(recv_i, recv_buf.data_ptr(), send_buf.data_ptr(), 0)     # next hop's parameters land in the send buffer's header
+            yield
+        quantize_to(own, send_buf.data_ptr() + meta, send_buf.data_ptr(), REVERSE)
+        scatter(own, send_buf.data_ptr())            # the owner keeps exactly what everybody else will receive
+        for send_i, recv_i in all_gather:
+            exchange(send_buf, send_i, recv_buf, recv_i)
+            scatter(recv_i, recv_buf.data_ptr())
+            send_buf, recv_buf, spare = recv_buf, spare, send_buf     # forward what was just received
+            yield
+
+    flat = tensor.view(-1)
+    use_p2p = transport == "p2p"
+    if transport == "auto":
+        try:
+            _p2p_slots(256, tensor.device, group, -1)      # probe: is symmetric memory available on this box / build?
+            use_p2p = True
+        except Exception:      # noqa: BLE001
+            use_p2p = False
+    lanes = max(1, int(lanes)) if use_p2p else 1
+    main = torch.cuda.current_stream(tensor.device)
+    if lanes == 1 or flat.numel() < lanes * world * SHARD_ALIGN:
+        for _ in ring(flat, main.cuda_stream, 0, use_p2p):
+            pass
         return tensor
-
-    nxt = dist.get_global_rank(group, (rank + 1) % world) if group is not None else (rank + 1) % world
-    prv = dist.get_global_rank(group, (rank - 1) % world) if group is not None else (rank - 1) % world
-    bufs = [torch.empty(slot_bytes, dtype=torch.uint8, device=tensor.device) for _ in range(3)]
-
-    def exchange(send_buf, send_i, recv_buf, recv_i):
-        ops = [dist.P2POp(dist.isend, send_buf[: meta + qbytes[send_i]], nxt, group=group),
-               dist.P2POp(dist.irecv, recv_buf[: meta + qbytes[recv_i]], prv, group=group)]
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()                                       # stream-ordered: the current stream waits, the host does not
-
-    send_buf, recv_buf, spare = bufs
-    first_params(reduce_scatter[0][0], send_buf.data_ptr())
-    for hop, (send_i, recv_i) in enumerate(reduce_scatter):
-        quantize_to(send_i, send_buf.data_ptr() + meta, send_buf.data_ptr(), REVERSE if hop else 0)
-        exchange(send_buf, send_i, recv_buf, recv_i)
-        accumulate(recv_i, recv_buf.data_ptr(), send_buf.data_ptr(), 0)     # next hop's parameters land in the send buffer's header
-    quantize_to(own, send_buf.data_ptr() + meta, send_buf.data_ptr(), REVERSE)
-    scatter(own, send_buf.data_ptr())            # the owner keeps exactly what everybody else will receive
-    for send_i, recv_i in all_gather:
-        exchange(send_buf, send_i, recv_buf, recv_i)
-        scatter(recv_i, recv_buf.data_ptr())
-        send_buf, recv_buf, spare = recv_buf, spare, send_buf     # forward what was just received
+    # several lanes: contiguous parts, one ring and one stream each, hops enqueued alternately
+    per = flat.numel() // lanes // SHARD_ALIGN * SHARD_ALIGN
+    parts = [flat[i * per: (i + 1) * per if i < lanes - 1 else flat.numel()] for i in range(lanes)]
+    streams = [main] + [_side_stream(tensor.device, i) for i in range(1, lanes)]
+    for st in streams[1:]:
+        st.wait_stream(main)
+    gens = []
+    for i, (part, st) in enumerate(zip(parts, streams)):
+        gens.append((st, ring(part, st.cuda_stream, i, True)))
+    while gens:
+        for st, g in list(gens):
+            with torch.cuda.stream(st):          # torch-side work of the lane (barriers, header copies) goes to the lane's stream too
+                try:
+                    next(g)
+                except StopIteration:
+                    gens.remove((st, g))
+    for st in streams[1:]:
+        main.wait_stream(st)
     return tensor

@@ -89,12 +89,13 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
         res["sharded_quantize_auto"] = ((s_auto, z_auto) == orc.compute_quant_params(x, orc.UINT8), bool(np.array_equal(q_auto.cpu().numpy(), whole8[b:e])))
         pd.destroy_native_comm(ctx)
         # quantized ring all-reduce: every rank ends with bit-identical values, close to the exact sum
-        for tdt, qdt, transport, rmode in ((torch.float32, torch.quint8, "nccl", "nearest"), (torch.bfloat16, torch.quint8, "nccl", "nearest"),
-                                           (torch.float32, torch.quint4x2, "nccl", "nearest"), (torch.float32, torch.quint8, "p2p", "nearest"),
-                                           (torch.bfloat16, torch.quint4x2, "p2p", "nearest"), (torch.float32, torch.quint8, "p2p", "nearest"),
-                                           (torch.float32, torch.quint8, "p2p", "stochastic_per_element"),
-                                           (torch.float32, torch.quint4x2, "auto", "nearest"), (torch.bfloat16, torch.quint8, "auto", "nearest"),
-                                           (torch.float32, torch.quint8, "nccl", "stochastic_per_element")):
+        for tdt, qdt, transport, rmode, lanes in ((torch.float32, torch.quint8, "nccl", "nearest", 1), (torch.bfloat16, torch.quint8, "nccl", "nearest", 1),
+                                                  (torch.float32, torch.quint4x2, "nccl", "nearest", 1), (torch.float32, torch.quint8, "p2p", "nearest", 1),
+                                                  (torch.bfloat16, torch.quint4x2, "p2p", "nearest", 1), (torch.float32, torch.quint8, "p2p", "nearest", 1),
+                                                  (torch.float32, torch.quint8, "p2p", "stochastic_per_element", 1),
+                                                  (torch.float32, torch.quint4x2, "auto", "nearest", 1), (torch.bfloat16, torch.quint8, "auto", "nearest", 1),
+                                                  (torch.float32, torch.quint8, "p2p", "nearest", 2), (torch.bfloat16, torch.quint8, "p2p", "nearest", 3),
+                                                  (torch.float32, torch.quint8, "nccl", "stochastic_per_element", 1)):
             tol_steps = 1.0 if rmode == "nearest" else 2.0          # per-element SR: up to one step per hop instead of half a step
             g = torch.Generator(device="cuda").manual_seed(100 + rank)
             t = (torch.rand(1_000_003, device="cuda", generator=g) * 2 - 1).to(tdt)
@@ -102,10 +103,10 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
             dist.all_reduce(exact)
             inputs = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(inputs, t)
-            pd.quantized_all_reduce_(t, dtype=qdt, ctx=ctx, transport=transport, round_mode=rmode)
+            pd.quantized_all_reduce_(t, dtype=qdt, ctx=ctx, transport=transport, round_mode=rmode, lanes=lanes)
             if rmode == "nearest":
                 # the whole collective replayed on the CPU with the oracle, hop by hop: the GPU result must be bit-identical
-                want = _ring_on_the_oracle(orc, pd, [i.cpu() for i in inputs], qdt)
+                want = _ring_on_the_oracle(orc, pd, [i.cpu() for i in inputs], qdt, lanes)
                 res[f"ring_bit_exact_{transport}_{tdt}_{qdt}_{len(res)}"] = (bool(np.array_equal(_bits(t.cpu()), want)),)
             gathered = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(gathered, t)
@@ -117,7 +118,7 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
             ok = (identical, err <= bound)
             if rmode != "nearest":      # unbiased: the mean error over 1e6 elements is far below one step
                 ok += (abs((t.double() - exact).mean().item()) < 0.01 * step,)
-            res[f"ring_{transport}_{tdt}_{qdt}_{rmode}_{len(res)}"] = ok
+            res[f"ring_{transport}_{tdt}_{qdt}_{rmode}_lanes{lanes}_{len(res)}"] = ok
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
@@ -128,7 +129,7 @@ def _bits(t):
     return t.contiguous().view(torch.uint8).numpy().copy()
 
 
-def _ring_on_the_oracle(orc, pd, inputs, qdt):
+def _ring_on_the_oracle(orc, pd, inputs, qdt, lanes=1):
     """What quantized_all_reduce_ computes, restated with the CPU oracle: chunk c starts on rank c, is quantized with the
     parameters of the running sum at every hop and accumulated with dequantize-ADD on the next rank; the rank that holds
     the complete sum quantizes it once more and EVERY rank takes the dequantized values of those packed bytes."""
@@ -140,17 +141,21 @@ def _ring_on_the_oracle(orc, pd, inputs, qdt):
     host = [(i.view(torch.int16).numpy().view(np.uint16).copy() if is_bf16 else i.numpy().copy()) for i in inputs]
     n = host[0].size
     out = np.empty_like(host[0])
-    for c in range(world):
-        b, e = pd.shard_bounds(n, world, c)
-        if e == b:
-            continue
-        acc = host[c][b:e].copy()
-        for k in range(1, world):
+    per = n // lanes // pd.SHARD_ALIGN * pd.SHARD_ALIGN           # every lane is an independent ring over its contiguous part
+    for lane in range(lanes):
+        p0, p1 = lane * per, ((lane + 1) * per if lane < lanes - 1 else n)
+        for c in range(world):
+            b, e = pd.shard_bounds(p1 - p0, world, c)
+            b, e = b + p0, e + p0
+            if e == b:
+                continue
+            acc = host[c][b:e].copy()
+            for k in range(1, world):
+                s, z = orc.compute_quant_params(acc, odt)
+                q = orc.quantize(acc, odt, s, z)
+                acc = orc.dequantize(q, odt, e - b, fdt, s, z, orc.ADD, out=host[(c + k) % world][b:e].copy())
             s, z = orc.compute_quant_params(acc, odt)
-            q = orc.quantize(acc, odt, s, z)
-            acc = orc.dequantize(q, odt, e - b, fdt, s, z, orc.ADD, out=host[(c + k) % world][b:e].copy())
-        s, z = orc.compute_quant_params(acc, odt)
-        out[b:e] = orc.dequantize(orc.quantize(acc, odt, s, z), odt, e - b, fdt, s, z, orc.SET)
+            out[b:e] = orc.dequantize(orc.quantize(acc, odt, s, z), odt, e - b, fdt, s, z, orc.SET)
     return out.view(np.uint8)
 
 
