@@ -216,6 +216,21 @@ PIQUANT_EXPORT void piquant_cuda_dequantize_forward_on_stream(piquant_context_t*
                                                               piquant_dtype_t dtype_out, size_t numel, const piquant_cuda_meta_t* d_meta,
                                                               void* forward_to, piquant_cuda_meta_t* forward_meta_to, int device, void* stream);
 
+/* Reduce step of an all-to-all ("direct") quantized all-reduce on an NVSwitch box: every rank has received one packed chunk
+ * from every other rank.  out += dequantize(ins[0]; d_metas[0]) + ... + dequantize(ins[count-1]; d_metas[count-1]), the
+ * sources folded IN ORDER with exactly the arithmetic of `count` successive piquant_dequantize(PIQUANT_REDUCE_OP_ADD) calls
+ * (bit-identical to them: a bf16 accumulator is rounded after every source), in ONE pass over `out` -- 2*sizeof(out
+ * type) + count*bits/8 bytes per element instead of count * (2*sizeof + bits/8) -- and, like
+ * piquant_cuda_dequantize_add_minmax_on_stream, min/max of the sums -> parameters for next_quant_dtype -> d_meta_next
+ * (+ d_meta_next_copy unless NULL).  1 <= count <= PIQUANT_CUDA_MAX_SUM_SOURCES; every source holds `numel` elements of
+ * dtype_in.  ins / d_metas are HOST arrays of device pointers (read before the call returns). */
+#define PIQUANT_CUDA_MAX_SUM_SOURCES 8
+PIQUANT_EXPORT void piquant_cuda_dequantize_sum_minmax_on_stream(piquant_context_t* ctx, const void* const* ins,
+                                                                 const piquant_cuda_meta_t* const* d_metas, size_t count,
+                                                                 piquant_dtype_t dtype_in, void* out, piquant_dtype_t dtype_out, size_t numel,
+                                                                 piquant_dtype_t next_quant_dtype, piquant_cuda_meta_t* d_meta_next,
+                                                                 piquant_cuda_meta_t* d_meta_next_copy, int device, void* stream);
+
 /* Stream-ordered copy of nbytes between any two device-accessible buffers (local, peer-mapped, pinned host) by a COPY
  * ENGINE (cudaMemcpyAsync): the SM-free way to move a packed payload into a neighbour's slot.  A kernel that stores into
  * peer memory is link-bound (NVLink sustains ~0.6 TB/s against ~7 TB/s of HBM) and holds every SM it occupies for the

@@ -21,8 +21,8 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "piquant" / "libpiquant.so"
 OBJ = HERE / "build"
-SOURCES = ["context.cu", "quantize.cu", "quantize_tma.cu", "dequantize.cu", "dequantize_tma.cu", "requantize.cu", "minmax.cu"]
-HEADERS = [CSRC / "pq_device.cuh", CSRC / "pq_kernels.h", CSRC / "quantize_common.cuh", CSRC / "dequantize_common.cuh", CSRC / "pq_tma.cuh",
+SOURCES = ["context.cu", "quantize.cu", "quantize_tma.cu", "dequantize.cu", "dequantize_tma.cu", "requantize.cu", "minmax.cu", "reduce_sum.cu"]
+HEADERS = [CSRC / "pq_device.cuh", CSRC / "pq_kernels.h", CSRC / "quantize_common.cuh", CSRC / "dequantize_common.cuh", CSRC / "pq_tma.cuh", CSRC / "pq_reduce.cuh",
            HERE.parent / "include" / "piquant.h", HERE.parent / "include" / "piquant_cuda.h"]
 
 NVCC_FLAGS = [

@@ -1368,6 +1368,40 @@ extern "C" void piquant_cuda_dequantize_add_minmax_on_stream(piquant_context_t* 
                                                 lease.cfg(*c), &reinterpret_cast<const DeviceMeta*>(d_meta)->P, lease.s->scratch, ro);
 }
 
+extern "C" void piquant_cuda_dequantize_sum_minmax_on_stream(piquant_context_t* ctx, const void* const* ins,
+                                                             const piquant_cuda_meta_t* const* d_metas, size_t count,
+                                                             piquant_dtype_t dtype_in, void* out, piquant_dtype_t dtype_out, size_t numel,
+                                                             piquant_dtype_t next_quant_dtype, piquant_cuda_meta_t* d_meta_next,
+                                                             piquant_cuda_meta_t* d_meta_next_copy, int device, void* stream) {
+    Context* c = as_ctx(ctx);
+    pq_assert(dtype_is_quant(dtype_in), "input dtype (%s) must be a quantized type", dtype_name(dtype_in));
+    pq_assert(dtype_is_float(dtype_out), "output dtype (%s) must be a dequantized type", dtype_name(dtype_out));
+    pq_assert(dtype_is_quant(next_quant_dtype), "type %s is not a quantization type", dtype_name(next_quant_dtype));
+    pq_assert(numel > 0, "sum of empty tensors");
+    pq_assert(count >= 1 && count <= PIQUANT_CUDA_MAX_SUM_SOURCES, "between 1 and %d sources per call (got %zu)", PIQUANT_CUDA_MAX_SUM_SOURCES, count);
+    pq_assert(ins != nullptr && d_metas != nullptr && d_meta_next != nullptr, "source arrays and parameter block must not be NULL");
+    check_float_ptr(out, dtype_out, "output");
+    const void* in_ptrs[kMaxSumSources];
+    const QuantParams* params[kMaxSumSources];
+    for (size_t s = 0; s < count; ++s) {
+        pq_assert(ins[s] != nullptr && d_metas[s] != nullptr, "source %zu: input and parameter block must not be NULL", s);
+        in_ptrs[s] = ins[s];
+        params[s] = &reinterpret_cast<const DeviceMeta*>(d_metas[s])->P;
+    }
+    const Site site = call_site(device, stream);
+    const int cur = require_device();
+    const int dev = device_of(site, {out, in_ptrs[0], d_metas[0], d_meta_next}, "piquant_cuda_dequantize_sum_minmax");
+    DeviceGuard guard(cur, dev);
+    Lease lease = acquire(*c, dev, site.stream);
+    ReduceOut ro;
+    ro.result = lease.s->d_result;
+    ro.meta_out = reinterpret_cast<DeviceMeta*>(d_meta_next);
+    ro.meta_out2 = reinterpret_cast<DeviceMeta*>(d_meta_next_copy);
+    ro.dt_quant = next_quant_dtype;
+    c->launches += launch_dequantize_sum_minmax(in_ptrs, params, static_cast<int>(count), dtype_kernel_view(dtype_in), out, dtype_out,
+                                                static_cast<int64_t>(numel), lease.cfg(*c), lease.s->scratch, ro);
+}
+
 extern "C" void piquant_cuda_dequantize_forward_on_stream(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
                                                           piquant_dtype_t dtype_out, size_t numel, const piquant_cuda_meta_t* d_meta,
                                                           void* forward_to, piquant_cuda_meta_t* forward_meta_to, int device, void* stream) {

@@ -203,6 +203,12 @@ int launch_dequantize_forward(const void* in, int dt_in, void* out, int dt_out, 
                               const LaunchCfg& cfg, const QuantParams* device_params, void* fwd, const DeviceMeta* fwd_meta_src,
                               DeviceMeta* fwd_meta_dst);
 
+// out += dequantize(ins[0]) + ... + dequantize(ins[n_src-1]) in one pass, sources folded in order with the ADD store op's
+// arithmetic (bit-identical to n_src separate ADD launches), min/max (+ parameters) of the sums to `ro` (reduce_sum.cu).
+constexpr int kMaxSumSources = 8;
+int launch_dequantize_sum_minmax(const void* const* ins, const QuantParams* const* device_params, int n_src, int dt_in, void* out, int dt_out,
+                                 int64_t numel, const LaunchCfg& cfg, const MinMaxScratch& scratch, const ReduceOut& ro);
+
 // Many small tensors, ONE launch (quantize.cu): tensors[i] = {in, out, numel, scale, zero_point}, all with the same
 // (dt_in, dt_out, mode).  Returns the number of kernels launched (one per 256 tensors).
 struct BatchItem {

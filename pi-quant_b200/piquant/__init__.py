@@ -248,6 +248,7 @@ class Context:
 
     DEVICE_AUTO = -1
     FLAG_LOCAL, FLAG_KEEP_IN_L2, FLAG_REVERSE = 1, 2, 4
+    MAX_SUM_SOURCES = 8          # PIQUANT_CUDA_MAX_SUM_SOURCES
 
     def quantize_on_stream(self, ptr_in: int, dtype_in: DataType, ptr_out: int, dtype_out: DataType, numel: int, scale: float,
                            zero_point: int, round_mode: RoundMode, device: int, stream: int) -> None:
@@ -307,6 +308,15 @@ class Context:
         """out = dequantize(in) and, in the same launch, the packed bytes (+ parameter block) stored on to the next rank (ring all-gather)."""
         C.piquant_cuda_dequantize_forward_on_stream(self._ctx, ptr_in, dtype_in.value, ptr_out, dtype_out.value, numel, ptr_meta,
                                                     ptr_forward, ptr_forward_meta, device, stream)
+
+    def dequantize_sum_minmax_on_stream(self, ptrs_in, dtype_in: DataType, ptr_out: int, dtype_out: DataType, numel: int, ptrs_meta,
+                                        next_quant_dtype: DataType, ptr_meta_next: int, ptr_meta_next_copy: int, device: int, stream: int) -> None:
+        """``out += dequantize(ptrs_in[0]) + dequantize(ptrs_in[1]) + ...`` (sources folded in order, bit-identical to that many
+        ADD calls) in ONE pass, plus min/max + parameters of the sums for ``next_quant_dtype`` -> ``ptr_meta_next``."""
+        ins, metas = ffi.new("uintptr_t[]", list(ptrs_in)), ffi.new("uintptr_t[]", list(ptrs_meta))
+        assert len(ins) == len(metas)
+        C.piquant_cuda_dequantize_sum_minmax_on_stream(self._ctx, ins, metas, len(ins), dtype_in.value, ptr_out, dtype_out.value, numel,
+                                                       next_quant_dtype.value, ptr_meta_next, ptr_meta_next_copy, device, stream)
 
     def copy_on_stream(self, ptr_dst: int, ptr_src: int, nbytes: int, device: int, stream: int) -> None:
         """Stream-ordered copy by a copy engine (cudaMemcpyAsync): local, peer-mapped or pinned memory on either side."""

@@ -135,8 +135,14 @@ def _side_stream(device: torch.device, lane: int) -> "torch.cuda.Stream":
 
 
 def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.quint8, group: Optional[dist.ProcessGroup] = None,
-                          ctx: Context = Context.get(), transport: str = "nccl", round_mode: str = "nearest", lanes: int = 1) -> torch.Tensor:
+                          ctx: Context = Context.get(), transport: str = "nccl", round_mode: str = "nearest", lanes: int = 1,
+                          algorithm: str = "ring") -> torch.Tensor:
     """In-place SUM all-reduce of a contiguous CUDA float32 / bfloat16 tensor with quantized transport.
+
+    ``algorithm="direct"`` (needs peer memory; see ``_direct_all_reduce``) is the NVSwitch-native form: every chunk
+    crosses the links once per phase like in a ring, but in ONE all-to-all exchange per phase instead of world-1
+    dependent hops, every value is quantized twice in total instead of ``world`` times, and the reduce step is one pass.
+    The rest of this text describes ``algorithm="ring"``.
 
     Ring reduce-scatter + ring all-gather over NVLink; every hop carries ``[64-byte parameter block | packed
     payload]`` -- 1, 1/2 or 1/4 byte per element instead of 4 (or 2).  A reduce-scatter hop is TWO passes over the
@@ -171,6 +177,12 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
         return tensor
     if transport not in ("nccl", "p2p", "auto"):
         raise ValueError(f"unknown transport {transport!r}")
+    if algorithm not in ("ring", "direct"):
+        raise ValueError(f"unknown algorithm {algorithm!r}")
+    if algorithm == "direct":
+        if transport == "nccl":
+            raise ValueError("algorithm='direct' moves the chunks with copy engines through peer memory; transport must be 'p2p' or 'auto'")
+        return _direct_all_reduce(tensor, dtype, group, ctx, rmode)
     fdt, qdt = torch_to_piquant_dtype(tensor.dtype), torch_to_piquant_dtype(dtype)
     meta = Context.META_BYTES
     device = tensor.device.index
@@ -306,4 +318,104 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
                     gens.remove((st, g))
     for st in streams[1:]:
         main.wait_stream(st)
+    return tensor
+
+
+_COPY_STREAMS: dict = {}
+
+
+def _copy_streams(device: torch.device, n: int):
+    key = device.index
+    have = _COPY_STREAMS.setdefault(key, [])
+    while len(have) < n:
+        have.append(torch.cuda.Stream(device=device))
+    return have[:n]
+
+
+def _direct_all_reduce(tensor: torch.Tensor, dtype: torch.dtype, group, ctx: Context, rmode: RoundMode, copy_streams: int = 3) -> torch.Tensor:
+    """Quantized all-reduce as two all-to-all exchanges over NVSwitch (every GPU reaches every peer at full link rate).
+
+    Chunk c of the tensor (``shard_bounds``) is owned by rank c.
+
+    1. scatter-reduce: for every other rank j, ONE launch computes min/max + parameters of my chunk j, one launch quantizes
+       it into a local staging slot ``[64-byte parameter block | packed payload]``, and a COPY ENGINE moves the slot into
+       rank j's receive slot number ``rank`` (``piquant_cuda_copy_on_stream`` on side streams): the SMs go on with chunk
+       j + 1 while chunk j is on the wire, so the phase costs what the link costs.
+    2. one stream-ordered barrier; then ONE kernel folds the world-1 received slots into my own float chunk in rank
+       order -- exactly world-1 successive dequantize(ADD) calls, in one pass -- and produces the parameters of the sums
+       (``piquant_cuda_dequantize_sum_minmax_on_stream``); the sums are quantized once and copy engines broadcast
+       ``[parameters | packed sums]`` to every peer's gather slot number ``rank`` while this rank dequantizes its own copy.
+    3. one barrier; every rank dequantizes the world-1 gathered slots (SET).  Owners dequantize the same bytes they sent,
+       so all ranks end with bit-identical values.
+
+    Every element is quantized twice whatever the world size (the ring quantizes the running sum at every hop), there
+    are 3 barriers instead of 2 * (world - 1), and nothing synchronises with the host."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    fdt, qdt = torch_to_piquant_dtype(tensor.dtype), torch_to_piquant_dtype(dtype)
+    meta = Context.META_BYTES
+    dev = tensor.device
+    device = dev.index
+    LOCAL, REVERSE = Context.FLAG_LOCAL, Context.FLAG_REVERSE
+    flat = tensor.view(-1)
+    bounds = [shard_bounds(flat.numel(), world, i) for i in range(world)]
+    qbytes = [qdt.storage_bytes(e - b) for b, e in bounds]
+    slot_bytes = (meta + max(qbytes) + 255) // 256 * 256
+    main = torch.cuda.current_stream(dev)
+    st = main.cuda_stream
+    sides = _copy_streams(dev, max(1, min(copy_streams, world - 1)))
+    # symmetric memory: [world scatter-reduce slots | world gather slots]; slot k of the first half receives from rank k,
+    # slot k of the second half holds the reduced chunk k
+    local, hdl = _p2p_slots(world * slot_bytes, dev, group, lane=-2)       # (2 * nbytes are allocated: two halves)
+    my_base = local.data_ptr()
+    peer_base = [int(hdl.buffer_ptrs[i]) for i in range(world)]
+    rs_off = lambda k: k * slot_bytes                                      # noqa: E731
+    ag_off = lambda k: (world + k) * slot_bytes                            # noqa: E731
+    stage = torch.empty((world - 1) * slot_bytes, dtype=torch.uint8, device=dev)
+
+    def chunk(i):
+        b, e = bounds[i]
+        return flat[b:e]
+
+    def send(src_ptr, dst_ptr, nbytes, k):
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side = sides[k % len(sides)]
+        side.wait_event(ev)
+        ctx.copy_on_stream(dst_ptr, src_ptr, nbytes, device, side.cuda_stream)
+
+    def join_sides():
+        for side in sides:
+            main.wait_stream(side)
+
+    hdl.barrier(channel=0)                                   # nobody still reads the slots of a previous call
+    others = [(rank + d) % world for d in range(1, world)]   # staggered: at any moment every rank receives from one sender
+    for k, j in enumerate(others):
+        c = chunk(j)
+        if not c.numel():
+            continue
+        base = stage.data_ptr() + k * slot_bytes
+        ctx.compute_meta_on_stream(c.data_ptr(), fdt, c.numel(), qdt, base, LOCAL, device, st)
+        ctx.quantize_meta_on_stream(c.data_ptr(), fdt, base + meta, qdt, c.numel(), rmode, base, REVERSE, device, st)
+        send(base, peer_base[j] + rs_off(rank), meta + qbytes[j], k)
+    join_sides()
+    hdl.barrier(channel=0)                                   # my scatter-reduce slots are complete
+    mine = chunk(rank)
+    own_slot = my_base + ag_off(rank)
+    if mine.numel():
+        srcs = [my_base + rs_off(k) for k in range(world) if k != rank]
+        for g in range(0, len(srcs), Context.MAX_SUM_SOURCES):       # one launch up to 9 ranks; the last launch's parameters are the sums'
+            part = srcs[g:g + Context.MAX_SUM_SOURCES]
+            ctx.dequantize_sum_minmax_on_stream([p + meta for p in part], qdt, mine.data_ptr(), fdt, mine.numel(), part, qdt, own_slot, 0, device, st)
+        ctx.quantize_meta_on_stream(mine.data_ptr(), fdt, own_slot + meta, qdt, mine.numel(), rmode, own_slot, REVERSE, device, st)
+        for k, j in enumerate(others):
+            send(own_slot, peer_base[j] + ag_off(rank), meta + qbytes[rank], k)
+        # the owner takes the dequantized values of exactly the bytes everybody else receives
+        ctx.dequantize_meta_on_stream(own_slot + meta, qdt, mine.data_ptr(), fdt, mine.numel(), ReduceOp.SET, own_slot, device, st)
+    join_sides()
+    hdl.barrier(channel=0)                                   # my gather slots are complete
+    for j in others:
+        c = chunk(j)
+        if c.numel():
+            src = my_base + ag_off(j)
+            ctx.dequantize_meta_on_stream(src + meta, qdt, c.data_ptr(), fdt, c.numel(), ReduceOp.SET, src, device, st)
     return tensor

@@ -121,6 +121,87 @@ def test_dequantize_add_minmax_equals_the_two_passes(dt_q, dt_out):
                     assert launched == 1, "aligned buffers must take the ONE fused kernel"
 
 
+@pytest.mark.parametrize("dt_out", FLOAT_DTYPES, ids=lambda d: DT_NAME[d])
+@pytest.mark.parametrize("dt_q", QUANT_DTYPES, ids=lambda d: DT_NAME[d])
+def test_dequantize_sum_minmax_equals_successive_add_calls(dt_q, dt_out):
+    """``piquant_cuda_dequantize_sum_minmax_on_stream``: up to 8 packed sources folded into the accumulator in ONE pass ==
+    that many piquant_dequantize(ADD) calls of the reference, in order, and the parameters of the sums."""
+    from gpu_util import DT
+    ctx = _ctx()
+    rng = np.random.default_rng(17)
+    dev, st = _site()
+    odt = np.float32 if dt_out == F32 else np.uint16
+    for n, n_src in ((1, 1), (63, 2), (64, 3), (4097, 7), (65_536, 8), (1_000_003, 7), (262_144 * 3 + 5, 5)):
+        for in_off, out_off in ((0, 0), (0, 16), (4, 0), (1, 2 if dt_out == BF16 else 4)):
+            acc = make_input(rng, n, dt_out, -1.0, 1.0)
+            want_out = acc.copy()
+            d_qs, metas = [], []
+            for k in range(n_src):
+                src = make_input(rng, n, F32, -2.0 - k, 3.0 + 0.5 * k)      # every source has its own range -> its own parameters
+                s_in, z_in = port.compute_quant_params(src, dt_q)
+                q = port.quantize(src, dt_q, s_in, z_in, NEAREST, semantics=SEM_BODY)
+                want_out = port.dequantize(q, dt_q, n, dt_out, s_in, z_in, ADD, out=want_out, semantics=SEM_BODY)
+                d_qs.append(_dev_bytes(q, in_off))
+                meta = torch.zeros(64, dtype=torch.uint8, device="cuda")
+                ctx.compute_meta_on_stream(_dev_bytes(src).data_ptr(), DT[F32], n, DT[dt_q], meta.data_ptr(), 0, dev, st)
+                metas.append(meta)
+            want_params = port.compute_quant_params(want_out, UINT8)
+            d_acc = _dev_bytes(acc, out_off)
+            nxt = torch.zeros(64, dtype=torch.uint8, device="cuda")
+            nxt2 = torch.zeros(64, dtype=torch.uint8, device="cuda")
+            before = ctx.kernel_launches
+            ctx.dequantize_sum_minmax_on_stream([t.data_ptr() for t in d_qs], DT[dt_q], d_acc.data_ptr(), DT[dt_out], n,
+                                                [m.data_ptr() for m in metas], DT[UINT8], nxt.data_ptr(), nxt2.data_ptr(), dev, st)
+            launched = ctx.kernel_launches - before
+            got_out = d_acc.cpu().numpy().view(odt)
+            assert np.array_equal(got_out.view(np.uint8), want_out.view(np.uint8)), (n, n_src, in_off, out_off)
+            assert _meta_tuple(nxt) == (_f32_bits(want_params[0]), 0, want_params[1]), (n, n_src, in_off, out_off)
+            assert torch.equal(nxt, nxt2)
+            if n >= 64 and in_off == 0 and out_off == 0:
+                assert launched == 1, "aligned buffers must take the ONE multi-source kernel"
+
+
+def test_dequantize_sum_minmax_mixed_alignment_and_flagged_source():
+    """Sources that do not share a byte phase take the separate launches (same results); a flagged parameter block stops
+    the whole launch and flags the block it was to produce."""
+    from gpu_util import DT
+    ctx = _ctx()
+    rng = np.random.default_rng(19)
+    dev, st = _site()
+    n = 300_001
+    acc = make_input(rng, n, F32, -1.0, 1.0)
+    want_out = acc.copy()
+    d_qs, metas = [], []
+    for k, off in enumerate((0, 4, 16)):
+        src = make_input(rng, n, F32, -1.0, 2.0 + k)
+        s_in, z_in = port.compute_quant_params(src, UINT4)
+        q = port.quantize(src, UINT4, s_in, z_in, NEAREST, semantics=SEM_BODY)
+        want_out = port.dequantize(q, UINT4, n, F32, s_in, z_in, ADD, out=want_out, semantics=SEM_BODY)
+        d_qs.append(_dev_bytes(q, off))
+        meta = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        ctx.compute_meta_on_stream(_dev_bytes(src).data_ptr(), DT[F32], n, DT[UINT4], meta.data_ptr(), 0, dev, st)
+        metas.append(meta)
+    d_acc = _dev_bytes(acc)
+    nxt = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    before = ctx.kernel_launches
+    ctx.dequantize_sum_minmax_on_stream([t.data_ptr() for t in d_qs], DT[UINT4], d_acc.data_ptr(), DT[F32], n, [m.data_ptr() for m in metas],
+                                        DT[UINT8], nxt.data_ptr(), 0, dev, st)
+    assert ctx.kernel_launches - before == 3
+    assert np.array_equal(d_acc.cpu().numpy().view(np.uint8), want_out.view(np.uint8))
+    want = port.compute_quant_params(want_out, UINT8)
+    assert _meta_tuple(nxt) == (_f32_bits(want[0]), 0, want[1])
+    # flagged source (error word = 1): accumulator untouched, produced block flagged
+    bad = metas[1].clone()
+    bad[4:8] = torch.tensor([1, 0, 0, 0], dtype=torch.uint8, device="cuda")
+    d_qs = [_dev_bytes(np.zeros(packed_bytes(UINT4, n), dtype=np.uint8)) for _ in range(3)]
+    d_acc = _dev_bytes(acc)
+    nxt = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    ctx.dequantize_sum_minmax_on_stream([t.data_ptr() for t in d_qs], DT[UINT4], d_acc.data_ptr(), DT[F32], n,
+                                        [metas[0].data_ptr(), bad.data_ptr(), metas[2].data_ptr()], DT[UINT8], nxt.data_ptr(), 0, dev, st)
+    assert np.array_equal(d_acc.cpu().numpy().view(np.uint8), acc.view(np.uint8))
+    assert _meta_tuple(nxt)[1] == 1
+
+
 def test_dequantize_add_minmax_ignores_nan_like_the_minmax_kernel():
     from gpu_util import DT
     ctx = _ctx()

@@ -89,6 +89,31 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
         res["sharded_quantize_auto"] = ((s_auto, z_auto) == orc.compute_quant_params(x, orc.UINT8), bool(np.array_equal(q_auto.cpu().numpy(), whole8[b:e])))
         pd.destroy_native_comm(ctx)
         # quantized ring all-reduce: every rank ends with bit-identical values, close to the exact sum
+        # the NVSwitch form: two all-to-all exchanges, ONE multi-source reduce kernel; replayed on the CPU with the oracle
+        for tdt, qdt, rmode, numel in ((torch.float32, torch.quint8, "nearest", 1_000_003), (torch.bfloat16, torch.quint8, "nearest", 1_000_003),
+                                       (torch.float32, torch.quint4x2, "nearest", 300_007), (torch.bfloat16, torch.quint2x4, "nearest", 70_001),
+                                       (torch.float32, torch.quint8, "nearest", 100), (torch.float32, torch.quint8, "nearest", 4_194_304),
+                                       (torch.float32, torch.quint8, "stochastic_per_element", 1_000_003)):
+            g = torch.Generator(device="cuda").manual_seed(500 + rank)
+            t = (torch.rand(numel, device="cuda", generator=g) * 2 - 1).to(tdt)
+            exact = t.double().clone()
+            dist.all_reduce(exact)
+            inputs = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(inputs, t)
+            pd.quantized_all_reduce_(t, dtype=qdt, ctx=ctx, transport="p2p", round_mode=rmode, algorithm="direct")
+            key = f"direct_{tdt}_{qdt}_{rmode}_{numel}"
+            if rmode == "nearest":
+                want = _direct_on_the_oracle(orc, pd, [i.cpu() for i in inputs], qdt)
+                res[key + "_bit_exact_vs_oracle"] = (bool(np.array_equal(_bits(t.cpu()), want)),)
+            gathered = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(gathered, t)
+            identical = all(torch.equal(gathered[0], gi) for gi in gathered)
+            levels = {torch.quint8: 255, torch.quint4x2: 15, torch.quint2x4: 3}[qdt]
+            step = 2.0 * world / levels
+            err = (t.double() - exact).abs().max().item()
+            # every input is rounded once (<= step/2 each, at the input's own scale 2/levels), the sum once more
+            bound = (0.5 if rmode == "nearest" else 1.0) * ((world - 1) * 2.0 / levels + step) + (0.05 * world if tdt == torch.bfloat16 else 1e-5)
+            res[key] = (identical, err <= bound)
         for tdt, qdt, transport, rmode, lanes in ((torch.float32, torch.quint8, "nccl", "nearest", 1), (torch.bfloat16, torch.quint8, "nccl", "nearest", 1),
                                                   (torch.float32, torch.quint4x2, "nccl", "nearest", 1), (torch.float32, torch.quint8, "p2p", "nearest", 1),
                                                   (torch.bfloat16, torch.quint4x2, "p2p", "nearest", 1), (torch.float32, torch.quint8, "p2p", "nearest", 1),
@@ -127,6 +152,34 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
 def _bits(t):
     import torch
     return t.contiguous().view(torch.uint8).numpy().copy()
+
+
+def _direct_on_the_oracle(orc, pd, inputs, qdt):
+    """What quantized_all_reduce_(algorithm="direct") computes, restated with the CPU oracle: chunk c is owned by rank c;
+    every other rank quantizes ITS chunk c with that chunk's own parameters, the owner adds the dequantized chunks to its
+    float chunk in rank order (dequantize with the ADD store op), quantizes the sums once and EVERY rank takes the
+    dequantized values of those packed bytes."""
+    import torch
+    world = len(inputs)
+    is_bf16 = inputs[0].dtype == torch.bfloat16
+    fdt = orc.BF16 if is_bf16 else orc.F32
+    odt = {torch.quint8: orc.UINT8, torch.quint4x2: orc.UINT4, torch.quint2x4: orc.UINT2}[qdt]
+    host = [(i.view(torch.int16).numpy().view(np.uint16).copy() if is_bf16 else i.numpy().copy()) for i in inputs]
+    n = host[0].size
+    out = np.empty_like(host[0])
+    for c in range(world):
+        b, e = pd.shard_bounds(n, world, c)
+        if e == b:
+            continue
+        acc = host[c][b:e].copy()
+        for r in range(world):
+            if r == c:
+                continue
+            s, z = orc.compute_quant_params(host[r][b:e], odt)
+            acc = orc.dequantize(orc.quantize(host[r][b:e], odt, s, z), odt, e - b, fdt, s, z, orc.ADD, out=acc)
+        s, z = orc.compute_quant_params(acc, odt)
+        out[b:e] = orc.dequantize(orc.quantize(acc, odt, s, z), odt, e - b, fdt, s, z, orc.SET)
+    return out.view(np.uint8)
 
 
 def _ring_on_the_oracle(orc, pd, inputs, qdt, lanes=1):

@@ -26,13 +26,14 @@ def main() -> None:
     ap.add_argument("--numel", type=int, default=1_000_000_000)
     ap.add_argument("--launches", type=int, default=2)
     ap.add_argument("--cells", default="bf16u2n,bf16u2s,bf16u4s,bf16u4n,requant_bf16")
+    ap.add_argument("--variant", type=int, default=1, help="1 = direct LDG.256 kernels, 2 = TMA ring kernels")
     a = ap.parse_args()
     n = a.numel
     torch.cuda.set_device(0)
     ctx = piquant.Context()
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.set_stochastic_threshold(0.37)
-    ctx.set_kernel_variant(1)
+    ctx.set_kernel_variant(a.variant)
     g = torch.Generator(device="cuda").manual_seed(0)
     xf = torch.empty(n, dtype=torch.float32, device="cuda").uniform_(-1, 1, generator=g)
     xb = xf.to(torch.bfloat16)
