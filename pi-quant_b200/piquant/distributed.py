@@ -136,7 +136,7 @@ def _side_stream(device: torch.device, lane: int) -> "torch.cuda.Stream":
 
 def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.quint8, group: Optional[dist.ProcessGroup] = None,
                           ctx: Context = Context.get(), transport: str = "nccl", round_mode: str = "nearest", lanes: int = 1,
-                          algorithm: str = "ring") -> torch.Tensor:
+                          algorithm: str = "ring", copy_streams: int = 2) -> torch.Tensor:
     """In-place SUM all-reduce of a contiguous CUDA float32 / bfloat16 tensor with quantized transport.
 
     ``algorithm="direct"`` (needs peer memory; see ``_direct_all_reduce``) is the NVSwitch-native form: every chunk
@@ -182,7 +182,7 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
     if algorithm == "direct":
         if transport == "nccl":
             raise ValueError("algorithm='direct' moves the chunks with copy engines through peer memory; transport must be 'p2p' or 'auto'")
-        return _direct_all_reduce(tensor, dtype, group, ctx, rmode)
+        return _direct_all_reduce(tensor, dtype, group, ctx, rmode, lanes, copy_streams)
     fdt, qdt = torch_to_piquant_dtype(tensor.dtype), torch_to_piquant_dtype(dtype)
     meta = Context.META_BYTES
     device = tensor.device.index
@@ -324,98 +324,135 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
 _COPY_STREAMS: dict = {}
 
 
-def _copy_streams(device: torch.device, n: int):
-    key = device.index
-    have = _COPY_STREAMS.setdefault(key, [])
+def _copy_streams(device: torch.device, lane: int, n: int):
+    have = _COPY_STREAMS.setdefault((device.index, lane), [])
     while len(have) < n:
         have.append(torch.cuda.Stream(device=device))
     return have[:n]
 
 
-def _direct_all_reduce(tensor: torch.Tensor, dtype: torch.dtype, group, ctx: Context, rmode: RoundMode, copy_streams: int = 3) -> torch.Tensor:
+def _direct_all_reduce(tensor: torch.Tensor, dtype: torch.dtype, group, ctx: Context, rmode: RoundMode, lanes: int = 1,
+                       copy_streams: int = 2) -> torch.Tensor:
     """Quantized all-reduce as two all-to-all exchanges over NVSwitch (every GPU reaches every peer at full link rate).
 
     Chunk c of the tensor (``shard_bounds``) is owned by rank c.
 
     1. scatter-reduce: for every other rank j, ONE launch computes min/max + parameters of my chunk j, one launch quantizes
        it into a local staging slot ``[64-byte parameter block | packed payload]``, and a COPY ENGINE moves the slot into
-       rank j's receive slot number ``rank`` (``piquant_cuda_copy_on_stream`` on side streams): the SMs go on with chunk
-       j + 1 while chunk j is on the wire, so the phase costs what the link costs.
-    2. one stream-ordered barrier; then ONE kernel folds the world-1 received slots into my own float chunk in rank
-       order -- exactly world-1 successive dequantize(ADD) calls, in one pass -- and produces the parameters of the sums
+       rank j's receive slot number ``rank`` and raises rank j's flag for it (``piquant_cuda_copy_on_stream`` + a
+       symmetric-memory signal on a side stream): the SMs go on with chunk j + 1 while chunk j is on the wire.
+    2. once the world-1 flags are up, ONE kernel folds the received slots into my own float chunk in rank order --
+       exactly world-1 successive dequantize(ADD) calls, in one pass -- and produces the parameters of the sums
        (``piquant_cuda_dequantize_sum_minmax_on_stream``); the sums are quantized once and copy engines broadcast
-       ``[parameters | packed sums]`` to every peer's gather slot number ``rank`` while this rank dequantizes its own copy.
-    3. one barrier; every rank dequantizes the world-1 gathered slots (SET).  Owners dequantize the same bytes they sent,
-       so all ranks end with bit-identical values.
+       ``[parameters | packed sums]`` to every peer's gather slot number ``rank`` (+ flag) while this rank dequantizes its own.
+    3. every rank dequantizes (SET) each gathered slot as soon as its flag is up, in the order the slots arrive.  Owners
+       dequantize the same bytes they sent, so all ranks end with bit-identical values.
 
-    Every element is quantized twice whatever the world size (the ring quantizes the running sum at every hop), there
-    are 3 barriers instead of 2 * (world - 1), and nothing synchronises with the host."""
+    Every element is quantized twice whatever the world size (the ring quantizes the running sum at every hop), one
+    barrier per call (nobody may still be reading the slots of the previous call) instead of 2 * (world - 1), and
+    nothing synchronises with the host.
+
+    ``lanes``: the tensor is cut into that many contiguous parts, each an independent all-reduce with its own slots,
+    flags and streams, enqueued alternately.  A lane alternates between link-bound stretches (the two exchanges) and
+    HBM-bound ones (reduce, dequantize); with two lanes one lane's kernels run while the other's payload is on the wire."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     fdt, qdt = torch_to_piquant_dtype(tensor.dtype), torch_to_piquant_dtype(dtype)
     meta = Context.META_BYTES
     dev = tensor.device
     device = dev.index
     LOCAL, REVERSE = Context.FLAG_LOCAL, Context.FLAG_REVERSE
-    flat = tensor.view(-1)
-    bounds = [shard_bounds(flat.numel(), world, i) for i in range(world)]
-    qbytes = [qdt.storage_bytes(e - b) for b, e in bounds]
-    slot_bytes = (meta + max(qbytes) + 255) // 256 * 256
-    main = torch.cuda.current_stream(dev)
-    st = main.cuda_stream
-    sides = _copy_streams(dev, max(1, min(copy_streams, world - 1)))
-    # symmetric memory: [world scatter-reduce slots | world gather slots]; slot k of the first half receives from rank k,
-    # slot k of the second half holds the reduced chunk k
-    local, hdl = _p2p_slots(world * slot_bytes, dev, group, lane=-2)       # (2 * nbytes are allocated: two halves)
-    my_base = local.data_ptr()
-    peer_base = [int(hdl.buffer_ptrs[i]) for i in range(world)]
-    rs_off = lambda k: k * slot_bytes                                      # noqa: E731
-    ag_off = lambda k: (world + k) * slot_bytes                            # noqa: E731
-    stage = torch.empty((world - 1) * slot_bytes, dtype=torch.uint8, device=dev)
+    CH_BARRIER, CH_SCATTER, CH_GATHER = 0, 1, 2             # signal-pad channels
+    others = [(rank + d) % world for d in range(1, world)]  # staggered: at any moment every rank receives from one sender
+    arrivals = [(rank - d) % world for d in range(1, world)]   # ... so this is the order in which slots arrive here
 
-    def chunk(i):
-        b, e = bounds[i]
-        return flat[b:e]
+    def lane_steps(flat, lane, main):
+        """generator: enqueues one all-reduce of `flat` on stream `main` (+ its copy streams), yielding between chunks"""
+        st = main.cuda_stream
+        bounds = [shard_bounds(flat.numel(), world, i) for i in range(world)]
+        qbytes = [qdt.storage_bytes(e - b) for b, e in bounds]
+        slot_bytes = (meta + max(qbytes) + 255) // 256 * 256
+        sides = _copy_streams(dev, lane, max(1, min(copy_streams, world - 1)))
+        # symmetric memory: [world scatter-reduce slots | world gather slots]; slot k of the first half receives from
+        # rank k, slot k of the second half holds the reduced chunk k
+        local, hdl = _p2p_slots(world * slot_bytes, dev, group, lane=-2 - lane)       # (allocates 2 * nbytes: the two halves)
+        my_base = local.data_ptr()
+        peer_base = [int(hdl.buffer_ptrs[i]) for i in range(world)]
+        rs_off = lambda k: k * slot_bytes                                      # noqa: E731
+        ag_off = lambda k: (world + k) * slot_bytes                            # noqa: E731
+        stage = torch.empty((world - 1) * slot_bytes, dtype=torch.uint8, device=dev)
+        stage.record_stream(main)
 
-    def send(src_ptr, dst_ptr, nbytes, k):
-        ev = torch.cuda.Event()
-        ev.record(main)
-        side = sides[k % len(sides)]
-        side.wait_event(ev)
-        ctx.copy_on_stream(dst_ptr, src_ptr, nbytes, device, side.cuda_stream)
+        def chunk(i):
+            b, e = bounds[i]
+            return flat[b:e]
 
-    def join_sides():
-        for side in sides:
+        def send(src_ptr, dst_rank, dst_off, nbytes, k, channel):
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side = sides[k % len(sides)]
+            side.wait_event(ev)
+            ctx.copy_on_stream(peer_base[dst_rank] + dst_off, src_ptr, nbytes, device, side.cuda_stream)
+            with torch.cuda.stream(side):
+                hdl.put_signal(dst_rank, channel)          # stream-ordered after the copy: the slot is complete when the flag is up
+
+        with torch.cuda.stream(main):
+            hdl.barrier(channel=CH_BARRIER)                # nobody still reads the slots of a previous call
+        for k, j in enumerate(others):
+            c = chunk(j)
+            if c.numel():
+                base = stage.data_ptr() + k * slot_bytes
+                ctx.compute_meta_on_stream(c.data_ptr(), fdt, c.numel(), qdt, base, LOCAL, device, st)
+                ctx.quantize_meta_on_stream(c.data_ptr(), fdt, base + meta, qdt, c.numel(), rmode, base, REVERSE, device, st)
+                send(base, j, rs_off(rank), meta + qbytes[j], k, CH_SCATTER)
+            yield
+        mine = chunk(rank)
+        own_slot = my_base + ag_off(rank)
+        if mine.numel():
+            with torch.cuda.stream(main):
+                for k in arrivals:
+                    hdl.wait_signal(k, CH_SCATTER)         # my scatter-reduce slots are complete
+            srcs = [my_base + rs_off(k) for k in range(world) if k != rank]
+            for g in range(0, len(srcs), Context.MAX_SUM_SOURCES):       # one launch up to 9 ranks; the last launch's parameters are the sums'
+                part = srcs[g:g + Context.MAX_SUM_SOURCES]
+                ctx.dequantize_sum_minmax_on_stream([p + meta for p in part], qdt, mine.data_ptr(), fdt, mine.numel(), part, qdt, own_slot, 0,
+                                                    device, st)
+            ctx.quantize_meta_on_stream(mine.data_ptr(), fdt, own_slot + meta, qdt, mine.numel(), rmode, own_slot, REVERSE, device, st)
+            yield
+            for k, j in enumerate(others):
+                send(own_slot, j, ag_off(rank), meta + qbytes[rank], k, CH_GATHER)
+            # the owner takes the dequantized values of exactly the bytes everybody else receives
+            ctx.dequantize_meta_on_stream(own_slot + meta, qdt, mine.data_ptr(), fdt, mine.numel(), ReduceOp.SET, own_slot, device, st)
+        yield
+        for j in arrivals:
+            c = chunk(j)
+            if c.numel():
+                src = my_base + ag_off(j)
+                with torch.cuda.stream(main):
+                    hdl.wait_signal(j, CH_GATHER)          # gather slot j is complete
+                ctx.dequantize_meta_on_stream(src + meta, qdt, c.data_ptr(), fdt, c.numel(), ReduceOp.SET, src, device, st)
+            yield
+        for side in sides:                                 # the staging slots and my gather slot are free again
             main.wait_stream(side)
 
-    hdl.barrier(channel=0)                                   # nobody still reads the slots of a previous call
-    others = [(rank + d) % world for d in range(1, world)]   # staggered: at any moment every rank receives from one sender
-    for k, j in enumerate(others):
-        c = chunk(j)
-        if not c.numel():
-            continue
-        base = stage.data_ptr() + k * slot_bytes
-        ctx.compute_meta_on_stream(c.data_ptr(), fdt, c.numel(), qdt, base, LOCAL, device, st)
-        ctx.quantize_meta_on_stream(c.data_ptr(), fdt, base + meta, qdt, c.numel(), rmode, base, REVERSE, device, st)
-        send(base, peer_base[j] + rs_off(rank), meta + qbytes[j], k)
-    join_sides()
-    hdl.barrier(channel=0)                                   # my scatter-reduce slots are complete
-    mine = chunk(rank)
-    own_slot = my_base + ag_off(rank)
-    if mine.numel():
-        srcs = [my_base + rs_off(k) for k in range(world) if k != rank]
-        for g in range(0, len(srcs), Context.MAX_SUM_SOURCES):       # one launch up to 9 ranks; the last launch's parameters are the sums'
-            part = srcs[g:g + Context.MAX_SUM_SOURCES]
-            ctx.dequantize_sum_minmax_on_stream([p + meta for p in part], qdt, mine.data_ptr(), fdt, mine.numel(), part, qdt, own_slot, 0, device, st)
-        ctx.quantize_meta_on_stream(mine.data_ptr(), fdt, own_slot + meta, qdt, mine.numel(), rmode, own_slot, REVERSE, device, st)
-        for k, j in enumerate(others):
-            send(own_slot, peer_base[j] + ag_off(rank), meta + qbytes[rank], k)
-        # the owner takes the dequantized values of exactly the bytes everybody else receives
-        ctx.dequantize_meta_on_stream(own_slot + meta, qdt, mine.data_ptr(), fdt, mine.numel(), ReduceOp.SET, own_slot, device, st)
-    join_sides()
-    hdl.barrier(channel=0)                                   # my gather slots are complete
-    for j in others:
-        c = chunk(j)
-        if c.numel():
-            src = my_base + ag_off(j)
-            ctx.dequantize_meta_on_stream(src + meta, qdt, c.data_ptr(), fdt, c.numel(), ReduceOp.SET, src, device, st)
+    flat = tensor.view(-1)
+    main = torch.cuda.current_stream(dev)
+    lanes = max(1, int(lanes))
+    if lanes == 1 or flat.numel() < lanes * world * SHARD_ALIGN:
+        for _ in lane_steps(flat, 0, main):
+            pass
+        return tensor
+    per = flat.numel() // lanes // SHARD_ALIGN * SHARD_ALIGN
+    parts = [flat[i * per: (i + 1) * per if i < lanes - 1 else flat.numel()] for i in range(lanes)]
+    streams = [main] + [_side_stream(dev, i) for i in range(1, lanes)]
+    for stream in streams[1:]:
+        stream.wait_stream(main)
+    gens = [lane_steps(part, i, stream) for i, (part, stream) in enumerate(zip(parts, streams))]
+    while gens:
+        for g in list(gens):
+            try:
+                next(g)
+            except StopIteration:
+                gens.remove(g)
+    for stream in streams[1:]:
+        main.wait_stream(stream)
     return tensor

@@ -90,20 +90,22 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
         pd.destroy_native_comm(ctx)
         # quantized ring all-reduce: every rank ends with bit-identical values, close to the exact sum
         # the NVSwitch form: two all-to-all exchanges, ONE multi-source reduce kernel; replayed on the CPU with the oracle
-        for tdt, qdt, rmode, numel in ((torch.float32, torch.quint8, "nearest", 1_000_003), (torch.bfloat16, torch.quint8, "nearest", 1_000_003),
-                                       (torch.float32, torch.quint4x2, "nearest", 300_007), (torch.bfloat16, torch.quint2x4, "nearest", 70_001),
-                                       (torch.float32, torch.quint8, "nearest", 100), (torch.float32, torch.quint8, "nearest", 4_194_304),
-                                       (torch.float32, torch.quint8, "stochastic_per_element", 1_000_003)):
+        for tdt, qdt, rmode, numel, lanes in ((torch.float32, torch.quint8, "nearest", 1_000_003, 1), (torch.bfloat16, torch.quint8, "nearest", 1_000_003, 1),
+                                              (torch.float32, torch.quint4x2, "nearest", 300_007, 1), (torch.bfloat16, torch.quint2x4, "nearest", 70_001, 1),
+                                              (torch.float32, torch.quint8, "nearest", 100, 1), (torch.float32, torch.quint8, "nearest", 4_194_304, 1),
+                                              (torch.float32, torch.quint8, "nearest", 1_000_003, 2), (torch.bfloat16, torch.quint4x2, "nearest", 1_000_003, 3),
+                                              (torch.float32, torch.quint8, "nearest", 200, 2),
+                                              (torch.float32, torch.quint8, "stochastic_per_element", 1_000_003, 2)):
             g = torch.Generator(device="cuda").manual_seed(500 + rank)
             t = (torch.rand(numel, device="cuda", generator=g) * 2 - 1).to(tdt)
             exact = t.double().clone()
             dist.all_reduce(exact)
             inputs = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(inputs, t)
-            pd.quantized_all_reduce_(t, dtype=qdt, ctx=ctx, transport="p2p", round_mode=rmode, algorithm="direct")
-            key = f"direct_{tdt}_{qdt}_{rmode}_{numel}"
+            pd.quantized_all_reduce_(t, dtype=qdt, ctx=ctx, transport="p2p", round_mode=rmode, algorithm="direct", lanes=lanes)
+            key = f"direct_{tdt}_{qdt}_{rmode}_{numel}_lanes{lanes}"
             if rmode == "nearest":
-                want = _direct_on_the_oracle(orc, pd, [i.cpu() for i in inputs], qdt)
+                want = _direct_on_the_oracle(orc, pd, [i.cpu() for i in inputs], qdt, lanes)
                 res[key + "_bit_exact_vs_oracle"] = (bool(np.array_equal(_bits(t.cpu()), want)),)
             gathered = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(gathered, t)
@@ -154,11 +156,11 @@ def _bits(t):
     return t.contiguous().view(torch.uint8).numpy().copy()
 
 
-def _direct_on_the_oracle(orc, pd, inputs, qdt):
+def _direct_on_the_oracle(orc, pd, inputs, qdt, lanes=1):
     """What quantized_all_reduce_(algorithm="direct") computes, restated with the CPU oracle: chunk c is owned by rank c;
     every other rank quantizes ITS chunk c with that chunk's own parameters, the owner adds the dequantized chunks to its
     float chunk in rank order (dequantize with the ADD store op), quantizes the sums once and EVERY rank takes the
-    dequantized values of those packed bytes."""
+    dequantized values of those packed bytes.  Every lane is an independent all-reduce of its contiguous part."""
     import torch
     world = len(inputs)
     is_bf16 = inputs[0].dtype == torch.bfloat16
@@ -167,18 +169,24 @@ def _direct_on_the_oracle(orc, pd, inputs, qdt):
     host = [(i.view(torch.int16).numpy().view(np.uint16).copy() if is_bf16 else i.numpy().copy()) for i in inputs]
     n = host[0].size
     out = np.empty_like(host[0])
-    for c in range(world):
-        b, e = pd.shard_bounds(n, world, c)
-        if e == b:
-            continue
-        acc = host[c][b:e].copy()
-        for r in range(world):
-            if r == c:
+    if n < lanes * world * pd.SHARD_ALIGN:
+        lanes = 1
+    per = n // lanes // pd.SHARD_ALIGN * pd.SHARD_ALIGN
+    for lane in range(lanes):
+        p0, p1 = lane * per, ((lane + 1) * per if lane < lanes - 1 else n)
+        for c in range(world):
+            b, e = pd.shard_bounds(p1 - p0, world, c)
+            b, e = b + p0, e + p0
+            if e == b:
                 continue
-            s, z = orc.compute_quant_params(host[r][b:e], odt)
-            acc = orc.dequantize(orc.quantize(host[r][b:e], odt, s, z), odt, e - b, fdt, s, z, orc.ADD, out=acc)
-        s, z = orc.compute_quant_params(acc, odt)
-        out[b:e] = orc.dequantize(orc.quantize(acc, odt, s, z), odt, e - b, fdt, s, z, orc.SET)
+            acc = host[c][b:e].copy()
+            for r in range(world):
+                if r == c:
+                    continue
+                s, z = orc.compute_quant_params(host[r][b:e], odt)
+                acc = orc.dequantize(orc.quantize(host[r][b:e], odt, s, z), odt, e - b, fdt, s, z, orc.ADD, out=acc)
+            s, z = orc.compute_quant_params(acc, odt)
+            out[b:e] = orc.dequantize(orc.quantize(acc, odt, s, z), odt, e - b, fdt, s, z, orc.SET)
     return out.view(np.uint8)
 
 

@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Quantized all-reduce variants next to NCCL's f32 all-reduce (torchrun --nproc-per-node N tools/allreduce_probe.py [log2 numel]).
+CUDA events, max over ranks; development tool -- the judged numbers come from bench.py's quantized_ring_all_reduce leg."""
+from __future__ import annotations
+
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (str(ROOT), str(ROOT / "pi-quant_b200")):
+    sys.path.insert(0, p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import piquant  # noqa: E402
+from piquant import distributed as pd  # noqa: E402
+
+
+def main() -> None:
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ctx = piquant.Context()
+    sizes = [int(a) for a in sys.argv[1:]] or [28]
+    for lg in sizes:
+        n = 1 << lg
+        base = torch.empty(n, dtype=torch.float32, device=dev).uniform_(-1, 1)
+        work = torch.empty_like(base)
+
+        def timed(fn, reps=8):
+            for _ in range(3):
+                work.copy_(base)
+                fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            tot = 0.0
+            for _ in range(reps):
+                work.copy_(base)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            t = torch.tensor([tot / reps], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        rows = [("nccl f32 all_reduce", timed(lambda: dist.all_reduce(work)))]
+        exact = work.clone()
+        for name, kw in (("ring p2p, 2 lanes", dict(transport="p2p", lanes=2)),
+                         ("direct, 1 lane, 1 copy stream", dict(transport="p2p", algorithm="direct", copy_streams=1)),
+                         ("direct, 1 lane, 2 copy streams", dict(transport="p2p", algorithm="direct", copy_streams=2)),
+                         ("direct, 2 lanes, 1 copy stream", dict(transport="p2p", algorithm="direct", lanes=2, copy_streams=1)),
+                         ("direct, 2 lanes, 2 copy streams", dict(transport="p2p", algorithm="direct", lanes=2, copy_streams=2)),
+                         ("direct, 3 lanes, 2 copy streams", dict(transport="p2p", algorithm="direct", lanes=3, copy_streams=2)),
+                         ("direct, 4 lanes, 1 copy stream", dict(transport="p2p", algorithm="direct", lanes=4, copy_streams=1)),
+                         ("direct u4, 2 lanes, 2 copy streams", dict(transport="p2p", algorithm="direct", lanes=2, copy_streams=2, dtype=torch.quint4x2))):
+            kw = dict(kw)
+            qd = kw.pop("dtype", torch.quint8)
+            ms = timed(lambda: pd.quantized_all_reduce_(work, dtype=qd, ctx=ctx, **kw))
+            err = (work - exact).abs().max()
+            dist.all_reduce(err, op=dist.ReduceOp.MAX)
+            rows.append((name, ms, float(err.item())))
+        if rank == 0:
+            print(f"numel = 2^{lg} f32 ({4 * n / 1e6:.0f} MB), {world} GPUs")
+            for r in rows:
+                extra = f"   {rows[0][1] / r[1]:5.2f}x nccl   max_abs_err {r[2]:.4f}" if len(r) > 2 else ""
+                print(f"  {r[0]:32s} {r[1] * 1e3:9.1f} us{extra}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
