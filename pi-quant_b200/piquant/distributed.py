@@ -91,7 +91,8 @@ def destroy_native_comm(ctx: Context = Context.get()) -> None:
 
 
 __all__ = ["SHARD_ALIGN", "shard_bounds", "combine_minmax", "local_neg_min_max", "compute_quant_params_sharded",
-           "params_from_minmax", "init_native_comm", "destroy_native_comm", "ring_schedule", "quantized_all_reduce_", "DataType"]
+           "params_from_minmax", "init_native_comm", "destroy_native_comm", "ring_schedule", "quantized_all_reduce_", "QuantizedAllReduce",
+           "DataType"]
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -331,8 +332,7 @@ def _copy_streams(device: torch.device, lane: int, n: int):
     return have[:n]
 
 
-def _direct_all_reduce(tensor: torch.Tensor, dtype: torch.dtype, group, ctx: Context, rmode: RoundMode, lanes: int = 1,
-                       copy_streams: int = 2) -> torch.Tensor:
+class _DirectPlan:
     """Quantized all-reduce as two all-to-all exchanges over NVSwitch (every GPU reaches every peer at full link rate).
 
     Chunk c of the tensor (``shard_bounds``) is owned by rank c.
@@ -355,32 +355,48 @@ def _direct_all_reduce(tensor: torch.Tensor, dtype: torch.dtype, group, ctx: Con
     ``lanes``: the tensor is cut into that many contiguous parts, each an independent all-reduce with its own slots,
     flags and streams, enqueued alternately.  A lane alternates between link-bound stretches (the two exchanges) and
     HBM-bound ones (reduce, dequantize); with two lanes one lane's kernels run while the other's payload is on the wire."""
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    fdt, qdt = torch_to_piquant_dtype(tensor.dtype), torch_to_piquant_dtype(dtype)
-    meta = Context.META_BYTES
-    dev = tensor.device
-    device = dev.index
-    LOCAL, REVERSE = Context.FLAG_LOCAL, Context.FLAG_REVERSE
-    CH_BARRIER, CH_SCATTER, CH_GATHER = 0, 1, 2             # signal-pad channels
-    others = [(rank + d) % world for d in range(1, world)]  # staggered: at any moment every rank receives from one sender
-    arrivals = [(rank - d) % world for d in range(1, world)]   # ... so this is the order in which slots arrive here
 
-    def lane_steps(flat, lane, main):
+    CH_BARRIER, CH_SCATTER, CH_GATHER = 0, 1, 2             # signal-pad channels
+
+    def __init__(self, numel: int, float_dtype: torch.dtype, dtype: torch.dtype, device: torch.device, group, ctx: Context, rmode: RoundMode,
+                 lanes: int = 1, copy_streams: int = 2):
+        """Everything that allocates or rendezvouses happens here, so that ``enqueue`` only launches (it may run inside a
+        CUDA graph capture)."""
+        self.group, self.ctx, self.rmode, self.dev, self.numel, self.float_dtype = group, ctx, rmode, device, numel, float_dtype
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.fdt, self.qdt = torch_to_piquant_dtype(float_dtype), torch_to_piquant_dtype(dtype)
+        world, rank, meta = self.world, self.rank, Context.META_BYTES
+        self.others = [(rank + d) % world for d in range(1, world)]     # staggered: at any moment every rank receives from one sender
+        self.arrivals = [(rank - d) % world for d in range(1, world)]   # ... so this is the order in which slots arrive here
+        lanes = max(1, int(lanes))
+        if numel < lanes * world * SHARD_ALIGN:
+            lanes = 1
+        per = numel // lanes // SHARD_ALIGN * SHARD_ALIGN
+        self.parts = [(i * per, (i + 1) * per if i < lanes - 1 else numel) for i in range(lanes)]
+        self.lane_streams = [None] + [_side_stream(device, i) for i in range(1, lanes)]       # lane 0 runs on the caller's stream
+        self.lanes = []
+        for lane, (p0, p1) in enumerate(self.parts):
+            bounds = [shard_bounds(p1 - p0, world, i) for i in range(world)]
+            qbytes = [self.qdt.storage_bytes(e - b) for b, e in bounds]
+            slot_bytes = (meta + max(qbytes) + 255) // 256 * 256
+            # symmetric memory: [world scatter-reduce slots | world gather slots]; slot k of the first half receives from
+            # rank k, slot k of the second half holds the reduced chunk k
+            local, hdl = _p2p_slots(world * slot_bytes, device, group, lane=-2 - lane)       # (allocates 2 * nbytes: the two halves)
+            self.lanes.append(dict(bounds=bounds, qbytes=qbytes, slot_bytes=slot_bytes, local=local, hdl=hdl,
+                                   peer_base=[int(hdl.buffer_ptrs[i]) for i in range(world)],
+                                   stage=torch.empty((world - 1) * slot_bytes, dtype=torch.uint8, device=device),
+                                   sides=_copy_streams(device, lane, max(1, min(copy_streams, world - 1)))))
+
+    def _lane_steps(self, flat: torch.Tensor, lane: int, main: "torch.cuda.Stream"):
         """generator: enqueues one all-reduce of `flat` on stream `main` (+ its copy streams), yielding between chunks"""
-        st = main.cuda_stream
-        bounds = [shard_bounds(flat.numel(), world, i) for i in range(world)]
-        qbytes = [qdt.storage_bytes(e - b) for b, e in bounds]
-        slot_bytes = (meta + max(qbytes) + 255) // 256 * 256
-        sides = _copy_streams(dev, lane, max(1, min(copy_streams, world - 1)))
-        # symmetric memory: [world scatter-reduce slots | world gather slots]; slot k of the first half receives from
-        # rank k, slot k of the second half holds the reduced chunk k
-        local, hdl = _p2p_slots(world * slot_bytes, dev, group, lane=-2 - lane)       # (allocates 2 * nbytes: the two halves)
-        my_base = local.data_ptr()
-        peer_base = [int(hdl.buffer_ptrs[i]) for i in range(world)]
+        L = self.lanes[lane]
+        ctx, world, rank, fdt, qdt, rmode = self.ctx, self.world, self.rank, self.fdt, self.qdt, self.rmode
+        meta, device, st = Context.META_BYTES, self.dev.index, main.cuda_stream
+        LOCAL, REVERSE = Context.FLAG_LOCAL, Context.FLAG_REVERSE
+        bounds, qbytes, slot_bytes, hdl, peer_base, sides = L["bounds"], L["qbytes"], L["slot_bytes"], L["hdl"], L["peer_base"], L["sides"]
+        my_base, stage = L["local"].data_ptr(), L["stage"].data_ptr()
         rs_off = lambda k: k * slot_bytes                                      # noqa: E731
         ag_off = lambda k: (world + k) * slot_bytes                            # noqa: E731
-        stage = torch.empty((world - 1) * slot_bytes, dtype=torch.uint8, device=dev)
-        stage.record_stream(main)
 
         def chunk(i):
             b, e = bounds[i]
@@ -396,21 +412,21 @@ def _direct_all_reduce(tensor: torch.Tensor, dtype: torch.dtype, group, ctx: Con
                 hdl.put_signal(dst_rank, channel)          # stream-ordered after the copy: the slot is complete when the flag is up
 
         with torch.cuda.stream(main):
-            hdl.barrier(channel=CH_BARRIER)                # nobody still reads the slots of a previous call
-        for k, j in enumerate(others):
+            hdl.barrier(channel=self.CH_BARRIER)           # nobody still reads the slots of a previous call
+        for k, j in enumerate(self.others):
             c = chunk(j)
             if c.numel():
-                base = stage.data_ptr() + k * slot_bytes
+                base = stage + k * slot_bytes
                 ctx.compute_meta_on_stream(c.data_ptr(), fdt, c.numel(), qdt, base, LOCAL, device, st)
                 ctx.quantize_meta_on_stream(c.data_ptr(), fdt, base + meta, qdt, c.numel(), rmode, base, REVERSE, device, st)
-                send(base, j, rs_off(rank), meta + qbytes[j], k, CH_SCATTER)
+                send(base, j, rs_off(rank), meta + qbytes[j], k, self.CH_SCATTER)
             yield
         mine = chunk(rank)
         own_slot = my_base + ag_off(rank)
         if mine.numel():
             with torch.cuda.stream(main):
-                for k in arrivals:
-                    hdl.wait_signal(k, CH_SCATTER)         # my scatter-reduce slots are complete
+                for k in self.arrivals:
+                    hdl.wait_signal(k, self.CH_SCATTER)    # my scatter-reduce slots are complete
             srcs = [my_base + rs_off(k) for k in range(world) if k != rank]
             for g in range(0, len(srcs), Context.MAX_SUM_SOURCES):       # one launch up to 9 ranks; the last launch's parameters are the sums'
                 part = srcs[g:g + Context.MAX_SUM_SOURCES]
@@ -418,41 +434,87 @@ def _direct_all_reduce(tensor: torch.Tensor, dtype: torch.dtype, group, ctx: Con
                                                     device, st)
             ctx.quantize_meta_on_stream(mine.data_ptr(), fdt, own_slot + meta, qdt, mine.numel(), rmode, own_slot, REVERSE, device, st)
             yield
-            for k, j in enumerate(others):
-                send(own_slot, j, ag_off(rank), meta + qbytes[rank], k, CH_GATHER)
+            for k, j in enumerate(self.others):
+                send(own_slot, j, ag_off(rank), meta + qbytes[rank], k, self.CH_GATHER)
             # the owner takes the dequantized values of exactly the bytes everybody else receives
             ctx.dequantize_meta_on_stream(own_slot + meta, qdt, mine.data_ptr(), fdt, mine.numel(), ReduceOp.SET, own_slot, device, st)
         yield
-        for j in arrivals:
+        for j in self.arrivals:
             c = chunk(j)
             if c.numel():
                 src = my_base + ag_off(j)
                 with torch.cuda.stream(main):
-                    hdl.wait_signal(j, CH_GATHER)          # gather slot j is complete
+                    hdl.wait_signal(j, self.CH_GATHER)     # gather slot j is complete
                 ctx.dequantize_meta_on_stream(src + meta, qdt, c.data_ptr(), fdt, c.numel(), ReduceOp.SET, src, device, st)
             yield
         for side in sides:                                 # the staging slots and my gather slot are free again
             main.wait_stream(side)
 
-    flat = tensor.view(-1)
-    main = torch.cuda.current_stream(dev)
-    lanes = max(1, int(lanes))
-    if lanes == 1 or flat.numel() < lanes * world * SHARD_ALIGN:
-        for _ in lane_steps(flat, 0, main):
-            pass
+    def enqueue(self, tensor: torch.Tensor) -> torch.Tensor:
+        """Launch the collective on the current stream (and the plan's side streams); no allocation, no synchronisation."""
+        assert tensor.is_cuda and tensor.is_contiguous() and tensor.numel() == self.numel and tensor.dtype == self.float_dtype
+        assert tensor.device == self.dev
+        flat = tensor.view(-1)
+        main = torch.cuda.current_stream(self.dev)
+        streams = [main] + self.lane_streams[1:]
+        for stream in streams[1:]:
+            stream.wait_stream(main)
+        gens = [self._lane_steps(flat[p0:p1], i, stream) for i, ((p0, p1), stream) in enumerate(zip(self.parts, streams))]
+        while gens:                                        # the lanes' chunks are enqueued alternately
+            for g in list(gens):
+                try:
+                    next(g)
+                except StopIteration:
+                    gens.remove(g)
+        for stream in streams[1:]:
+            main.wait_stream(stream)
         return tensor
-    per = flat.numel() // lanes // SHARD_ALIGN * SHARD_ALIGN
-    parts = [flat[i * per: (i + 1) * per if i < lanes - 1 else flat.numel()] for i in range(lanes)]
-    streams = [main] + [_side_stream(dev, i) for i in range(1, lanes)]
-    for stream in streams[1:]:
-        stream.wait_stream(main)
-    gens = [lane_steps(part, i, stream) for i, (part, stream) in enumerate(zip(parts, streams))]
-    while gens:
-        for g in list(gens):
-            try:
-                next(g)
-            except StopIteration:
-                gens.remove(g)
-    for stream in streams[1:]:
-        main.wait_stream(stream)
-    return tensor
+
+
+_DIRECT_PLANS: dict = {}
+
+
+def _direct_all_reduce(tensor: torch.Tensor, dtype: torch.dtype, group, ctx: Context, rmode: RoundMode, lanes: int = 1,
+                       copy_streams: int = 2) -> torch.Tensor:
+    grp = group if group is not None else dist.group.WORLD
+    key = (grp.group_name, tensor.device.index, tensor.numel(), tensor.dtype, dtype, id(ctx), rmode, lanes, copy_streams)
+    plan = _DIRECT_PLANS.get(key)
+    if plan is None:
+        plan = _DIRECT_PLANS[key] = _DirectPlan(tensor.numel(), tensor.dtype, dtype, tensor.device, group, ctx, rmode, lanes, copy_streams)
+    return plan.enqueue(tensor)
+
+
+class QuantizedAllReduce:
+    """The direct quantized all-reduce of ONE persistent tensor (a gradient bucket), captured into a CUDA graph.
+
+    The collective is ~75 launches, copies and flag operations per lane; enqueued from Python they cost more host time than
+    the GPU needs for tensors below ~1 GB.  Captured once, ``plan()`` replays the whole exchange -- kernels, copy-engine
+    transfers into peer memory, flags -- with one graph launch on the current stream.  Every rank must construct and call
+    the object in the same order (construction is a collective: symmetric-memory rendezvous).  Nearest rounding only: a
+    captured launch would replay the same random stream."""
+
+    def __init__(self, tensor: torch.Tensor, *, dtype: torch.dtype = torch.quint8, group: Optional[dist.ProcessGroup] = None,
+                 ctx: Context = Context.get(), lanes: int = 2, copy_streams: int = 2):
+        assert tensor.is_cuda and tensor.is_contiguous() and tensor.dtype in (torch.float32, torch.bfloat16)
+        assert dtype in _QUANT_TYPES
+        self.tensor = tensor
+        self.world = dist.get_world_size(group)
+        if self.world == 1:
+            self.graph = None
+            return
+        self.plan = _DirectPlan(tensor.numel(), tensor.dtype, dtype, tensor.device, group, ctx, RoundMode.NEAREST, lanes, copy_streams)
+        ctx.kernel_launches                                  # (touches the library: its per-device state exists before the capture)
+        warm = torch.zeros(SHARD_ALIGN * self.world, dtype=tensor.dtype, device=tensor.device)
+        meta = torch.zeros(Context.META_BYTES, dtype=torch.uint8, device=tensor.device)
+        device, stream = _site(warm)
+        ctx.compute_meta_on_stream(warm.data_ptr(), torch_to_piquant_dtype(tensor.dtype), warm.numel(), torch_to_piquant_dtype(dtype),
+                                   meta.data_ptr(), Context.FLAG_LOCAL, device, stream)
+        torch.cuda.synchronize(tensor.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self.plan.enqueue(tensor)
+
+    def __call__(self) -> torch.Tensor:
+        if self.graph is not None:
+            self.graph.replay()
+        return self.tensor

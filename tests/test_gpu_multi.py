@@ -116,6 +116,18 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
             # every input is rounded once (<= step/2 each, at the input's own scale 2/levels), the sum once more
             bound = (0.5 if rmode == "nearest" else 1.0) * ((world - 1) * 2.0 / levels + step) + (0.05 * world if tdt == torch.bfloat16 else 1e-5)
             res[key] = (identical, err <= bound)
+        # the same collective captured into a CUDA graph for a persistent tensor, replayed with new contents
+        for tdt, qdt, numel, lanes in ((torch.float32, torch.quint8, 1_000_003, 2), (torch.bfloat16, torch.quint4x2, 300_007, 1)):
+            t = torch.zeros(numel, device="cuda", dtype=tdt)
+            plan = pd.QuantizedAllReduce(t, dtype=qdt, ctx=ctx, lanes=lanes)
+            for rep in range(3):
+                g = torch.Generator(device="cuda").manual_seed(900 + 10 * rep + rank)
+                t.copy_((torch.rand(numel, device="cuda", generator=g) * 2 - 1).to(tdt))
+                inputs = [torch.empty_like(t) for _ in range(world)]
+                dist.all_gather(inputs, t)
+                plan()
+                want = _direct_on_the_oracle(orc, pd, [i.cpu() for i in inputs], qdt, lanes)
+                res[f"graph_replay_{tdt}_{qdt}_{rep}"] = (bool(np.array_equal(_bits(t.cpu()), want)),)
         for tdt, qdt, transport, rmode, lanes in ((torch.float32, torch.quint8, "nccl", "nearest", 1), (torch.bfloat16, torch.quint8, "nccl", "nearest", 1),
                                                   (torch.float32, torch.quint4x2, "nccl", "nearest", 1), (torch.float32, torch.quint8, "p2p", "nearest", 1),
                                                   (torch.bfloat16, torch.quint4x2, "p2p", "nearest", 1), (torch.float32, torch.quint8, "p2p", "nearest", 1),

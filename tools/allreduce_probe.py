@@ -56,20 +56,26 @@ def main() -> None:
                          ("direct, 1 lane, 2 copy streams", dict(transport="p2p", algorithm="direct", copy_streams=2)),
                          ("direct, 2 lanes, 1 copy stream", dict(transport="p2p", algorithm="direct", lanes=2, copy_streams=1)),
                          ("direct, 2 lanes, 2 copy streams", dict(transport="p2p", algorithm="direct", lanes=2, copy_streams=2)),
-                         ("direct, 3 lanes, 2 copy streams", dict(transport="p2p", algorithm="direct", lanes=3, copy_streams=2)),
-                         ("direct, 4 lanes, 1 copy stream", dict(transport="p2p", algorithm="direct", lanes=4, copy_streams=1)),
-                         ("direct u4, 2 lanes, 2 copy streams", dict(transport="p2p", algorithm="direct", lanes=2, copy_streams=2, dtype=torch.quint4x2))):
+                         ):
             kw = dict(kw)
             qd = kw.pop("dtype", torch.quint8)
             ms = timed(lambda: pd.quantized_all_reduce_(work, dtype=qd, ctx=ctx, **kw))
             err = (work - exact).abs().max()
             dist.all_reduce(err, op=dist.ReduceOp.MAX)
             rows.append((name, ms, float(err.item())))
+        for lanes in (1, 2, 3, 4):
+            for cs in (1, 2):
+                plan = pd.QuantizedAllReduce(work, dtype=torch.quint8, ctx=ctx, lanes=lanes, copy_streams=cs)
+                ms = timed(plan)
+                err = (work - exact).abs().max()
+                dist.all_reduce(err, op=dist.ReduceOp.MAX)
+                rows.append((f"direct CUDA GRAPH, {lanes} lanes, {cs} copy streams", ms, float(err.item())))
+                del plan
         if rank == 0:
             print(f"numel = 2^{lg} f32 ({4 * n / 1e6:.0f} MB), {world} GPUs")
             for r in rows:
                 extra = f"   {rows[0][1] / r[1]:5.2f}x nccl   max_abs_err {r[2]:.4f}" if len(r) > 2 else ""
-                print(f"  {r[0]:32s} {r[1] * 1e3:9.1f} us{extra}", flush=True)
+                print(f"  {r[0]:48s} {r[1] * 1e3:9.1f} us{extra}", flush=True)
     dist.destroy_process_group()
 
 
