@@ -137,7 +137,7 @@ def _side_stream(device: torch.device, lane: int) -> "torch.cuda.Stream":
 
 def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.quint8, group: Optional[dist.ProcessGroup] = None,
                           ctx: Context = Context.get(), transport: str = "nccl", round_mode: str = "nearest", lanes: int = 1,
-                          algorithm: str = "ring", copy_streams: int = 2) -> torch.Tensor:
+                          algorithm: str = "ring") -> torch.Tensor:
     """In-place SUM all-reduce of a contiguous CUDA float32 / bfloat16 tensor with quantized transport.
 
     ``algorithm="direct"`` (needs peer memory; see ``_direct_all_reduce``) is the NVSwitch-native form: every chunk
@@ -183,7 +183,7 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
     if algorithm == "direct":
         if transport == "nccl":
             raise ValueError("algorithm='direct' moves the chunks with copy engines through peer memory; transport must be 'p2p' or 'auto'")
-        return _direct_all_reduce(tensor, dtype, group, ctx, rmode, lanes, copy_streams)
+        return _direct_all_reduce(tensor, dtype, group, ctx, rmode, lanes)
     fdt, qdt = torch_to_piquant_dtype(tensor.dtype), torch_to_piquant_dtype(dtype)
     meta = Context.META_BYTES
     device = tensor.device.index
@@ -326,6 +326,7 @@ _COPY_STREAMS: dict = {}
 
 
 def _copy_streams(device: torch.device, lane: int, n: int):
+    """streams that carry nothing but copy-engine transfers"""
     have = _COPY_STREAMS.setdefault((device.index, lane), [])
     while len(have) < n:
         have.append(torch.cuda.Stream(device=device))
@@ -337,32 +338,36 @@ class _DirectPlan:
 
     Chunk c of the tensor (``shard_bounds``) is owned by rank c.
 
-    1. scatter-reduce: for every other rank j, ONE launch computes min/max + parameters of my chunk j, one launch quantizes
-       it into a local staging slot ``[64-byte parameter block | packed payload]``, and a COPY ENGINE moves the slot into
-       rank j's receive slot number ``rank`` and raises rank j's flag for it (``piquant_cuda_copy_on_stream`` + a
-       symmetric-memory signal on a side stream): the SMs go on with chunk j + 1 while chunk j is on the wire.
-    2. once the world-1 flags are up, ONE kernel folds the received slots into my own float chunk in rank order --
-       exactly world-1 successive dequantize(ADD) calls, in one pass -- and produces the parameters of the sums
-       (``piquant_cuda_dequantize_sum_minmax_on_stream``); the sums are quantized once and copy engines broadcast
+    1. scatter: for every other rank j, ONE launch computes min/max + parameters of my chunk j, one launch quantizes it
+       into a local staging slot ``[64-byte parameter block | packed payload]``, and a COPY ENGINE moves the slot into rank
+       j's receive slot number ``rank`` and then writes rank j's arrival flag for it -- two ``cudaMemcpyAsync`` on the
+       plan's copy stream (``piquant_cuda_copy_on_stream``), no kernel: the SMs go on with chunk j + 1 while chunk j is on
+       the wire, and the copies follow each other without a gap (measured on 8 B200s: one copy in flight per GPU moves
+       568 GB/s out of every GPU at once, two or more in flight 450-510 GB/s -- profiles/r2_allreduce_probe_n8.txt).
+    2. reduce: once the world-1 flags are up, ONE kernel folds the received slots into my own float chunk in rank order
+       -- exactly world-1 successive dequantize(ADD) calls, in one pass -- and produces the parameters of the sums
+       (``piquant_cuda_dequantize_sum_minmax_on_stream``); the sums are quantized once and the copy engine broadcasts
        ``[parameters | packed sums]`` to every peer's gather slot number ``rank`` (+ flag) while this rank dequantizes its own.
-    3. every rank dequantizes (SET) each gathered slot as soon as its flag is up, in the order the slots arrive.  Owners
-       dequantize the same bytes they sent, so all ranks end with bit-identical values.
+    3. gather: every rank dequantizes (SET) each gathered slot as soon as its flag is up, in the order the slots arrive.
+       Owners dequantize the same bytes they sent, so all ranks end with bit-identical values.
 
     Every element is quantized twice whatever the world size (the ring quantizes the running sum at every hop), one
     barrier per call (nobody may still be reading the slots of the previous call) instead of 2 * (world - 1), and
     nothing synchronises with the host.
 
-    ``lanes``: the tensor is cut into that many contiguous parts, each an independent all-reduce with its own slots,
-    flags and streams, enqueued alternately.  A lane alternates between link-bound stretches (the two exchanges) and
-    HBM-bound ones (reduce, dequantize); with two lanes one lane's kernels run while the other's payload is on the wire."""
+    ``lanes``: the tensor is cut into that many contiguous parts, each an independent all-reduce with its own slots and
+    flags, run STAGGERED on the same two streams: scatter A, scatter B, reduce A, reduce B, gather A, gather B.  The
+    copy stream is a FIFO, so the link carries B's scatter while the SMs reduce A, and A's broadcast while they reduce
+    B: the link -- the bound of this collective -- never waits for a kernel except at the very start."""
 
-    CH_BARRIER, CH_SCATTER, CH_GATHER = 0, 1, 2             # signal-pad channels
+    CH_BARRIER, CH_SCATTER, CH_GATHER = 0, 1, 2             # signal-pad channels (torch symmetric memory: one u32 per channel and rank)
 
     def __init__(self, numel: int, float_dtype: torch.dtype, dtype: torch.dtype, device: torch.device, group, ctx: Context, rmode: RoundMode,
-                 lanes: int = 1, copy_streams: int = 2):
+                 lanes: int = 1):
         """Everything that allocates or rendezvouses happens here, so that ``enqueue`` only launches (it may run inside a
         CUDA graph capture)."""
         self.group, self.ctx, self.rmode, self.dev, self.numel, self.float_dtype = group, ctx, rmode, device, numel, float_dtype
+        self.trace = None                                   # a list: CUDA events at the phase boundaries of the next enqueue (tools/allreduce_probe.py)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.fdt, self.qdt = torch_to_piquant_dtype(float_dtype), torch_to_piquant_dtype(dtype)
         world, rank, meta = self.world, self.rank, Context.META_BYTES
@@ -373,27 +378,29 @@ class _DirectPlan:
             lanes = 1
         per = numel // lanes // SHARD_ALIGN * SHARD_ALIGN
         self.parts = [(i * per, (i + 1) * per if i < lanes - 1 else numel) for i in range(lanes)]
-        self.lane_streams = [None] + [_side_stream(device, i) for i in range(1, lanes)]       # lane 0 runs on the caller's stream
+        self.copy_stream = _copy_streams(device, 0, 1)[0]
+        self.one = torch.ones(1, dtype=torch.int32, device=device)      # what a raised flag holds
         self.lanes = []
         for lane, (p0, p1) in enumerate(self.parts):
             bounds = [shard_bounds(p1 - p0, world, i) for i in range(world)]
             qbytes = [self.qdt.storage_bytes(e - b) for b, e in bounds]
             slot_bytes = (meta + max(qbytes) + 255) // 256 * 256
-            # symmetric memory: [world scatter-reduce slots | world gather slots]; slot k of the first half receives from
+            # symmetric memory: [world scatter slots | world gather slots]; slot k of the first half receives from
             # rank k, slot k of the second half holds the reduced chunk k
             local, hdl = _p2p_slots(world * slot_bytes, device, group, lane=-2 - lane)       # (allocates 2 * nbytes: the two halves)
             self.lanes.append(dict(bounds=bounds, qbytes=qbytes, slot_bytes=slot_bytes, local=local, hdl=hdl,
                                    peer_base=[int(hdl.buffer_ptrs[i]) for i in range(world)],
-                                   stage=torch.empty((world - 1) * slot_bytes, dtype=torch.uint8, device=device),
-                                   sides=_copy_streams(device, lane, max(1, min(copy_streams, world - 1)))))
+                                   peer_pad=[int(hdl.signal_pad_ptrs[i]) for i in range(world)],
+                                   stage=torch.empty((world - 1) * slot_bytes, dtype=torch.uint8, device=device)))
+        torch.cuda.synchronize(device)
 
-    def _lane_steps(self, flat: torch.Tensor, lane: int, main: "torch.cuda.Stream"):
-        """generator: enqueues one all-reduce of `flat` on stream `main` (+ its copy streams), yielding between chunks"""
+    def _lane_phases(self, flat: torch.Tensor, lane: int, main: "torch.cuda.Stream"):
+        """generator: enqueues one all-reduce of `flat` on `main` and the copy stream, yielding between its three phases"""
         L = self.lanes[lane]
         ctx, world, rank, fdt, qdt, rmode = self.ctx, self.world, self.rank, self.fdt, self.qdt, self.rmode
-        meta, device, st = Context.META_BYTES, self.dev.index, main.cuda_stream
+        meta, device, st, side = Context.META_BYTES, self.dev.index, main.cuda_stream, self.copy_stream
         LOCAL, REVERSE = Context.FLAG_LOCAL, Context.FLAG_REVERSE
-        bounds, qbytes, slot_bytes, hdl, peer_base, sides = L["bounds"], L["qbytes"], L["slot_bytes"], L["hdl"], L["peer_base"], L["sides"]
+        bounds, qbytes, slot_bytes, hdl, peer_base, peer_pad = L["bounds"], L["qbytes"], L["slot_bytes"], L["hdl"], L["peer_base"], L["peer_pad"]
         my_base, stage = L["local"].data_ptr(), L["stage"].data_ptr()
         rs_off = lambda k: k * slot_bytes                                      # noqa: E731
         ag_off = lambda k: (world + k) * slot_bytes                            # noqa: E731
@@ -402,40 +409,51 @@ class _DirectPlan:
             b, e = bounds[i]
             return flat[b:e]
 
-        def send(src_ptr, dst_rank, dst_off, nbytes, k, channel):
+        def send(src_ptr, dst_rank, dst_off, nbytes, channel):
+            """copy engine: payload, then the arrival flag (stream order = arrival order; flag word [channel][rank] of dst's pad)"""
+            ctx.copy_on_stream(peer_base[dst_rank] + dst_off, src_ptr, nbytes, device, side.cuda_stream)
+            ctx.copy_on_stream(peer_pad[dst_rank] + 4 * (world * channel + rank), self.one.data_ptr(), 4, device, side.cuda_stream)
+
+        def copies_follow_main():
             ev = torch.cuda.Event()
             ev.record(main)
-            side = sides[k % len(sides)]
             side.wait_event(ev)
-            ctx.copy_on_stream(peer_base[dst_rank] + dst_off, src_ptr, nbytes, device, side.cuda_stream)
-            with torch.cuda.stream(side):
-                hdl.put_signal(dst_rank, channel)          # stream-ordered after the copy: the slot is complete when the flag is up
 
-        with torch.cuda.stream(main):
-            hdl.barrier(channel=self.CH_BARRIER)           # nobody still reads the slots of a previous call
+        def mark(label):
+            if self.trace is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(main)
+                self.trace.append((lane, label, ev))
+
+        mark("start")
+        hdl.barrier(channel=self.CH_BARRIER)               # (current stream = main) nobody still reads the slots of a previous call
+        mark("barrier")
         for k, j in enumerate(self.others):
             c = chunk(j)
             if c.numel():
                 base = stage + k * slot_bytes
                 ctx.compute_meta_on_stream(c.data_ptr(), fdt, c.numel(), qdt, base, LOCAL, device, st)
                 ctx.quantize_meta_on_stream(c.data_ptr(), fdt, base + meta, qdt, c.numel(), rmode, base, REVERSE, device, st)
-                send(base, j, rs_off(rank), meta + qbytes[j], k, self.CH_SCATTER)
-            yield
+                copies_follow_main()
+                send(base, j, rs_off(rank), meta + qbytes[j], self.CH_SCATTER)
+                mark(f"quantized chunk {j}")
+        yield
         mine = chunk(rank)
         own_slot = my_base + ag_off(rank)
         if mine.numel():
-            with torch.cuda.stream(main):
-                for k in self.arrivals:
-                    hdl.wait_signal(k, self.CH_SCATTER)    # my scatter-reduce slots are complete
+            for k in self.arrivals:
+                hdl.wait_signal(k, self.CH_SCATTER)        # my scatter slots are complete (the kernel lowers the flag again)
+            mark("all scatter slots arrived")
             srcs = [my_base + rs_off(k) for k in range(world) if k != rank]
             for g in range(0, len(srcs), Context.MAX_SUM_SOURCES):       # one launch up to 9 ranks; the last launch's parameters are the sums'
                 part = srcs[g:g + Context.MAX_SUM_SOURCES]
                 ctx.dequantize_sum_minmax_on_stream([p + meta for p in part], qdt, mine.data_ptr(), fdt, mine.numel(), part, qdt, own_slot, 0,
                                                     device, st)
             ctx.quantize_meta_on_stream(mine.data_ptr(), fdt, own_slot + meta, qdt, mine.numel(), rmode, own_slot, REVERSE, device, st)
-            yield
-            for k, j in enumerate(self.others):
-                send(own_slot, j, ag_off(rank), meta + qbytes[rank], k, self.CH_GATHER)
+            mark("reduced + quantized own chunk")
+            copies_follow_main()
+            for j in self.others:
+                send(own_slot, j, ag_off(rank), meta + qbytes[rank], self.CH_GATHER)
             # the owner takes the dequantized values of exactly the bytes everybody else receives
             ctx.dequantize_meta_on_stream(own_slot + meta, qdt, mine.data_ptr(), fdt, mine.numel(), ReduceOp.SET, own_slot, device, st)
         yield
@@ -443,44 +461,41 @@ class _DirectPlan:
             c = chunk(j)
             if c.numel():
                 src = my_base + ag_off(j)
-                with torch.cuda.stream(main):
-                    hdl.wait_signal(j, self.CH_GATHER)     # gather slot j is complete
+                hdl.wait_signal(j, self.CH_GATHER)         # gather slot j is complete
                 ctx.dequantize_meta_on_stream(src + meta, qdt, c.data_ptr(), fdt, c.numel(), ReduceOp.SET, src, device, st)
-            yield
-        for side in sides:                                 # the staging slots and my gather slot are free again
-            main.wait_stream(side)
+                mark(f"dequantized chunk {j}")
 
     def enqueue(self, tensor: torch.Tensor) -> torch.Tensor:
-        """Launch the collective on the current stream (and the plan's side streams); no allocation, no synchronisation."""
+        """Launch the collective on the current stream (and the plan's copy stream); no allocation, no synchronisation."""
         assert tensor.is_cuda and tensor.is_contiguous() and tensor.numel() == self.numel and tensor.dtype == self.float_dtype
         assert tensor.device == self.dev
         flat = tensor.view(-1)
         main = torch.cuda.current_stream(self.dev)
-        streams = [main] + self.lane_streams[1:]
-        for stream in streams[1:]:
-            stream.wait_stream(main)
-        gens = [self._lane_steps(flat[p0:p1], i, stream) for i, ((p0, p1), stream) in enumerate(zip(self.parts, streams))]
-        while gens:                                        # the lanes' chunks are enqueued alternately
+        self.copy_stream.wait_stream(main)                 # (a capture needs the fork; eagerly: staging slots of the previous call are free)
+        gens = [self._lane_phases(flat[p0:p1], i, main) for i, (p0, p1) in enumerate(self.parts)]
+        while gens:                                        # phase by phase, lane after lane: scatter A, scatter B, reduce A, ...
             for g in list(gens):
                 try:
                     next(g)
                 except StopIteration:
                     gens.remove(g)
-        for stream in streams[1:]:
-            main.wait_stream(stream)
+        main.wait_stream(self.copy_stream)                 # the staging slots and my gather slots are free again
+        if self.trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(main)
+            self.trace.append((0, "copy stream joined", ev))
         return tensor
 
 
 _DIRECT_PLANS: dict = {}
 
 
-def _direct_all_reduce(tensor: torch.Tensor, dtype: torch.dtype, group, ctx: Context, rmode: RoundMode, lanes: int = 1,
-                       copy_streams: int = 2) -> torch.Tensor:
+def _direct_all_reduce(tensor: torch.Tensor, dtype: torch.dtype, group, ctx: Context, rmode: RoundMode, lanes: int = 1) -> torch.Tensor:
     grp = group if group is not None else dist.group.WORLD
-    key = (grp.group_name, tensor.device.index, tensor.numel(), tensor.dtype, dtype, id(ctx), rmode, lanes, copy_streams)
+    key = (grp.group_name, tensor.device.index, tensor.numel(), tensor.dtype, dtype, id(ctx), rmode, lanes)
     plan = _DIRECT_PLANS.get(key)
     if plan is None:
-        plan = _DIRECT_PLANS[key] = _DirectPlan(tensor.numel(), tensor.dtype, dtype, tensor.device, group, ctx, rmode, lanes, copy_streams)
+        plan = _DIRECT_PLANS[key] = _DirectPlan(tensor.numel(), tensor.dtype, dtype, tensor.device, group, ctx, rmode, lanes)
     return plan.enqueue(tensor)
 
 
@@ -494,7 +509,7 @@ class QuantizedAllReduce:
     captured launch would replay the same random stream."""
 
     def __init__(self, tensor: torch.Tensor, *, dtype: torch.dtype = torch.quint8, group: Optional[dist.ProcessGroup] = None,
-                 ctx: Context = Context.get(), lanes: int = 2, copy_streams: int = 2):
+                 ctx: Context = Context.get(), lanes: int = 2):
         assert tensor.is_cuda and tensor.is_contiguous() and tensor.dtype in (torch.float32, torch.bfloat16)
         assert dtype in _QUANT_TYPES
         self.tensor = tensor
@@ -502,7 +517,7 @@ class QuantizedAllReduce:
         if self.world == 1:
             self.graph = None
             return
-        self.plan = _DirectPlan(tensor.numel(), tensor.dtype, dtype, tensor.device, group, ctx, RoundMode.NEAREST, lanes, copy_streams)
+        self.plan = _DirectPlan(tensor.numel(), tensor.dtype, dtype, tensor.device, group, ctx, RoundMode.NEAREST, lanes)
         ctx.kernel_launches                                  # (touches the library: its per-device state exists before the capture)
         warm = torch.zeros(SHARD_ALIGN * self.world, dtype=tensor.dtype, device=tensor.device)
         meta = torch.zeros(Context.META_BYTES, dtype=torch.uint8, device=tensor.device)

@@ -52,10 +52,9 @@ def main() -> None:
         rows = [("nccl f32 all_reduce", timed(lambda: dist.all_reduce(work)))]
         exact = work.clone()
         for name, kw in (("ring p2p, 2 lanes", dict(transport="p2p", lanes=2)),
-                         ("direct, 1 lane, 1 copy stream", dict(transport="p2p", algorithm="direct", copy_streams=1)),
-                         ("direct, 1 lane, 2 copy streams", dict(transport="p2p", algorithm="direct", copy_streams=2)),
-                         ("direct, 2 lanes, 1 copy stream", dict(transport="p2p", algorithm="direct", lanes=2, copy_streams=1)),
-                         ("direct, 2 lanes, 2 copy streams", dict(transport="p2p", algorithm="direct", lanes=2, copy_streams=2)),
+                         ("direct, 1 lane", dict(transport="p2p", algorithm="direct")),
+                         ("direct, 2 staggered lanes", dict(transport="p2p", algorithm="direct", lanes=2)),
+                         ("direct u4, 1 lane", dict(transport="p2p", algorithm="direct", dtype=torch.quint4x2)),
                          ):
             kw = dict(kw)
             qd = kw.pop("dtype", torch.quint8)
@@ -63,13 +62,54 @@ def main() -> None:
             err = (work - exact).abs().max()
             dist.all_reduce(err, op=dist.ReduceOp.MAX)
             rows.append((name, ms, float(err.item())))
+        # where the time goes: CUDA events at the phase boundaries of one eager call (rank 0's view)
+        plan = pd._DirectPlan(n, torch.float32, torch.quint8, dev, None, ctx, piquant.RoundMode.NEAREST, 1)
+        for rep in range(3):
+            work.copy_(base)
+            torch.cuda.synchronize()
+            dist.barrier()
+            plan.trace = [] if rep == 2 else None
+            plan.enqueue(work)
+            torch.cuda.synchronize()
+        if rank == 0:
+            t0 = plan.trace[0][2]
+            print("  timeline of one eager direct all-reduce (1 lane), us since start, rank 0:")
+            for lane, label, ev in plan.trace:
+                print(f"    {t0.elapsed_time(ev) * 1e3:9.1f}  {label}")
+        # what the links give: every rank copies a packed chunk to `fan` different peers at once, one stream per peer
+        import torch.distributed._symmetric_memory as symm_mem
+        nb = n // world
+        buf = symm_mem.empty(world * nb, dtype=torch.uint8, device=dev)
+        hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+        src = torch.empty(nb, dtype=torch.uint8, device=dev)
+        streams = [torch.cuda.Stream() for _ in range(world - 1)]
+        for fan in (1, 2, 3, 4, 7):
+            if fan > world - 1:
+                continue
+            def burst():
+                cur = torch.cuda.current_stream()
+                for k in range(world - 1):
+                    st = streams[k % fan]
+                    if k < fan:
+                        st.wait_stream(cur)
+                    peer = (rank + 1 + k) % world
+                    ctx.copy_on_stream(int(hdl.buffer_ptrs[peer]) + rank * nb, src.data_ptr(), nb, local, st.cuda_stream)
+                for st in streams[:fan]:
+                    cur.wait_stream(st)
+            ms = timed(burst, reps=5)
+            if rank == 0:
+                print(f"  link probe: {world - 1} copies of {nb / 1e6:.1f} MB to {world - 1} peers, {fan} in flight: {ms * 1e3:8.1f} us  "
+                      f"= {(world - 1) * nb / ms / 1e6:7.1f} GB/s out per GPU (every GPU sending and receiving)")
+        del buf, hdl
         for lanes in (1, 2, 3, 4):
-            for cs in (1, 2):
-                plan = pd.QuantizedAllReduce(work, dtype=torch.quint8, ctx=ctx, lanes=lanes, copy_streams=cs)
+            for qd, qn in ((torch.quint8, "u8"), (torch.quint4x2, "u4")):
+                if qn == "u4" and lanes not in (1, 2):
+                    continue
+                plan = pd.QuantizedAllReduce(work, dtype=qd, ctx=ctx, lanes=lanes)
                 ms = timed(plan)
                 err = (work - exact).abs().max()
                 dist.all_reduce(err, op=dist.ReduceOp.MAX)
-                rows.append((f"direct CUDA GRAPH, {lanes} lanes, {cs} copy streams", ms, float(err.item())))
+                rows.append((f"direct {qn} CUDA GRAPH, {lanes} staggered lanes", ms, float(err.item())))
                 del plan
         if rank == 0:
             print(f"numel = 2^{lg} f32 ({4 * n / 1e6:.0f} MB), {world} GPUs")
