@@ -785,17 +785,23 @@ def ring_allreduce_leg(torch, dist, ctx, world, rank, dev) -> dict:
     res = {"numel": n, "ms_nccl_f32": round(ms_nccl, 3)}
     bus = 2 * (world - 1) / world * n * 4 / 1e9
     res["nccl_busbw_GBps"] = round(bus / (ms_nccl * 1e-3), 1)
-    for key, kw in (("quantized_u8_nccl_sendrecv", dict(transport="nccl")), ("quantized_u8_p2p_fused", dict(transport="p2p")),
-                    ("quantized_u8_p2p_fused_2_lanes", dict(transport="p2p", lanes=2)),
-                    ("quantized_u8_p2p_fused_4_lanes", dict(transport="p2p", lanes=4)),
-                    ("quantized_u8_p2p_fused_2_lanes_stochastic_per_element", dict(transport="p2p", lanes=2, round_mode="stochastic_per_element")),
+    for key, kw in (("quantized_u8_ring_nccl_sendrecv", dict(transport="nccl", algorithm="ring")),
+                    ("quantized_u8_ring_p2p_fused_2_lanes", dict(transport="p2p", algorithm="ring", lanes=2)),
+                    ("quantized_u8_ring_p2p_fused_2_lanes_stochastic_per_element",
+                     dict(transport="p2p", algorithm="ring", lanes=2, round_mode="stochastic_per_element")),
                     ("quantized_u8_direct_all_to_all", dict(transport="p2p", algorithm="direct")),
                     ("quantized_u8_direct_all_to_all_stochastic_per_element", dict(transport="p2p", algorithm="direct", round_mode="stochastic_per_element")),
-                    ("quantized_u4_direct_all_to_all", dict(transport="p2p", algorithm="direct", qdtype="quint4x2"))):
+                    ("quantized_u8_direct_all_to_all_cuda_graph", dict(graph=True)),
+                    ("quantized_u4_direct_all_to_all_cuda_graph", dict(graph=True, qdtype="quint4x2"))):
         try:
             kw = dict(kw)
             qdtype = getattr(torch, kw.pop("qdtype", "quint8"))
-            ms = timed(lambda: pd.quantized_all_reduce_(work, dtype=qdtype, ctx=ctx, **kw))
+            if kw.pop("graph", False):
+                plan = pd.QuantizedAllReduce(work, dtype=qdtype, ctx=ctx)
+                ms = timed(plan)
+                del plan
+            else:
+                ms = timed(lambda: pd.quantized_all_reduce_(work, dtype=qdtype, ctx=ctx, **kw))
             mx, mean = error_stats(exact)
             res[key] = {"ms": round(ms, 3), "speedup_vs_nccl_f32": round(ms_nccl / ms, 3), "effective_busbw_GBps": round(bus / (ms * 1e-3), 1),
                         "max_abs_err": mx, "abs_mean_err": mean, "bit_identical_on_every_rank": identical_on_every_rank()}
@@ -806,7 +812,8 @@ def ring_allreduce_leg(torch, dist, ctx, world, rank, dev) -> dict:
                    "nothing is sent; abs_mean_err shows the bias nearest rounding accumulates per hop and per-element stochastic rounding does not; "
                    "direct_all_to_all = the NVSwitch form: quantize each chunk once, copy engines move it to its owner, ONE multi-source "
                    "dequantize-sum kernel reduces, the packed sums are broadcast by copy engines and dequantized: 2 quantizations per value "
-                   "whatever the world size, 3 barriers")
+                   "whatever the world size, 1 barrier + per-slot arrival flags written by the copy engine; cuda_graph = the same collective of a "
+                   "persistent tensor captured once (piquant.distributed.QuantizedAllReduce) and replayed")
     return res
 
 

@@ -142,7 +142,7 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
             dist.all_reduce(exact)
             inputs = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(inputs, t)
-            pd.quantized_all_reduce_(t, dtype=qdt, ctx=ctx, transport=transport, round_mode=rmode, lanes=lanes)
+            pd.quantized_all_reduce_(t, dtype=qdt, ctx=ctx, transport=transport, round_mode=rmode, lanes=lanes, algorithm="ring")
             if rmode == "nearest":
                 # the whole collective replayed on the CPU with the oracle, hop by hop: the GPU result must be bit-identical
                 want = _ring_on_the_oracle(orc, pd, [i.cpu() for i in inputs], qdt, lanes)
