@@ -807,6 +807,30 @@ def ring_allreduce_leg(torch, dist, ctx, world, rank, dev) -> dict:
                         "max_abs_err": mx, "abs_mean_err": mean, "bit_identical_on_every_rank": identical_on_every_rank()}
         except Exception as e:      # noqa: BLE001  (symmetric memory not available on this box)
             res[key] = f"unavailable: {type(e).__name__}: {str(e)[:120]}"
+    # parity in the same run: a 1 M-element all-reduce of every form replayed on the CPU with the oracle (oracle/replay.py), bit for bit
+    try:
+        import numpy as np
+        from oracle import port as orc, replay
+        m = 1_000_003
+        small = torch.empty(m, dtype=torch.float32, device=dev).uniform_(-1, 1, generator=gen)
+        gathered = [torch.empty_like(small) for _ in range(world)]
+        dist.all_gather(gathered, small)
+        host = [g.cpu().numpy() for g in gathered]
+        want = {"direct": replay.direct_all_reduce(host, orc.UINT8, orc.F32, pd.shard_bounds, pd.SHARD_ALIGN, 1),
+                "ring": replay.ring_all_reduce(host, orc.UINT8, orc.F32, pd.shard_bounds, pd.SHARD_ALIGN, 1)}
+        checks = {}
+        for name, run in (("direct", lambda t: pd.quantized_all_reduce_(t, dtype=torch.quint8, ctx=ctx, transport="p2p", algorithm="direct", lanes=1)),
+                          ("direct_cuda_graph", lambda t: pd.QuantizedAllReduce(t, dtype=torch.quint8, ctx=ctx, lanes=1)()),
+                          ("ring", lambda t: pd.quantized_all_reduce_(t, dtype=torch.quint8, ctx=ctx, transport="p2p", algorithm="ring", lanes=1))):
+            t = small.clone()
+            run(t)
+            ok = torch.tensor([int(np.array_equal(t.cpu().numpy().view(np.uint8), want[name.split("_")[0]]))], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            checks[name] = bool(ok.item())
+        res["parity_vs_oracle_replay"] = {"numel": m, "bit_exact_on_every_rank": checks,
+                                          "what": "GPU result vs the collective replayed with the CPU oracle's compute_quant_params/quantize/dequantize"}
+    except Exception as e:      # noqa: BLE001
+        res["parity_vs_oracle_replay"] = f"unavailable: {type(e).__name__}: {str(e)[:160]}"
     res["note"] = ("ring reduce-scatter + all-gather, [64 B params | u8 payload] per hop, no host sync; a reduce-scatter hop = quantize + ONE fused "
                    "dequantize-ADD/min-max/params kernel; p2p_fused = kernels store into / forward to the neighbour's slot over NVLink peer memory, "
                    "nothing is sent; abs_mean_err shows the bias nearest rounding accumulates per hop and per-element stochastic rounding does not; "

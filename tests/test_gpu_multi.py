@@ -168,68 +168,25 @@ def _bits(t):
     return t.contiguous().view(torch.uint8).numpy().copy()
 
 
-def _direct_on_the_oracle(orc, pd, inputs, qdt, lanes=1):
-    """What quantized_all_reduce_(algorithm="direct") computes, restated with the CPU oracle: chunk c is owned by rank c;
-    every other rank quantizes ITS chunk c with that chunk's own parameters, the owner adds the dequantized chunks to its
-    float chunk in rank order (dequantize with the ADD store op), quantizes the sums once and EVERY rank takes the
-    dequantized values of those packed bytes.  Every lane is an independent all-reduce of its contiguous part."""
+def _host_views(orc, inputs, qdt):
     import torch
-    world = len(inputs)
     is_bf16 = inputs[0].dtype == torch.bfloat16
-    fdt = orc.BF16 if is_bf16 else orc.F32
     odt = {torch.quint8: orc.UINT8, torch.quint4x2: orc.UINT4, torch.quint2x4: orc.UINT2}[qdt]
     host = [(i.view(torch.int16).numpy().view(np.uint16).copy() if is_bf16 else i.numpy().copy()) for i in inputs]
-    n = host[0].size
-    out = np.empty_like(host[0])
-    if n < lanes * world * pd.SHARD_ALIGN:
-        lanes = 1
-    per = n // lanes // pd.SHARD_ALIGN * pd.SHARD_ALIGN
-    for lane in range(lanes):
-        p0, p1 = lane * per, ((lane + 1) * per if lane < lanes - 1 else n)
-        for c in range(world):
-            b, e = pd.shard_bounds(p1 - p0, world, c)
-            b, e = b + p0, e + p0
-            if e == b:
-                continue
-            acc = host[c][b:e].copy()
-            for r in range(world):
-                if r == c:
-                    continue
-                s, z = orc.compute_quant_params(host[r][b:e], odt)
-                acc = orc.dequantize(orc.quantize(host[r][b:e], odt, s, z), odt, e - b, fdt, s, z, orc.ADD, out=acc)
-            s, z = orc.compute_quant_params(acc, odt)
-            out[b:e] = orc.dequantize(orc.quantize(acc, odt, s, z), odt, e - b, fdt, s, z, orc.SET)
-    return out.view(np.uint8)
+    return host, odt, (orc.BF16 if is_bf16 else orc.F32)
+
+
+def _direct_on_the_oracle(orc, pd, inputs, qdt, lanes=1):
+    """the collective replayed on the CPU with nothing but the oracle's three functions (oracle/replay.py)"""
+    from oracle import replay
+    host, odt, fdt = _host_views(orc, inputs, qdt)
+    return replay.direct_all_reduce(host, odt, fdt, pd.shard_bounds, pd.SHARD_ALIGN, lanes)
 
 
 def _ring_on_the_oracle(orc, pd, inputs, qdt, lanes=1):
-    """What quantized_all_reduce_ computes, restated with the CPU oracle: chunk c starts on rank c, is quantized with the
-    parameters of the running sum at every hop and accumulated with dequantize-ADD on the next rank; the rank that holds
-    the complete sum quantizes it once more and EVERY rank takes the dequantized values of those packed bytes."""
-    import torch
-    world = len(inputs)
-    odt = {torch.quint8: orc.UINT8, torch.quint4x2: orc.UINT4, torch.quint2x4: orc.UINT2}[qdt]
-    is_bf16 = inputs[0].dtype == torch.bfloat16
-    fdt = orc.BF16 if is_bf16 else orc.F32
-    host = [(i.view(torch.int16).numpy().view(np.uint16).copy() if is_bf16 else i.numpy().copy()) for i in inputs]
-    n = host[0].size
-    out = np.empty_like(host[0])
-    per = n // lanes // pd.SHARD_ALIGN * pd.SHARD_ALIGN           # every lane is an independent ring over its contiguous part
-    for lane in range(lanes):
-        p0, p1 = lane * per, ((lane + 1) * per if lane < lanes - 1 else n)
-        for c in range(world):
-            b, e = pd.shard_bounds(p1 - p0, world, c)
-            b, e = b + p0, e + p0
-            if e == b:
-                continue
-            acc = host[c][b:e].copy()
-            for k in range(1, world):
-                s, z = orc.compute_quant_params(acc, odt)
-                q = orc.quantize(acc, odt, s, z)
-                acc = orc.dequantize(q, odt, e - b, fdt, s, z, orc.ADD, out=host[(c + k) % world][b:e].copy())
-            s, z = orc.compute_quant_params(acc, odt)
-            out[b:e] = orc.dequantize(orc.quantize(acc, odt, s, z), odt, e - b, fdt, s, z, orc.SET)
-    return out.view(np.uint8)
+    from oracle import replay
+    host, odt, fdt = _host_views(orc, inputs, qdt)
+    return replay.ring_all_reduce(host, odt, fdt, pd.shard_bounds, pd.SHARD_ALIGN, lanes)
 
 
 def test_sharded_params_and_quantize_two_gpus():
