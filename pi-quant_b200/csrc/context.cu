@@ -383,7 +383,19 @@ struct Context {
             const unsigned hw = std::thread::hardware_concurrency();
             size_t want = num_threads ? num_threads : 1;
             if (hw && want > hw) want = hw;
-            if (want > 6) want = 6;             // a handful of streaming copies saturate a socket's memory channels
+            // Measured on a 16-core B200 host (tools/pageable_probe.py, profiles/r2_pageable_probe.txt): 1 / 2 / 4 / 6 / 8 / 12 / 16
+            // workers move 2.3 / 4.3 / 7.1 / 8.2 / 9.5 / 10.8 / 10.7 Gelem/s of f32 -> u8 (pinned buffers: 13.4), so up to 12 pay.
+            // A box usually runs one process per GPU: each takes its share of the cores, at least 2.
+            int n_dev = 1;
+            if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1) { cudaGetLastError(); n_dev = 1; }
+            size_t cap = hw ? hw / static_cast<unsigned>(n_dev) : 6;
+            if (cap < 2) cap = 2;
+            if (cap > 12) cap = 12;
+            if (const char* e = getenv("PIQUANT_COPY_THREADS")) {      // explicit override
+                const long v = strtol(e, nullptr, 10);
+                if (v >= 1 && v <= 256) cap = static_cast<size_t>(v);
+            }
+            if (want > cap) want = cap;
             copiers.reset(new CopyPool(static_cast<int>(want) - 1));     // the calling thread copies too
         });
         return *copiers;
