@@ -518,7 +518,8 @@ class QuantizedAllReduce:
     the GPU needs for tensors below ~1 GB.  Captured once, ``plan()`` replays the whole exchange -- kernels, copy-engine
     transfers into peer memory, flags -- with one graph launch on the current stream.  Every rank must construct and call
     the object in the same order (construction is a collective: symmetric-memory rendezvous).  Nearest rounding only: a
-    captured launch would replay the same random stream."""
+    captured launch would replay the same random stream.  Plans of equal size share their receive slots (the barrier at
+    the start of every call keeps successive calls apart): replay them on ONE stream, like any collective of a group."""
 
     def __init__(self, tensor: torch.Tensor, *, dtype: torch.dtype = torch.quint8, group: Optional[dist.ProcessGroup] = None,
                  ctx: Context = Context.get(), lanes: Optional[int] = None):
@@ -531,7 +532,7 @@ class QuantizedAllReduce:
             return
         lanes = lanes if lanes is not None else (2 if self.world == 2 else 1)
         self.plan = _DirectPlan(tensor.numel(), tensor.dtype, dtype, tensor.device, group, ctx, RoundMode.NEAREST, lanes)
-        ctx.kernel_launches                                  # (touches the library: its per-device state exists before the capture)
+        # one tiny eager call: the library's per-device state (slot table, two allocations) exists before the capture starts
         warm = torch.zeros(SHARD_ALIGN * self.world, dtype=tensor.dtype, device=tensor.device)
         meta = torch.zeros(Context.META_BYTES, dtype=torch.uint8, device=tensor.device)
         device, stream = _site(warm)
