@@ -459,7 +459,7 @@ def run_extra(torch, ctx, D, RoundMode, ReduceOp, x, q, scale, zp, dev) -> dict:
     torch.cuda.synchronize()
     t_total = (time.perf_counter() - t0) / 2000
     out["call_overhead_us_numel_4096"] = {"host_issue": round(t_issue * 1e6, 2), "throughput_back_to_back": round(t_total * 1e6, 2),
-                                         "note": "reference ABI (piquant_quantize): cffi call + pointer classification (2 driver queries) + cudaLaunchKernelEx (PDL)"}
+                                         "note": "reference ABI (piquant_quantize) FROM PYTHON: cffi call + pointer classification (2 driver queries) + cudaLaunchKernelEx (PDL); the same call from C costs 2.2 us, an empty <<<>>> launch 2.3 us (tools/call_overhead.cu, profiles/r2_call_overhead_c_abi.txt)"}
     # the same call with device and stream passed along (piquant_cuda_quantize_on_stream: what piquant.torch uses): no classification
     dev_i, st_i = dev.index, torch.cuda.current_stream().cuda_stream
     torch.cuda.synchronize()
@@ -702,6 +702,39 @@ def small_tensor_leg(torch, ctx, dev) -> dict:
                 t = time.perf_counter() - t0
                 row[label] = {"total_s": round(t, 5), "us_per_tensor": round(t / runs * 1e6, 2), "Gelem/s": round(runs * numel / t / 1e9, 1),
                               "GB/s": round(bpe * runs * numel / t / 1e9, 1)}
+            # the same batch with outputs allocated beforehand (the allocation of 1000 quantized torch tensors is most of the
+            # time above): wall clock of the call, and the device time of its launches between two CUDA events
+            outs = [torch.empty(t1.shape, dtype=tdt, device=dev) for _ in range(runs)]
+            args = dict(scales=[s_] * runs, zero_points=[z_] * runs, dtype=tdt, ctx=ctx, outs=outs)
+            pt.quantize_batch([t1] * runs, **args)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            pt.quantize_batch([t1] * runs, **args)
+            e1.record()
+            torch.cuda.synchronize()
+            t = time.perf_counter() - t0
+            dev_t = e0.elapsed_time(e1) * 1e-3
+            row["one_batch_preallocated_outputs"] = {"total_s": round(t, 5), "us_per_tensor": round(t / runs * 1e6, 2),
+                                                     "device_us_per_tensor": round(dev_t / runs * 1e6, 3),
+                                                     "device_GB/s": round(bpe * runs * numel / dev_t / 1e9, 1)}
+            if name == "quint8":
+                # ... and with 1000 DISTINCT input tensors (the recipe above reads one 4 MB tensor a thousand times: every CTA column
+                # of the batch hits the same L2 lines at once)
+                many = torch.rand(runs, numel, dtype=torch.float32, device=dev)
+                ins = [many[i] for i in range(runs)]
+                pt.quantize_batch(ins, **args)
+                torch.cuda.synchronize()
+                e0.record()
+                pt.quantize_batch(ins, **args)
+                e1.record()
+                torch.cuda.synchronize()
+                dev_t = e0.elapsed_time(e1) * 1e-3
+                row["one_batch_preallocated_outputs_distinct_inputs"] = {"device_us_per_tensor": round(dev_t / runs * 1e6, 3),
+                                                                         "device_GB/s": round(bpe * runs * numel / dev_t / 1e9, 1)}
+                del many, ins
+            del outs
             a, b = keep[0], pt.quantize(t1, scale=s_, zero_point=z_, dtype=tdt, ctx=ctx)
             row["batch_equals_per_call"] = bool(torch.equal(torch.empty(0, dtype=torch.uint8, device=dev).set_(a.untyped_storage()),
                                                             torch.empty(0, dtype=torch.uint8, device=dev).set_(b.untyped_storage())))
