@@ -67,7 +67,7 @@ __device__ __forceinline__ void dequant_stream_body(DequantArgs& a, [[maybe_unus
     [[maybe_unused]] float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
     [[maybe_unused]] uint32_t pmn = 0x7f807f80u, pmx = 0xff80ff80u;      // packed bf16x2 accumulators
 
-    if (const int64_t tile = blockIdx.x; tile < n_tiles) {      // one tile per CTA, hardware-scheduled (see quantize.cu)
+    auto do_tile = [&](const int64_t tile) {
         const int64_t first = tile * TILE + threadIdx.x;
         uint32_t wi[U][NWI];
         uint32_t wp[U][OP == OP_ADD ? NWO : 1];
@@ -116,6 +116,12 @@ __device__ __forceinline__ void dequant_stream_body(DequantArgs& a, [[maybe_unus
                 store_words<NWO, A32, FUSE == FUSE_MINMAX>(out + item * 64, wo);
             }
         }
+    };
+    if constexpr (FUSE == FUSE_MINMAX) {
+        // the ticketed tail is paid once per CTA: a few tiles per CTA by grid stride (launch_cell sizes the grid; reduce_sum.cu has the measurement)
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) do_tile(tile);
+    } else {
+        if (blockIdx.x < n_tiles) do_tile(blockIdx.x);         // one tile per CTA, hardware-scheduled (see quantize.cu)
     }
 
     if (blockIdx.x == gridDim.x - 1) {
@@ -241,11 +247,15 @@ static int launch_cell(const void* in, void* out, int64_t numel, const QuantPara
     // a fused epilogue rides on the vector kernel only; the caller splits the work when this returns 0
     if (fr.kind != FUSE_NONE) {
         if (!vec) return 0;
-        const int64_t grid = (a.n_items + tile - 1) / tile;
         DequantFuse f{};
         DequantFusedKernel fn = nullptr;
+        int64_t grid = (a.n_items + tile - 1) / tile;
         if constexpr (OP == OP_ADD) {
-            if (fr.kind != FUSE_MINMAX || grid > fr.scratch->max_blocks) return 0;
+            if (fr.kind != FUSE_MINMAX) return 0;
+            int64_t per_cta = grid / (static_cast<int64_t>(cfg.sm_count) * 4 * 2);      // 4 CTAs of 58 registers per SM
+            per_cta = per_cta < 1 ? 1 : (per_cta > 4 ? 4 : per_cta);
+            grid = (grid + per_cta - 1) / per_cta;
+            if (grid > fr.scratch->max_blocks) grid = fr.scratch->max_blocks;
             f.tail = make_reduce_tail(*fr.scratch, *fr.reduce);
             fn = a32 ? dequant_fused_kernel<BITS, OUT_DT, OP_ADD, true, FUSE_MINMAX> : dequant_fused_kernel<BITS, OUT_DT, OP_ADD, false, FUSE_MINMAX>;
         } else {

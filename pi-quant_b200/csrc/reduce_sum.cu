@@ -30,17 +30,20 @@ struct SumArgs {
     ReduceTail         tail;
 };
 
-template <int BITS, int OUT_DT, bool A32>
-__global__ void __launch_bounds__(kThreads, 2) dequant_sum_kernel(const SumArgs a) {
+// CTAs per SM the register allocation aims at: 64 registers (4 CTAs) hold an f32 accumulator item + 8 packed items without
+// spilling; the bf16 cells carry twice the packed words per item (80 registers, 3 CTAs; 8-bit sources 128 registers, 2 CTAs).
+constexpr int sum_min_blocks(int bits, int out_dt) { return out_dt == DT_F32 ? 4 : (bits == 8 ? 2 : 3); }
+
+template <int BITS, int OUT_DT, bool A32, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) dequant_sum_kernel(const SumArgs a) {
     constexpr int PER = 8 / BITS;
     constexpr int V = OUT_DT == DT_F32 ? 16 : 32;       // elements per item (64 accumulator bytes)
     constexpr int OSZ = OUT_DT == DT_F32 ? 4 : 2;
     constexpr int IB = V * BITS / 8;                    // packed bytes per item and source: 4..32
     constexpr int NWI = IB / 4;
     constexpr int NWO = 16;
-    constexpr uint32_t QMAX = (1u << BITS) - 1u;
 
-    __shared__ QuantParams s_P[kMaxSumSources];
+    __shared__ DequantArgs s_src[kMaxSumSources];     // per source: parameters + what dequant_words derives from them (fast flag, 2^23 + zp)
     __shared__ int s_bad;
 
     char* out = a.out + a.head_bytes * PER * OSZ;
@@ -65,8 +68,16 @@ __global__ void __launch_bounds__(kThreads, 2) dequant_sum_kernel(const SumArgs 
     if (threadIdx.x == 0) s_bad = 0;
     __syncthreads();
     if (threadIdx.x < a.n_src) {
-        if (device_params_failed(a.dP[threadIdx.x])) s_bad = 1;
-        else s_P[threadIdx.x] = *a.dP[threadIdx.x];
+        if (device_params_failed(a.dP[threadIdx.x])) {
+            s_bad = 1;
+        } else {
+            DequantArgs& d = s_src[threadIdx.x];
+            d.in = a.in[threadIdx.x];
+            d.out = a.out;
+            d.numel = a.numel;
+            d.P = *a.dP[threadIdx.x];
+            set_dequant_fast(d, BITS, OUT_DT);
+        }
     }
     __syncthreads();
     if (s_bad) {
@@ -88,22 +99,12 @@ __global__ void __launch_bounds__(kThreads, 2) dequant_sum_kernel(const SumArgs 
 #pragma unroll
             for (int s = 0; s < kMaxSumSources; ++s) {
                 if (s < a.n_src) {
-                    const QuantParams& P = s_P[s];
-                    uint32_t w[NWI];
+                    // one ADD of source s onto the accumulator words: the byte-permute form of dequantize_common.cuh where the zero
+                    // point allows it (3 instructions per element), the general per-element steps otherwise -- bit-identical
+                    uint32_t next[NWO];
+                    dequant_words<BITS, OUT_DT, OP_ADD, NWI, NWO>(wi[s], acc, s_src[s], next);
 #pragma unroll
-                    for (int k = 0; k < NWI; ++k) w[k] = wi[s][k] ^ P.sign_xor;     // signed dtypes: two's complement -> offset binary
-#pragma unroll
-                    for (int e = 0; e < V; ++e) {
-                        const uint32_t q = (w[(e * BITS) / 32] >> ((e * BITS) % 32)) & QMAX;
-                        if constexpr (OUT_DT == DT_F32) {
-                            acc[e] = __float_as_uint(dequant_f32<BITS, OP_ADD>(q, __uint_as_float(acc[e]), P));
-                        } else if ((e & 1) == 0) {
-                            const uint32_t q1 = (w[((e + 1) * BITS) / 32] >> (((e + 1) * BITS) % 32)) & QMAX;
-                            const float lo = dequant_bf16_pre<BITS, OP_ADD>(q, bf16_lo(acc[e >> 1]), P);
-                            const float hi = dequant_bf16_pre<BITS, OP_ADD>(q1, bf16_hi(acc[e >> 1]), P);
-                            acc[e >> 1] = pack_bf16x2(lo, hi);     // rounded after every source, like a stored accumulator
-                        }
-                    }
+                    for (int k = 0; k < NWO; ++k) acc[k] = next[k];     // (a bf16 accumulator is rounded here, after every source)
                 }
             }
 #pragma unroll
@@ -124,14 +125,7 @@ __global__ void __launch_bounds__(kThreads, 2) dequant_sum_kernel(const SumArgs 
         // ragged head / tail bytes: source after source through the byte-granular ADD (keeps the reference's u2->f32 tail quirk)
         const int64_t total = (a.numel + PER - 1) / PER;
         auto ragged = [&](int64_t b) {
-            DequantArgs t;
-            t.out = a.out;
-            t.numel = a.numel;
-            for (int s = 0; s < a.n_src; ++s) {
-                t.in = a.in[s];
-                t.P = s_P[s];
-                dequant_one_byte<BITS, OUT_DT, OP_ADD>(t, b);
-            }
+            for (int s = 0; s < a.n_src; ++s) dequant_one_byte<BITS, OUT_DT, OP_ADD>(s_src[s], b);
 #pragma unroll
             for (int k = 0; k < PER; ++k) {
                 const int64_t e = b * PER + k;
@@ -195,9 +189,17 @@ static int launch_sum_cell(const void* const* ins, const QuantParams* const* dPs
     }
     if (!vec) return 0;
     a.tail = make_reduce_tail(scratch, ro);
-    int64_t grid = (a.n_items + kThreads - 1) / kThreads;
+    // Several tiles per CTA (grid stride): the ticketed tail -- two barriers, an atomic, a fence -- and the parameter staging are paid
+    // once per CTA, and with one 45 KB tile per CTA they cost as much as the tile (measured, 7 x u8 -> f32, 33.5 M elements:
+    // 1 / 2 / 4 tiles per CTA = 91.7 / 83.4 / 81.8 us, profiles/r2_sum_kernel_sweep.txt); short tensors keep one tile per CTA
+    // so that every SM still gets its share.
+    constexpr int MINB = sum_min_blocks(BITS, OUT_DT);
+    const int64_t n_tiles = (a.n_items + kThreads - 1) / kThreads;
+    int64_t per_cta = n_tiles / (static_cast<int64_t>(cfg.sm_count) * MINB * 2);
+    per_cta = per_cta < 1 ? 1 : (per_cta > 4 ? 4 : per_cta);
+    int64_t grid = (n_tiles + per_cta - 1) / per_cta;
     if (grid > scratch.max_blocks) grid = scratch.max_blocks;      // one partial per CTA; further tiles by grid stride
-    const SumKernel fn = a32 ? dequant_sum_kernel<BITS, OUT_DT, true> : dequant_sum_kernel<BITS, OUT_DT, false>;
+    const SumKernel fn = a32 ? dequant_sum_kernel<BITS, OUT_DT, true, MINB> : dequant_sum_kernel<BITS, OUT_DT, false, MINB>;
     launch_kernel(fn, static_cast<unsigned>(grid), kThreads, 0, cfg.stream, a);
     PQ_CUDA_CHECK(cudaGetLastError());
     return 1;
@@ -207,6 +209,8 @@ int launch_dequantize_sum_minmax(const void* const* ins, const QuantParams* cons
                                  int64_t numel, const LaunchCfg& cfg, const MinMaxScratch& scratch, const ReduceOut& ro) {
     pq_assert(numel > 0, "sum of empty tensors");
     pq_assert(n_src >= 1 && n_src <= kMaxSumSources, "between 1 and %d sources per launch (got %d)", kMaxSumSources, n_src);
+    // one source: that is the fused dequantize-ADD + min/max stream kernel (two items per thread, 58 registers)
+    if (n_src == 1) return launch_dequantize_add_minmax(ins[0], dt_in, out, dt_out, numel, make_params(1.0f, 0, 0.0f, dt_in), cfg, dPs[0], scratch, ro);
     int n = 0;
     if (dt_out == DT_F32) {
         switch (dt_in) {

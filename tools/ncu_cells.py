@@ -52,6 +52,30 @@ def main() -> None:
         "f32i8n": lambda: ctx.quantize_ptr(xf.data_ptr(), D.F32, q.data_ptr(), D.INT8, n, 2 / 255, 0, RoundMode.NEAREST),
         "requant_bf16": lambda: ctx.requantize_ptr(xb.data_ptr(), D.BF16, ob.data_ptr(), D.UINT8, n, 2 / 255, 128),
     }
+    # round-2 kernels: parameters on the device, fused accumulate, multi-source reduce (chunk of an 8-GPU all-reduce by default)
+    dev_i, st = torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream
+    meta = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    nxt = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    srcs = []
+
+    def sources(k):
+        while len(srcs) < k:
+            srcs.append(torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda"))
+        return srcs[:k]
+
+    ctx.compute_meta_on_stream(xf.data_ptr(), D.F32, min(n, 1 << 20), D.UINT8, meta.data_ptr(), piquant.Context.FLAG_LOCAL, dev_i, st)
+    acc = torch.zeros(n, dtype=torch.float32, device="cuda")
+    table.update({
+        "meta_f32": lambda: ctx.compute_meta_on_stream(xf.data_ptr(), D.F32, n, D.UINT8, nxt.data_ptr(), piquant.Context.FLAG_LOCAL, dev_i, st),
+        "addmm_u8_f32": lambda: ctx.dequantize_add_minmax_on_stream(q.data_ptr(), D.UINT8, acc.data_ptr(), D.F32, n, meta.data_ptr(), D.UINT8,
+                                                                    nxt.data_ptr(), 0, dev_i, st),
+        "sum7_u8_f32": lambda: ctx.dequantize_sum_minmax_on_stream([t.data_ptr() for t in sources(7)], D.UINT8, acc.data_ptr(), D.F32, n,
+                                                                   [meta.data_ptr()] * 7, D.UINT8, nxt.data_ptr(), 0, dev_i, st),
+        "sum1_u8_f32": lambda: ctx.dequantize_sum_minmax_on_stream([t.data_ptr() for t in sources(1)], D.UINT8, acc.data_ptr(), D.F32, n,
+                                                                   [meta.data_ptr()], D.UINT8, nxt.data_ptr(), 0, dev_i, st),
+        "sum7_u4_bf16": lambda: ctx.dequantize_sum_minmax_on_stream([t.data_ptr() for t in sources(7)], D.UINT4, ob.data_ptr(), D.BF16, n,
+                                                                    [meta.data_ptr()] * 7, D.UINT8, nxt.data_ptr(), 0, dev_i, st),
+    })
     for name in a.cells.split(","):
         for _ in range(a.launches):
             table[name]()
