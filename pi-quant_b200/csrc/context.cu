@@ -171,6 +171,9 @@ public:
             stream_copy(dst, src, bytes);
             return;
         }
+        // one distributed copy at a time: calls on different devices of one context share the pool (they are bound by the same
+        // host memory system, so taking turns costs nothing)
+        std::lock_guard<std::mutex> turn(call_mu_);
         {
             std::lock_guard<std::mutex> lock(mu_);
             dst_ = static_cast<char*>(dst);
@@ -217,6 +220,7 @@ private:
         }
     }
     std::vector<std::thread> threads_;
+    std::mutex call_mu_;
     std::mutex mu_;
     std::condition_variable cv_, cv_done_;
     bool stop_ = false;
