@@ -156,7 +156,8 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
     (profiles/r2_allreduce_probe_n8.txt); captured into a CUDA graph (``QuantizedAllReduce``) 1.06 ms.
     ``algorithm="auto"`` (default): direct when the GPUs can map each other's memory, else the ring over NCCL send/recv
     -- a fallback for boxes without peer access that is SLOWER than NCCL's own f32 all-reduce beyond 2 GPUs (0.39x at 8).
-    ``lanes=None``: 2 for the direct form on 2 GPUs, else 1.  The rest of this text describes ``algorithm="ring"``.
+    ``lanes=None``: 2 for the direct form on 2 GPUs and tensors of 256 MB or more, else 1.  The rest of this text describes
+    ``algorithm="ring"``.
 
     Ring reduce-scatter + ring all-gather over NVLink; every hop carries ``[64-byte parameter block | packed
     payload]`` -- 1, 1/2 or 1/4 byte per element instead of 4 (or 2).  A reduce-scatter hop is TWO passes over the
@@ -198,7 +199,7 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
     if algorithm == "auto":
         algorithm = "direct" if transport != "nccl" and _peer_memory_available(tensor.device, group) else "ring"
     if algorithm == "direct":
-        return _direct_all_reduce(tensor, dtype, group, ctx, rmode, lanes if lanes is not None else (2 if world == 2 else 1))
+        return _direct_all_reduce(tensor, dtype, group, ctx, rmode, lanes if lanes is not None else _auto_lanes(tensor, world))
     lanes = 1 if lanes is None else lanes
     fdt, qdt = torch_to_piquant_dtype(tensor.dtype), torch_to_piquant_dtype(dtype)
     meta = Context.META_BYTES
@@ -364,8 +365,9 @@ class _DirectPlan:
        Owners dequantize the same bytes they sent, so all ranks end with bit-identical values.
 
     Every element is quantized twice whatever the world size (the ring quantizes the running sum at every hop), one
-    barrier per call (nobody may still be reading the slots of the previous call) instead of 2 * (world - 1), and
-    nothing synchronises with the host.
+    barrier per call (nobody may still be reading the slots of the previous call; it sits on the copy stream, in front of
+    the first transfer, so the first chunk is quantized while the ranks meet) instead of 2 * (world - 1), and nothing
+    synchronises with the host.
 
     ``lanes``: the tensor is cut into that many contiguous parts, each an independent all-reduce with its own slots and
     flags, run STAGGERED on the same two streams: scatter A, scatter B, reduce A, reduce B, gather A, gather B.  The
@@ -438,8 +440,10 @@ class _DirectPlan:
                 self.trace.append((lane, label, ev))
 
         mark("start")
-        hdl.barrier(channel=self.CH_BARRIER)               # (current stream = main) nobody still reads the slots of a previous call
-        mark("barrier")
+        # Nobody may still be reading the slots of a previous call when the first copy of this one lands -- a barrier, but on the
+        # COPY stream: min/max + quantize of the first chunk touch local memory only and run while the ranks meet.
+        with torch.cuda.stream(side):
+            hdl.barrier(channel=self.CH_BARRIER)
         for k, j in enumerate(self.others):
             c = chunk(j)
             if c.numel():
@@ -502,6 +506,13 @@ class _DirectPlan:
 _DIRECT_PLANS: dict = {}
 
 
+def _auto_lanes(tensor: torch.Tensor, world: int) -> int:
+    """Two staggered lanes pay on 2 GPUs for large tensors (2^28 f32: 1.01 -> 0.76-0.82 ms); on an NVSwitch box with more ranks the
+    halved copies lose more link efficiency than the overlap wins (8 GPUs: 1.06 -> 1.18 ms), and below ~256 MB the second lane only
+    doubles the host work (profiles/r2_allreduce_probe_n2.txt, _n8.txt)."""
+    return 2 if world == 2 and tensor.numel() * tensor.element_size() >= (256 << 20) else 1
+
+
 def _direct_all_reduce(tensor: torch.Tensor, dtype: torch.dtype, group, ctx: Context, rmode: RoundMode, lanes: int = 1) -> torch.Tensor:
     grp = group if group is not None else dist.group.WORLD
     key = (grp.group_name, tensor.device.index, tensor.numel(), tensor.dtype, dtype, id(ctx), rmode, lanes)
@@ -530,7 +541,7 @@ class QuantizedAllReduce:
         if self.world == 1:
             self.graph = None
             return
-        lanes = lanes if lanes is not None else (2 if self.world == 2 else 1)
+        lanes = lanes if lanes is not None else _auto_lanes(tensor, self.world)
         self.plan = _DirectPlan(tensor.numel(), tensor.dtype, dtype, tensor.device, group, ctx, RoundMode.NEAREST, lanes)
         # one tiny eager call: the library's per-device state (slot table, two allocations) exists before the capture starts
         warm = torch.zeros(SHARD_ALIGN * self.world, dtype=tensor.dtype, device=tensor.device)

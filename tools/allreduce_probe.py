@@ -52,9 +52,9 @@ def main() -> None:
         rows = [("nccl f32 all_reduce", timed(lambda: dist.all_reduce(work)))]
         exact = work.clone()
         for name, kw in (("ring p2p, 2 lanes", dict(transport="p2p", algorithm="ring", lanes=2)),
-                         ("direct, 1 lane", dict(transport="p2p", algorithm="direct")),
+                         ("direct, 1 lane", dict(transport="p2p", algorithm="direct", lanes=1)),
                          ("direct, 2 staggered lanes", dict(transport="p2p", algorithm="direct", lanes=2)),
-                         ("direct u4, 1 lane", dict(transport="p2p", algorithm="direct", dtype=torch.quint4x2)),
+                         ("direct u4, 1 lane", dict(transport="p2p", algorithm="direct", lanes=1, dtype=torch.quint4x2)),
                          ):
             kw = dict(kw)
             qd = kw.pop("dtype", torch.quint8)
