@@ -365,9 +365,8 @@ class _DirectPlan:
        Owners dequantize the same bytes they sent, so all ranks end with bit-identical values.
 
     Every element is quantized twice whatever the world size (the ring quantizes the running sum at every hop), one
-    barrier per call (nobody may still be reading the slots of the previous call; it sits on the copy stream, in front of
-    the first transfer, so the first chunk is quantized while the ranks meet) instead of 2 * (world - 1), and nothing
-    synchronises with the host.
+    barrier per call (nobody may still be reading the slots of the previous call; it also starts the ranks in lockstep)
+    instead of 2 * (world - 1), and nothing synchronises with the host.
 
     ``lanes``: the tensor is cut into that many contiguous parts, each an independent all-reduce with its own slots and
     flags, run STAGGERED on the same two streams: scatter A, scatter B, reduce A, reduce B, gather A, gather B.  The
@@ -381,6 +380,7 @@ class _DirectPlan:
         """Everything that allocates or rendezvouses happens here, so that ``enqueue`` only launches (it may run inside a
         CUDA graph capture)."""
         self.group, self.ctx, self.rmode, self.dev, self.numel, self.float_dtype = group, ctx, rmode, device, numel, float_dtype
+        self.barrier_on_main = True
         self.trace = None                                   # a list: CUDA events at the phase boundaries of the next enqueue (tools/allreduce_probe.py)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.fdt, self.qdt = torch_to_piquant_dtype(float_dtype), torch_to_piquant_dtype(dtype)
@@ -440,10 +440,17 @@ class _DirectPlan:
                 self.trace.append((lane, label, ev))
 
         mark("start")
-        # Nobody may still be reading the slots of a previous call when the first copy of this one lands -- a barrier, but on the
-        # COPY stream: min/max + quantize of the first chunk touch local memory only and run while the ranks meet.
-        with torch.cuda.stream(side):
+        # Nobody may still be reading the slots of a previous call when the first copy of this one lands: one barrier.  It sits on
+        # the MAIN stream although only the copies need it: it also starts the ranks in lockstep, which is what keeps the staggered
+        # schedule staggered (every receiver fed by one sender at a time).  Measured on 8 GPUs in one run: barrier on the main
+        # stream 1.06-1.08 ms, on the copy stream (first chunk quantized while the ranks meet) 1.18-1.23 ms -- the skewed ranks'
+        # copies collide at the receivers (profiles/r2_allreduce_probe_n8_barrier_ab.txt).
+        if self.barrier_on_main:
             hdl.barrier(channel=self.CH_BARRIER)
+        else:                                                # (A/B switch of tools/allreduce_probe.py)
+            with torch.cuda.stream(side):
+                hdl.barrier(channel=self.CH_BARRIER)
+        mark("barrier")
         for k, j in enumerate(self.others):
             c = chunk(j)
             if c.numel():

@@ -127,6 +127,20 @@ def main() -> None:
                 if rank == 0:
                     print(f"  multicast probe failed: {type(e).__name__}: {str(e)[:200]}")
         del buf, hdl
+        # A/B in one run: the barrier at the start on the copy stream (default) or on the main stream
+        for rep in range(2):
+            for on_main in (False, True):
+                plan = pd._DirectPlan(n, torch.float32, torch.quint8, dev, None, ctx, piquant.RoundMode.NEAREST, 1)
+                plan.barrier_on_main = on_main
+                ms = timed(lambda: plan.enqueue(work))
+                rows.append((f"direct eager, barrier on {'main' if on_main else 'copy'} stream (rep {rep})", ms, 0.0))
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    plan.enqueue(work)
+                ms = timed(g.replay)
+                rows.append((f"direct graph, barrier on {'main' if on_main else 'copy'} stream (rep {rep})", ms, 0.0))
+                del g, plan
         for lanes in (1,):
             for qd, qn in ((torch.quint8, "u8"), (torch.quint4x2, "u4")):
                 plan = pd.QuantizedAllReduce(work, dtype=qd, ctx=ctx, lanes=lanes)
