@@ -237,6 +237,12 @@ PIQUANT_EXPORT void piquant_cuda_dequantize_sum_minmax_on_stream(piquant_context
  * whole transfer; a DMA transfer leaves the SMs to the kernels of other streams. */
 PIQUANT_EXPORT void piquant_cuda_copy_on_stream(piquant_context_t* ctx, void* dst, const void* src, size_t nbytes, int device, void* stream);
 
+/* Stream-ordered wait for an arrival flag: a 4-byte word in device memory that a copy engine -- of this GPU or of a peer,
+ * directly or through the NVSwitch multicast address of a symmetric buffer -- sets to a non-zero value AFTER the payload it
+ * announces (two piquant_cuda_copy_on_stream on one stream).  A one-thread kernel polls the word, lowers it to 0 again and ends;
+ * work queued behind it on `stream` sees the payload.  Nothing here blocks the host. */
+PIQUANT_EXPORT void piquant_cuda_wait_flag_on_stream(piquant_context_t* ctx, void* flag, int device, void* stream);
+
 /* ---- many small tensors, one launch -----------------------------------------------------------------------------
  * The reference's own Python benchmark quantizes a 1e6-element tensor 1000 times (reference python/benchmark/benchmark.py:16-23);
  * on a GPU a launch costs more than 1e6 elements of data.  One call quantizes `count` independent tensors -- each with

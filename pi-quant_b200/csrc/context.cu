@@ -1448,6 +1448,18 @@ extern "C" void piquant_cuda_copy_on_stream(piquant_context_t* ctx, void* dst, c
     PQ_CUDA_CHECK(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDefault, site.stream));
 }
 
+extern "C" void piquant_cuda_wait_flag_on_stream(piquant_context_t* ctx, void* flag, int device, void* stream) {
+    Context* c = as_ctx(ctx);
+    pq_assert(flag != nullptr && (reinterpret_cast<uintptr_t>(flag) & 3u) == 0, "the flag must be a 4-byte aligned device address");
+    const Site site = call_site(device, stream);
+    const int cur = require_device();
+    const int dev = device_of(site, {flag}, "piquant_cuda_wait_flag");
+    DeviceGuard guard(cur, dev);
+    LaunchCfg cfg{};
+    cfg.stream = site.stream;
+    c->launches += launch_wait_flag(static_cast<unsigned*>(flag), cfg);
+}
+
 extern "C" void piquant_cuda_quantize_auto_on_stream(piquant_context_t* ctx, const void* in, piquant_dtype_t dtype_in, void* out,
                                                      piquant_dtype_t dtype_out, size_t numel, piquant_round_mode_t mode, float* out_scale,
                                                      int64_t* out_zero_point, int device, void* stream) {

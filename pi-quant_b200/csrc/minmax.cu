@@ -171,6 +171,25 @@ int launch_minmax_publish(float* minmax4, const LaunchCfg& cfg) {
     return 1;
 }
 
+// One thread spins until a 4-byte arrival flag (written by a peer's copy engine, possibly through the NVSwitch multicast
+// address) is up, lowers it again, and ends: the kernels queued behind it on the stream see what was copied before the flag.
+__global__ void wait_flag_kernel(unsigned* flag) {
+    pdl_launch_dependents();
+    pdl_wait();
+    unsigned v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v == 0u) __nanosleep(64);
+    } while (v == 0u);
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(0u) : "memory");
+}
+
+int launch_wait_flag(unsigned* flag, const LaunchCfg& cfg) {
+    launch_kernel(wait_flag_kernel, 1u, 1u, 0, cfg.stream, flag);
+    PQ_CUDA_CHECK(cudaGetLastError());
+    return 1;
+}
+
 int launch_params(const float* minmax4, int dt_quant, DeviceMeta* out, DeviceMeta* mapped_out, const LaunchCfg& cfg) {
     launch_kernel(params_kernel, 1u, 1u, 0, cfg.stream, minmax4, dtype_bits(dt_quant), dtype_is_signed_quant(dt_quant) ? 1 : 0,
                   dtype_sign_xor(dt_quant), out, mapped_out);

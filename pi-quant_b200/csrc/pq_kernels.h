@@ -226,6 +226,8 @@ int launch_quantize_batch(const BatchItem* items, int count, int dt_in, int dt_o
 // dt_quant may be a signed extension type: the public (scale, zero_point) are then the signed ones
 // (reference src/piquant.cpp:245-258 with type_min = -type_max - 1) and P is the unsigned kernel view.
 int launch_params(const float* minmax4, int dt_quant, DeviceMeta* out, DeviceMeta* mapped_out, const LaunchCfg& cfg);
+// stream-ordered wait for a 4-byte arrival flag in device memory (set to non-zero by a copy engine of this or a peer GPU); resets it
+int launch_wait_flag(unsigned* flag, const LaunchCfg& cfg);
 // minmax4[0..1] = {-minmax4[2], minmax4[3]}: after {-min, max} was combined across ranks by an all-reduce
 int launch_minmax_publish(float* minmax4, const LaunchCfg& cfg);
 

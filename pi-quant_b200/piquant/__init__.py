@@ -318,6 +318,10 @@ class Context:
         C.piquant_cuda_dequantize_sum_minmax_on_stream(self._ctx, ins, metas, len(ins), dtype_in.value, ptr_out, dtype_out.value, numel,
                                                        next_quant_dtype.value, ptr_meta_next, ptr_meta_next_copy, device, stream)
 
+    def wait_flag_on_stream(self, ptr_flag: int, device: int, stream: int) -> None:
+        """Stream-ordered wait until the 4-byte flag at ``ptr_flag`` is non-zero (set by a copy engine after its payload); resets it."""
+        C.piquant_cuda_wait_flag_on_stream(self._ctx, ptr_flag, device, stream)
+
     def copy_on_stream(self, ptr_dst: int, ptr_src: int, nbytes: int, device: int, stream: int) -> None:
         """Stream-ordered copy by a copy engine (cudaMemcpyAsync): local, peer-mapped or pinned memory on either side."""
         C.piquant_cuda_copy_on_stream(self._ctx, ptr_dst, ptr_src, nbytes, device, stream)

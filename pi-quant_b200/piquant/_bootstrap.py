@@ -102,6 +102,7 @@ void  piquant_cuda_dequantize_forward_on_stream(piquant_context_t* ctx, uintptr_
 void  piquant_cuda_dequantize_sum_minmax_on_stream(piquant_context_t* ctx, const uintptr_t* ins, const uintptr_t* d_metas, size_t count, int dtype_in,
                                                    uintptr_t out, int dtype_out, size_t numel, int next_quant_dtype, uintptr_t d_meta_next,
                                                    uintptr_t d_meta_next_copy, int device, uintptr_t stream);
+void  piquant_cuda_wait_flag_on_stream(piquant_context_t* ctx, uintptr_t flag, int device, uintptr_t stream);
 void  piquant_cuda_copy_on_stream(piquant_context_t* ctx, uintptr_t dst, uintptr_t src, size_t nbytes, int device, uintptr_t stream);
 typedef struct piquant_cuda_batch_item_t { uintptr_t in; uintptr_t out; size_t numel; float scale; int64_t zero_point; } piquant_cuda_batch_item_t;
 void  piquant_cuda_quantize_batch(piquant_context_t* ctx, const piquant_cuda_batch_item_t* items, size_t count, int dtype_in, int dtype_out,

@@ -146,7 +146,7 @@ def _side_stream(device: torch.device, lane: int) -> "torch.cuda.Stream":
 
 def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.quint8, group: Optional[dist.ProcessGroup] = None,
                           ctx: Context = Context.get(), transport: str = "auto", round_mode: str = "nearest", lanes: Optional[int] = None,
-                          algorithm: str = "auto") -> torch.Tensor:
+                          algorithm: str = "auto", multicast: Optional[bool] = None) -> torch.Tensor:
     """In-place SUM all-reduce of a contiguous CUDA float32 / bfloat16 tensor with quantized transport.
 
     ``algorithm="direct"`` (needs peer memory; see ``_DirectPlan``) is the NVSwitch-native form: every chunk crosses the
@@ -156,6 +156,8 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
     (profiles/r2_allreduce_probe_n8.txt); captured into a CUDA graph (``QuantizedAllReduce``) 1.06 ms.
     ``algorithm="auto"`` (default): direct when the GPUs can map each other's memory, else the ring over NCCL send/recv
     -- a fallback for boxes without peer access that is SLOWER than NCCL's own f32 all-reduce beyond 2 GPUs (0.39x at 8).
+    ``multicast`` (direct form): broadcast the reduced chunks through the NVSwitch multicast address of the symmetric buffer
+    (``None``: when the box has it and there are more than 2 ranks).
     ``lanes=None``: 2 for the direct form on 2 GPUs and tensors of 256 MB or more, else 1.  The rest of this text describes
     ``algorithm="ring"``.
 
@@ -199,7 +201,7 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
     if algorithm == "auto":
         algorithm = "direct" if transport != "nccl" and _peer_memory_available(tensor.device, group) else "ring"
     if algorithm == "direct":
-        return _direct_all_reduce(tensor, dtype, group, ctx, rmode, lanes if lanes is not None else _auto_lanes(tensor, world))
+        return _direct_all_reduce(tensor, dtype, group, ctx, rmode, lanes if lanes is not None else _auto_lanes(tensor, world), multicast)
     lanes = 1 if lanes is None else lanes
     fdt, qdt = torch_to_piquant_dtype(tensor.dtype), torch_to_piquant_dtype(dtype)
     meta = Context.META_BYTES
@@ -375,8 +377,10 @@ class _DirectPlan:
 
     CH_BARRIER, CH_SCATTER, CH_GATHER = 0, 1, 2             # signal-pad channels (torch symmetric memory: one u32 per channel and rank)
 
+    GATHER_PIECES = 4                                       # multicast gather: pieces per reduced chunk, each with its own arrival flag
+
     def __init__(self, numel: int, float_dtype: torch.dtype, dtype: torch.dtype, device: torch.device, group, ctx: Context, rmode: RoundMode,
-                 lanes: int = 1):
+                 lanes: int = 1, multicast: Optional[bool] = None):
         """Everything that allocates or rendezvouses happens here, so that ``enqueue`` only launches (it may run inside a
         CUDA graph capture)."""
         self.group, self.ctx, self.rmode, self.dev, self.numel, self.float_dtype = group, ctx, rmode, device, numel, float_dtype
@@ -401,11 +405,26 @@ class _DirectPlan:
             slot_bytes = (meta + max(qbytes) + 255) // 256 * 256
             # symmetric memory: [world scatter slots | world gather slots]; slot k of the first half receives from
             # rank k, slot k of the second half holds the reduced chunk k
-            local, hdl = _p2p_slots(world * slot_bytes, device, group, lane=-2 - lane)       # (allocates 2 * nbytes: the two halves)
+            # ... followed by 4 KB of arrival flags for the multicast gather: flag [owner][piece], one u32 each
+            local, hdl = _p2p_slots(world * slot_bytes + 2048, device, group, lane=-2 - lane)       # (allocates 2 * nbytes: the two halves)
+            flags_off = 2 * world * slot_bytes
+            local[flags_off:].zero_()
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            # pieces of every chunk (element offsets, multiples of 256 elements = 64 packed bytes at 2 bits): identical on every rank
+            pieces = []
+            for b, e in bounds:
+                n_c = e - b
+                cuts = sorted({min(n_c, (n_c * k // self.GATHER_PIECES) // 256 * 256) for k in range(self.GATHER_PIECES)} | {n_c})
+                pieces.append([(lo, hi) for lo, hi in zip(cuts[:-1], cuts[1:]) if hi > lo])
             self.lanes.append(dict(bounds=bounds, qbytes=qbytes, slot_bytes=slot_bytes, local=local, hdl=hdl,
                                    peer_base=[int(hdl.buffer_ptrs[i]) for i in range(world)],
                                    peer_pad=[int(hdl.signal_pad_ptrs[i]) for i in range(world)],
-                                   stage=torch.empty((world - 1) * slot_bytes, dtype=torch.uint8, device=device)))
+                                   mc=mc, flags_off=flags_off, pieces=pieces,
+                                   stage=torch.empty(world * slot_bytes, dtype=torch.uint8, device=device)))
+        # NVSwitch multicast for the gather exchange: one copy-engine transfer per piece reaches every rank (measured at 8 GPUs:
+        # 0.83 TB/s INTO every GPU against 0.48-0.56 TB/s for seven unicast copies).  Off on 2 GPUs (one peer: nothing to replicate).
+        have_mc = all(L["mc"] for L in self.lanes) and world * self.GATHER_PIECES * 4 <= 2048
+        self.multicast = have_mc and world > 2 if multicast is None else bool(multicast) and have_mc
         torch.cuda.synchronize(device)
 
     def _lane_phases(self, flat: torch.Tensor, lane: int, main: "torch.cuda.Stream"):
@@ -462,7 +481,9 @@ class _DirectPlan:
                 mark(f"quantized chunk {j}")
         yield
         mine = chunk(rank)
-        own_slot = my_base + ag_off(rank)
+        # where [parameters | packed sums] of my chunk are produced: my own gather slot, or -- the multicast transfer writes EVERY
+        # replica of that slot, mine included, and must not copy onto itself -- a local staging slot
+        own_slot = stage + (world - 1) * slot_bytes if self.multicast else my_base + ag_off(rank)
         if mine.numel():
             for k in self.arrivals:
                 hdl.wait_signal(k, self.CH_SCATTER)        # my scatter slots are complete (the kernel lowers the flag again)
@@ -475,11 +496,32 @@ class _DirectPlan:
             ctx.quantize_meta_on_stream(mine.data_ptr(), fdt, own_slot + meta, qdt, mine.numel(), rmode, own_slot, REVERSE, device, st)
             mark("reduced + quantized own chunk")
             copies_follow_main()
-            for j in self.others:
-                send(own_slot, j, ag_off(rank), meta + qbytes[rank], self.CH_GATHER)
+            if self.multicast:
+                mc_slot, mc_flags = L["mc"] + ag_off(rank), L["mc"] + L["flags_off"] + 4 * rank * self.GATHER_PIECES
+                for p, (lo, hi) in enumerate(L["pieces"][rank]):
+                    b0 = 0 if p == 0 else meta + qdt.storage_bytes(lo)
+                    b1 = meta + qdt.storage_bytes(hi)
+                    ctx.copy_on_stream(mc_slot + b0, own_slot + b0, b1 - b0, device, side.cuda_stream)     # ONE transfer, every rank's slot
+                    ctx.copy_on_stream(mc_flags + 4 * p, self.one.data_ptr(), 4, device, side.cuda_stream)  # ... then every rank's flag
+            else:
+                for j in self.others:
+                    send(own_slot, j, ag_off(rank), meta + qbytes[rank], self.CH_GATHER)
             # the owner takes the dequantized values of exactly the bytes everybody else receives
             ctx.dequantize_meta_on_stream(own_slot + meta, qdt, mine.data_ptr(), fdt, mine.numel(), ReduceOp.SET, own_slot, device, st)
         yield
+        if self.multicast:
+            # all owners broadcast at once, so piece p of every chunk arrives at about the same time: dequantize round by round
+            my_flags = my_base + L["flags_off"]
+            for p in range(self.GATHER_PIECES):
+                for j in self.arrivals:
+                    if p < len(L["pieces"][j]):
+                        lo, hi = L["pieces"][j][p]
+                        src = my_base + ag_off(j)
+                        ctx.wait_flag_on_stream(my_flags + 4 * (j * self.GATHER_PIECES + p), device, st)
+                        ctx.dequantize_meta_on_stream(src + meta + qdt.storage_bytes(lo), qdt, chunk(j)[lo:hi].data_ptr(), fdt, hi - lo,
+                                                      ReduceOp.SET, src, device, st)
+                mark(f"dequantized piece {p} of every chunk")
+            return
         for j in self.arrivals:
             c = chunk(j)
             if c.numel():
@@ -520,12 +562,13 @@ def _auto_lanes(tensor: torch.Tensor, world: int) -> int:
     return 2 if world == 2 and tensor.numel() * tensor.element_size() >= (256 << 20) else 1
 
 
-def _direct_all_reduce(tensor: torch.Tensor, dtype: torch.dtype, group, ctx: Context, rmode: RoundMode, lanes: int = 1) -> torch.Tensor:
+def _direct_all_reduce(tensor: torch.Tensor, dtype: torch.dtype, group, ctx: Context, rmode: RoundMode, lanes: int = 1,
+                       multicast: Optional[bool] = None) -> torch.Tensor:
     grp = group if group is not None else dist.group.WORLD
-    key = (grp.group_name, tensor.device.index, tensor.numel(), tensor.dtype, dtype, id(ctx), rmode, lanes)
+    key = (grp.group_name, tensor.device.index, tensor.numel(), tensor.dtype, dtype, id(ctx), rmode, lanes, multicast)
     plan = _DIRECT_PLANS.get(key)
     if plan is None:
-        plan = _DIRECT_PLANS[key] = _DirectPlan(tensor.numel(), tensor.dtype, dtype, tensor.device, group, ctx, rmode, lanes)
+        plan = _DIRECT_PLANS[key] = _DirectPlan(tensor.numel(), tensor.dtype, dtype, tensor.device, group, ctx, rmode, lanes, multicast)
     return plan.enqueue(tensor)
 
 
@@ -540,7 +583,7 @@ class QuantizedAllReduce:
     the start of every call keeps successive calls apart): replay them on ONE stream, like any collective of a group."""
 
     def __init__(self, tensor: torch.Tensor, *, dtype: torch.dtype = torch.quint8, group: Optional[dist.ProcessGroup] = None,
-                 ctx: Context = Context.get(), lanes: Optional[int] = None):
+                 ctx: Context = Context.get(), lanes: Optional[int] = None, multicast: Optional[bool] = None):
         assert tensor.is_cuda and tensor.is_contiguous() and tensor.dtype in (torch.float32, torch.bfloat16)
         assert dtype in _QUANT_TYPES
         self.tensor = tensor
@@ -549,7 +592,7 @@ class QuantizedAllReduce:
             self.graph = None
             return
         lanes = lanes if lanes is not None else _auto_lanes(tensor, self.world)
-        self.plan = _DirectPlan(tensor.numel(), tensor.dtype, dtype, tensor.device, group, ctx, RoundMode.NEAREST, lanes)
+        self.plan = _DirectPlan(tensor.numel(), tensor.dtype, dtype, tensor.device, group, ctx, RoundMode.NEAREST, lanes, multicast)
         # one tiny eager call: the library's per-device state (slot table, two allocations) exists before the capture starts
         warm = torch.zeros(SHARD_ALIGN * self.world, dtype=tensor.dtype, device=tensor.device)
         meta = torch.zeros(Context.META_BYTES, dtype=torch.uint8, device=tensor.device)

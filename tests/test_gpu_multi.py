@@ -90,6 +90,24 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
         pd.destroy_native_comm(ctx)
         # quantized ring all-reduce: every rank ends with bit-identical values, close to the exact sum
         # the NVSwitch form: two all-to-all exchanges, ONE multi-source reduce kernel; replayed on the CPU with the oracle
+        # the gather exchange through the NVSwitch multicast address (forced on: 2 ranks would not pick it), pieces with their own flags
+        for tdt, qdt, numel, lanes, graph in ((torch.float32, torch.quint8, 1_000_003, 1, False), (torch.bfloat16, torch.quint4x2, 300_007, 2, False),
+                                              (torch.float32, torch.quint2x4, 70_001, 1, False), (torch.float32, torch.quint8, 100, 1, False),
+                                              (torch.float32, torch.quint8, 4_194_304, 1, True)):
+            t = torch.zeros(numel, device="cuda", dtype=tdt)
+            plan = pd.QuantizedAllReduce(t, dtype=qdt, ctx=ctx, lanes=lanes, multicast=True) if graph else None
+            if (plan.plan.multicast if graph else True):
+                for rep in range(3):
+                    g = torch.Generator(device="cuda").manual_seed(700 + 10 * rep + rank)
+                    t.copy_((torch.rand(numel, device="cuda", generator=g) * 2 - 1).to(tdt))
+                    inputs = [torch.empty_like(t) for _ in range(world)]
+                    dist.all_gather(inputs, t)
+                    if graph:
+                        plan()
+                    else:
+                        pd.quantized_all_reduce_(t, dtype=qdt, ctx=ctx, algorithm="direct", lanes=lanes, multicast=True)
+                    want = _direct_on_the_oracle(orc, pd, [i.cpu() for i in inputs], qdt, lanes)
+                    res[f"multicast_{tdt}_{qdt}_{numel}_graph{graph}_{rep}"] = (bool(np.array_equal(_bits(t.cpu()), want)),)
         for tdt, qdt, rmode, numel, lanes in ((torch.float32, torch.quint8, "nearest", 1_000_003, 1), (torch.bfloat16, torch.quint8, "nearest", 1_000_003, 1),
                                               (torch.float32, torch.quint4x2, "nearest", 300_007, 1), (torch.bfloat16, torch.quint2x4, "nearest", 70_001, 1),
                                               (torch.float32, torch.quint8, "nearest", 100, 1), (torch.float32, torch.quint8, "nearest", 4_194_304, 1),

@@ -127,19 +127,36 @@ def main() -> None:
                 if rank == 0:
                     print(f"  multicast probe failed: {type(e).__name__}: {str(e)[:200]}")
         del buf, hdl
-        # A/B in one run: the barrier at the start on the copy stream (default) or on the main stream
+        # A/B in one run: gather exchange by seven unicast copies or through the NVSwitch multicast address (pieces + flags)
         for rep in range(2):
-            for on_main in (False, True):
-                plan = pd._DirectPlan(n, torch.float32, torch.quint8, dev, None, ctx, piquant.RoundMode.NEAREST, 1)
-                plan.barrier_on_main = on_main
+            for mcast in (False, True):
+                plan = pd._DirectPlan(n, torch.float32, torch.quint8, dev, None, ctx, piquant.RoundMode.NEAREST, 1, mcast)
+                name = "multicast" if plan.multicast else "unicast"
                 ms = timed(lambda: plan.enqueue(work))
-                rows.append((f"direct eager, barrier on {'main' if on_main else 'copy'} stream (rep {rep})", ms, 0.0))
+                err = (work - exact).abs().max()
+                dist.all_reduce(err, op=dist.ReduceOp.MAX)
+                rows.append((f"direct eager, {name} gather (rep {rep})", ms, float(err.item())))
                 g = torch.cuda.CUDAGraph()
                 torch.cuda.synchronize()
                 with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     plan.enqueue(work)
                 ms = timed(g.replay)
-                rows.append((f"direct graph, barrier on {'main' if on_main else 'copy'} stream (rep {rep})", ms, 0.0))
+                err = (work - exact).abs().max()
+                dist.all_reduce(err, op=dist.ReduceOp.MAX)
+                rows.append((f"direct graph, {name} gather (rep {rep})", ms, float(err.item())))
+                if rep == 1 and plan.multicast:
+                    work.copy_(base)
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    plan.trace = []
+                    plan.enqueue(work)
+                    torch.cuda.synchronize()
+                    if rank == 0:
+                        t0 = plan.trace[0][2]
+                        print("  timeline of one eager direct all-reduce with the multicast gather, us since start, rank 0:")
+                        for lane, label, ev in plan.trace:
+                            print(f"    {t0.elapsed_time(ev) * 1e3:9.1f}  {label}")
+                    plan.trace = None
                 del g, plan
         for lanes in (1,):
             for qd, qn in ((torch.quint8, "u8"), (torch.quint4x2, "u4")):
