@@ -156,8 +156,8 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
     (profiles/r2_allreduce_probe_n8.txt); captured into a CUDA graph (``QuantizedAllReduce``) 1.06 ms.
     ``algorithm="auto"`` (default): direct when the GPUs can map each other's memory, else the ring over NCCL send/recv
     -- a fallback for boxes without peer access that is SLOWER than NCCL's own f32 all-reduce beyond 2 GPUs (0.39x at 8).
-    ``multicast`` (direct form): broadcast the reduced chunks through the NVSwitch multicast address of the symmetric buffer
-    (``None``: when the box has it and there are more than 2 ranks).
+    ``multicast=True`` (direct form, opt-in): broadcast the reduced chunks through the NVSwitch multicast address of the symmetric
+    buffer; bit-identical results, measured slower than the default at 8 GPUs (see ``_DirectPlan``).
     ``lanes=None``: 2 for the direct form on 2 GPUs and tensors of 256 MB or more, else 1.  The rest of this text describes
     ``algorithm="ring"``.
 
@@ -421,10 +421,14 @@ class _DirectPlan:
                                    peer_pad=[int(hdl.signal_pad_ptrs[i]) for i in range(world)],
                                    mc=mc, flags_off=flags_off, pieces=pieces,
                                    stage=torch.empty(world * slot_bytes, dtype=torch.uint8, device=device)))
-        # NVSwitch multicast for the gather exchange: one copy-engine transfer per piece reaches every rank (measured at 8 GPUs:
-        # 0.83 TB/s INTO every GPU against 0.48-0.56 TB/s for seven unicast copies).  Off on 2 GPUs (one peer: nothing to replicate).
+        # NVSwitch multicast for the gather exchange (opt-in): one copy-engine transfer per piece reaches every rank.  A single
+        # 33.5 MB multicast per rank delivers 0.75-0.85 TB/s INTO every GPU against 0.48-0.56 TB/s for seven unicast copies, but
+        # all seven slots then arrive together and the dequantizes queue up behind them; cut into 4 pieces with their own flags
+        # (so that dequantizing overlaps the arrivals) the exchange measured SLOWER than the unicast form at 8 GPUs -- 1.12 ms
+        # against 1.08 ms for the whole collective, the first piece landing 400 us after the reduce
+        # (profiles/r2_allreduce_probe_n8_multicast_ab.txt) -- so the default stays unicast.
         have_mc = all(L["mc"] for L in self.lanes) and world * self.GATHER_PIECES * 4 <= 2048
-        self.multicast = have_mc and world > 2 if multicast is None else bool(multicast) and have_mc
+        self.multicast = bool(multicast) and have_mc
         torch.cuda.synchronize(device)
 
     def _lane_phases(self, flat: torch.Tensor, lane: int, main: "torch.cuda.Stream"):
