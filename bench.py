@@ -703,7 +703,8 @@ def small_tensor_leg(torch, ctx, dev) -> dict:
                 row[label] = {"total_s": round(t, 5), "us_per_tensor": round(t / runs * 1e6, 2), "Gelem/s": round(runs * numel / t / 1e9, 1),
                               "GB/s": round(bpe * runs * numel / t / 1e9, 1)}
             # the same batch with outputs allocated beforehand (the allocation of 1000 quantized torch tensors is most of the
-            # time above): wall clock of the call, and the device time of its launches between two CUDA events
+            # time above; what remains is mostly Python turning 1000 tensors into descriptors): wall clock of the call and the
+            # time between two CUDA events around it
             outs = [torch.empty(t1.shape, dtype=tdt, device=dev) for _ in range(runs)]
             args = dict(scales=[s_] * runs, zero_points=[z_] * runs, dtype=tdt, ctx=ctx, outs=outs)
             pt.quantize_batch([t1] * runs, **args)
@@ -719,21 +720,37 @@ def small_tensor_leg(torch, ctx, dev) -> dict:
             row["one_batch_preallocated_outputs"] = {"total_s": round(t, 5), "us_per_tensor": round(t / runs * 1e6, 2),
                                                      "device_us_per_tensor": round(dev_t / runs * 1e6, 3),
                                                      "device_GB/s": round(bpe * runs * numel / dev_t / 1e9, 1)}
+            # a PREPARED batch (piquant.torch.QuantizeBatch: descriptor array built once): what is left is one native call
+            prepared = pt.QuantizeBatch([t1] * runs, **args)
+            prepared.run()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e0.record()
+            prepared.run()
+            e1.record()
+            torch.cuda.synchronize()
+            t = time.perf_counter() - t0
+            dev_t = e0.elapsed_time(e1) * 1e-3
+            row["prepared_batch"] = {"total_s": round(t, 5), "us_per_tensor": round(t / runs * 1e6, 3), "device_us_per_tensor": round(dev_t / runs * 1e6, 3),
+                                     "device_GB/s": round(bpe * runs * numel / dev_t / 1e9, 1)}
+            del prepared
             if name == "quint8":
                 # ... and with 1000 DISTINCT input tensors (the recipe above reads one 4 MB tensor a thousand times: every CTA column
                 # of the batch hits the same L2 lines at once)
                 many = torch.rand(runs, numel, dtype=torch.float32, device=dev)
                 ins = [many[i] for i in range(runs)]
-                pt.quantize_batch(ins, **args)
+                prepared = pt.QuantizeBatch(ins, **args)
+                prepared.run()
                 torch.cuda.synchronize()
                 e0.record()
-                pt.quantize_batch(ins, **args)
+                prepared.run()
                 e1.record()
                 torch.cuda.synchronize()
                 dev_t = e0.elapsed_time(e1) * 1e-3
-                row["one_batch_preallocated_outputs_distinct_inputs"] = {"device_us_per_tensor": round(dev_t / runs * 1e6, 3),
-                                                                         "device_GB/s": round(bpe * runs * numel / dev_t / 1e9, 1)}
-                del many, ins
+                row["prepared_batch_distinct_inputs"] = {"device_us_per_tensor": round(dev_t / runs * 1e6, 3),
+                                                         "device_GB/s": round(bpe * runs * numel / dev_t / 1e9, 1),
+                                                         "note": "5 GB of HBM traffic in one batch: the kernel's own rate"}
+                del many, ins, prepared
             del outs
             a, b = keep[0], pt.quantize(t1, scale=s_, zero_point=z_, dtype=tdt, ctx=ctx)
             row["batch_equals_per_call"] = bool(torch.equal(torch.empty(0, dtype=torch.uint8, device=dev).set_(a.untyped_storage()),

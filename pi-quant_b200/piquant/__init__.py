@@ -326,9 +326,15 @@ class Context:
         """Stream-ordered copy by a copy engine (cudaMemcpyAsync): local, peer-mapped or pinned memory on either side."""
         C.piquant_cuda_copy_on_stream(self._ctx, ptr_dst, ptr_src, nbytes, device, stream)
 
+    @staticmethod
+    def make_batch(items):
+        """The native descriptor array of a batch: items = sequence of (ptr_in, ptr_out, numel, scale, zero_point).  Build it once
+        for tensors that are quantized repeatedly (converting a thousand Python tuples costs more than quantizing them)."""
+        return ffi.new("piquant_cuda_batch_item_t[]", items if isinstance(items, list) else list(items))     # tuples initialise the structs
+
     def quantize_batch(self, items, dtype_in: DataType, dtype_out: DataType, round_mode: RoundMode, device: int, stream: int) -> None:
-        """items: sequence of (ptr_in, ptr_out, numel, scale, zero_point); ONE kernel launch per 256 tensors."""
-        arr = ffi.new("piquant_cuda_batch_item_t[]", items if isinstance(items, list) else list(items))     # tuples initialise the structs
+        """items: sequence of (ptr_in, ptr_out, numel, scale, zero_point) or the result of ``make_batch``; ONE kernel launch per 256 tensors."""
+        arr = items if isinstance(items, ffi.CData) else Context.make_batch(items)
         C.piquant_cuda_quantize_batch(self._ctx, arr, len(arr), dtype_in.value, dtype_out.value, round_mode.value, device, stream)
 
     def comm_set_transport(self, transport: int) -> None:

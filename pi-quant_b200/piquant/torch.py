@@ -185,6 +185,32 @@ def quantize_batch(tensors, *, scales, zero_points, dtype: torch.dtype, round_mo
     return outs
 
 
+class QuantizeBatch:
+    """A prepared ``quantize_batch``: the descriptor array is built once, every ``run()`` is one native call (one launch per 256
+    tensors).  For sets of small tensors that are quantized again and again (the buckets of a model): the tensors, their outputs
+    and their parameters are fixed at construction -- update parameters with ``set_params``."""
+
+    def __init__(self, tensors, *, scales, zero_points, dtype: torch.dtype, ctx: Context = Context.get(), outs=None):
+        assert dtype in _QUANT_TYPES, f"Unsupported quantized dtype: {dtype}. Must be one of {list(_QUANT_TYPES)}"
+        self.tensors = [_contiguous(t) for t in tensors]
+        assert self.tensors and self.tensors[0].is_cuda
+        first = self.tensors[0]
+        assert all(t.dtype == first.dtype and t.device == first.device for t in self.tensors), "one float dtype and one device per batch"
+        self.outs = outs if outs is not None else [torch.empty(t.shape, dtype=dtype, device=t.device) for t in self.tensors]
+        assert len(self.outs) == len(self.tensors) == len(scales) == len(zero_points)
+        self.ctx, self.dtype_in, self.dtype_out = ctx, torch_to_piquant_dtype(first.dtype), torch_to_piquant_dtype(dtype)
+        self.items = Context.make_batch([(t.data_ptr(), o.data_ptr(), t.numel(), float(s), int(z))
+                                         for t, o, s, z in zip(self.tensors, self.outs, scales, zero_points)])
+
+    def set_params(self, index: int, scale: float, zero_point: int) -> None:
+        self.items[index].scale, self.items[index].zero_point = float(scale), int(zero_point)
+
+    def run(self, round_mode: str = "nearest"):
+        device, stream = _site(self.tensors[0])
+        self.ctx.quantize_batch(self.items, self.dtype_in, self.dtype_out, _ROUND_MODES[round_mode], device, stream)
+        return self.outs
+
+
 def new_meta(device: torch.device) -> torch.Tensor:
     """A 64-byte device block for parameters that never leave the GPU (``piquant_cuda_meta_t``)."""
     return torch.zeros(Context.META_BYTES, dtype=torch.uint8, device=device)

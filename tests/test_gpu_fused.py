@@ -508,3 +508,23 @@ def test_pageable_host_tensors_through_the_bounce_pipeline():
     out = torch.zeros(packed_bytes(UINT4, xb.size), dtype=torch.uint8, device="cuda")
     ctx.quantize_ptr(xb.ctypes.data, DT[BF16], out.data_ptr(), DT[UINT4], xb.size, s4, z4, MODE[0])
     assert np.array_equal(out.cpu().numpy(), port.quantize(xb, UINT4, s4, z4, NEAREST, semantics=SEM_BODY))
+
+
+def test_prepared_quantize_batch_equals_per_call_and_takes_new_parameters():
+    """piquant.torch.QuantizeBatch: descriptors built once, run() == quantize() per tensor; set_params is honoured."""
+    import piquant.torch as pt
+    ctx = _ctx()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    tensors = [torch.rand(n, device="cuda", generator=g) * 4 - 2 for n in (1, 63, 4097, 100_003, 1_000_000)]
+    params = [pt.compute_quant_params(t, dtype=torch.quint4x2, ctx=ctx) for t in tensors]
+    batch = pt.QuantizeBatch(tensors, scales=[p[0] for p in params], zero_points=[p[1] for p in params], dtype=torch.quint4x2, ctx=ctx)
+    before = ctx.kernel_launches
+    outs = batch.run()
+    assert ctx.kernel_launches - before == 1
+    raw = lambda t: torch.empty(0, dtype=torch.uint8, device="cuda").set_(t.untyped_storage())      # noqa: E731
+    for t, o, (s, z) in zip(tensors, outs, params):
+        assert torch.equal(raw(o), raw(pt.quantize(t, scale=s, zero_point=z, dtype=torch.quint4x2, ctx=ctx)))
+    batch.set_params(2, 0.5, 3)
+    outs = batch.run()
+    assert torch.equal(raw(outs[2]), raw(pt.quantize(tensors[2], scale=0.5, zero_point=3, dtype=torch.quint4x2, ctx=ctx)))
+    assert torch.equal(raw(outs[4]), raw(pt.quantize(tensors[4], scale=params[4][0], zero_point=params[4][1], dtype=torch.quint4x2, ctx=ctx)))
