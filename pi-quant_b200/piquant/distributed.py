@@ -91,7 +91,7 @@ def destroy_native_comm(ctx: Context = Context.get()) -> None:
 
 
 __all__ = ["SHARD_ALIGN", "shard_bounds", "combine_minmax", "local_neg_min_max", "compute_quant_params_sharded",
-           "params_from_minmax", "init_native_comm", "destroy_native_comm", "ring_schedule", "quantized_all_reduce_", "QuantizedAllReduce",
+           "params_from_minmax", "init_native_comm", "destroy_native_comm", "ring_schedule", "gather_pieces", "quantized_all_reduce_", "QuantizedAllReduce",
            "DataType"]
 
 
@@ -337,6 +337,14 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
     return tensor
 
 
+def gather_pieces(numel: int, pieces: int):
+    """[lo, hi) element ranges that cut a chunk of ``numel`` elements into at most ``pieces`` non-empty parts at multiples of 256
+    elements (64 packed bytes at 2 bits: every part starts vector-aligned on both sides).  A pure function of its arguments, so
+    every rank derives the same table for every chunk."""
+    cuts = sorted({min(numel, (numel * k // pieces) // 256 * 256) for k in range(pieces)} | {numel})
+    return [(lo, hi) for lo, hi in zip(cuts[:-1], cuts[1:]) if hi > lo]
+
+
 _COPY_STREAMS: dict = {}
 
 
@@ -410,12 +418,7 @@ class _DirectPlan:
             flags_off = 2 * world * slot_bytes
             local[flags_off:].zero_()
             mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
-            # pieces of every chunk (element offsets, multiples of 256 elements = 64 packed bytes at 2 bits): identical on every rank
-            pieces = []
-            for b, e in bounds:
-                n_c = e - b
-                cuts = sorted({min(n_c, (n_c * k // self.GATHER_PIECES) // 256 * 256) for k in range(self.GATHER_PIECES)} | {n_c})
-                pieces.append([(lo, hi) for lo, hi in zip(cuts[:-1], cuts[1:]) if hi > lo])
+            pieces = [gather_pieces(e - b, self.GATHER_PIECES) for b, e in bounds]
             self.lanes.append(dict(bounds=bounds, qbytes=qbytes, slot_bytes=slot_bytes, local=local, hdl=hdl,
                                    peer_base=[int(hdl.buffer_ptrs[i]) for i in range(world)],
                                    peer_pad=[int(hdl.signal_pad_ptrs[i]) for i in range(world)],

@@ -127,3 +127,25 @@ def test_ring_schedule_is_an_all_reduce():
                     assert np.array_equal(data[r][(r + 1) % world], want[(r + 1) % world])
         for r in range(world):
             assert np.array_equal(data[r], want)
+
+
+def test_gather_pieces_cover_the_chunk_at_vector_aligned_cuts():
+    """The piece table of the multicast gather: a partition of [0, numel) into <= pieces non-empty ranges whose interior cuts are
+    multiples of 256 elements; the same on every rank by construction (pure function)."""
+    from piquant.distributed import gather_pieces
+
+    for numel in (0, 1, 255, 256, 257, 1000, 4096, 33_554_432, 33_554_432 + 77, 1_000_003):
+        for pieces in (1, 2, 4, 7):
+            got = gather_pieces(numel, pieces)
+            assert len(got) <= pieces
+            if numel == 0:
+                assert got == []
+                continue
+            assert got[0][0] == 0 and got[-1][1] == numel
+            for (lo, hi), nxt in zip(got, got[1:] + [None]):
+                assert hi > lo and lo % 256 == 0
+                if nxt is not None:
+                    assert nxt[0] == hi
+            if numel >= pieces * 512:                      # large chunks are cut evenly (within one alignment unit)
+                sizes = [hi - lo for lo, hi in got]
+                assert len(got) == pieces and max(sizes) - min(sizes) <= 512
