@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/r2final_pytest.log 2>&1; echo "pytest rc=$?"; tail -n 3 gpurun_out/r2final_pytest.log
-python __graft_entry__.py smoke > gpurun_out/r2final_smoke.log 2>&1; echo "smoke rc=$?"; tail -n 2 gpurun_out/r2final_smoke.log
+python __graft_entry__.py smoke > gpurun_out/r2final_smoke.log 2>&1; echo "smoke rc=$?"; tail -n 1 gpurun_out/r2final_smoke.log
 python bench.py > gpurun_out/r2final_bench.json 2> gpurun_out/r2final_bench.err; echo "bench rc=$?"
-python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/r2final_bench_ref.json 2> gpurun_out/r2final_bench_ref.err; echo "ref rc=$?"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2final_launches.csv python bench.py --steps 20 --warmup 3 > gpurun_out/r2final_bench_under_ncu.log 2>&1; echo "ncu rc=$?"
