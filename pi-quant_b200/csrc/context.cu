@@ -389,10 +389,16 @@ struct Context {
             if (hw && want > hw) want = hw;
             // Measured on a 16-core B200 host (tools/pageable_probe.py, profiles/r2_pageable_probe.txt): 1 / 2 / 4 / 6 / 8 / 12 / 16
             // workers move 2.3 / 4.3 / 7.1 / 8.2 / 9.5 / 10.8 / 10.7 Gelem/s of f32 -> u8 (pinned buffers: 13.4), so up to 12 pay.
-            // A box usually runs one process per GPU: each takes its share of the cores, at least 2.
-            int n_dev = 1;
-            if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1) { cudaGetLastError(); n_dev = 1; }
-            size_t cap = hw ? hw / static_cast<unsigned>(n_dev) : 6;
+            // One process per GPU is the usual layout: each takes its share of the cores, at least 2.  The launcher says how many
+            // share the box (torchrun: LOCAL_WORLD_SIZE; Open MPI / Slurm equivalents); without one this is the only process.
+            long local_world = 1;
+            for (const char* name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "SLURM_NTASKS_PER_NODE"}) {
+                if (const char* e = getenv(name)) {
+                    const long v = strtol(e, nullptr, 10);
+                    if (v >= 1 && v <= 1024) { local_world = v; break; }
+                }
+            }
+            size_t cap = hw ? hw / static_cast<unsigned>(local_world) : 6;
             if (cap < 2) cap = 2;
             if (cap > 12) cap = 12;
             if (const char* e = getenv("PIQUANT_COPY_THREADS")) {      // explicit override
