@@ -604,11 +604,30 @@ def strong_scaling_legs(torch, dist, piquant, D, RoundMode, ReduceOp, x, q, worl
             offs = [(b + j * n_r) if (b + (j + 1) * n_r) <= n_all else b for j in range(windows)] if total < n_all else [b]
             offs = [o - o % 64 for o in offs]
 
-            def launch(k, n_r=n_r, offs=offs, src=src, DIN=DIN, DQ=DQ, s_g=s_g, z_g=z_g, per=per):
-                o = offs[k % len(offs)]
-                ctx.quantize_ptr(src[o:o + n_r].data_ptr(), DIN, q[o // per:].data_ptr(), DQ, n_r, s_g, z_g, RoundMode.NEAREST)
+            ptrs = [(src[o:o + n_r].data_ptr(), q[o // per:].data_ptr()) for o in offs]      # (slicing a tensor costs more host time than the call)
+
+            def launch(k, n_r=n_r, ptrs=ptrs, DIN=DIN, DQ=DQ, s_g=s_g, z_g=z_g):
+                pi, po = ptrs[k % len(ptrs)]
+                ctx.quantize_ptr(pi, DIN, po, DQ, n_r, s_g, z_g, RoundMode.NEAREST)
             reps = 200 if total < n_all else 20
             t_n = device_time(launch, reps)
+            t_graph = None
+            if total < n_all:
+                # a shard this small is issue-bound from Python (a call costs 4-5 us of host time, the kernel less): the same launches
+                # captured once into a CUDA graph and replayed show what the GPU side takes
+                try:
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=side):
+                        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+                        for k in range(64):
+                            launch(k)
+                    ctx.set_stream(stream.cuda_stream)
+                    t_graph = device_time(lambda k: graph.replay(), 5, 2) / 64
+                    del graph
+                except Exception:      # noqa: BLE001
+                    ctx.set_stream(stream.cuda_stream)
             o1 = [j * total for j in range(max(1, min(32, n_all // total)))]
             t_1 = only_rank0(lambda: device_time_local(torch, lambda k: solo.quantize_ptr(src[o1[k % len(o1)]:].data_ptr(), DIN, q[o1[k % len(o1)] // per:].data_ptr(), DQ, total, s_g, z_g, RoundMode.NEAREST), reps))
             # parity: the shard's packed bytes at both shard boundaries == the oracle on the same elements with the global parameters
@@ -628,6 +647,11 @@ def strong_scaling_legs(torch, dist, piquant, D, RoundMode, ReduceOp, x, q, worl
                 "Gelem/s": round(total / t_n / 1e9, 1), "GB/s_aggregate": round(gbs, 1), "frac_of_measured_peak_x_N": round(gbs / (peak * world), 4),
                 "strong_scaling_efficiency": round(t_1 / (world * t_n), 4), "parity_sharded": flags_all(ok),
                 "note": "CUDA events over back-to-back launches on rotating windows, max over ranks; parity = packed bytes of both shard-boundary windows vs the CPU oracle on every rank"}
+            if t_graph is not None:
+                out[f"quantize_{dt_name}_27.264M_sharded"].update({
+                    "us_cuda_graph_replay": round(t_graph * 1e6, 2), "GB/s_aggregate_cuda_graph_replay": round(bpe * total / t_graph / 1e9, 1),
+                    "strong_scaling_efficiency_cuda_graph_replay": round(t_1 / (world * t_graph), 4),
+                    "note_cuda_graph": "64 of the same launches captured once and replayed: no host issue cost; T_1 is the eager one-GPU time"})
     del xb_all
 
     # ---- C5: u8[total] -> f32 dequantize with the ADD store op, sharded ------------------------------------------
