@@ -141,6 +141,36 @@ def test_extension_values_are_validated_before_any_cuda_call(lib):
     assert Context.params_from_minmax(-1.0, 1.0, DataType.INT8) == port.params_from_minmax(-1.0, 1.0, port.INT8) == (np.float32(2 / 255), -1)
 
 
+def test_round2_entry_points_validate_their_arguments_before_any_cuda_call(lib):
+    """The fused / multi-source / flag entry points check dtype classes, source counts and pointers first (reference convention:
+    message + abort, src/piquant.cpp:88-98), so a bad call dies with its own message even on a box without a GPU."""
+    pre = ("b = ctypes.create_string_buffer(256)\n"
+           "arr = (ctypes.c_void_p * 9)(*[ctypes.addressof(b)] * 9)\n"
+           "V = ctypes.c_void_p\n")
+    cases = [
+        # 9 sources: one more than PIQUANT_CUDA_MAX_SUM_SOURCES
+        ("lib.piquant_cuda_dequantize_sum_minmax_on_stream(V(ctx), arr, arr, ctypes.c_size_t(9), 4, b, 0, ctypes.c_size_t(64), 4, b, None, 0, None)",
+         "between 1 and 8 sources"),
+        ("lib.piquant_cuda_dequantize_sum_minmax_on_stream(V(ctx), arr, arr, ctypes.c_size_t(0), 4, b, 0, ctypes.c_size_t(64), 4, b, None, 0, None)",
+         "between 1 and 8 sources"),
+        # a float dtype where a quantized one belongs
+        ("lib.piquant_cuda_dequantize_sum_minmax_on_stream(V(ctx), arr, arr, ctypes.c_size_t(2), 0, b, 0, ctypes.c_size_t(64), 4, b, None, 0, None)",
+         "must be a quantized type"),
+        ("lib.piquant_cuda_dequantize_add_minmax_on_stream(V(ctx), b, 4, b, 0, ctypes.c_size_t(64), b, 1, b, None, 0, None)",
+         "is not a quantization type"),
+        # the flag of piquant_cuda_wait_flag_on_stream is a 4-byte word
+        ("lib.piquant_cuda_wait_flag_on_stream(V(ctx), V(ctypes.addressof(b) + 2), 0, None)", "4-byte aligned"),
+        ("lib.piquant_cuda_wait_flag_on_stream(V(ctx), None, 0, None)", "4-byte aligned"),
+        ("lib.piquant_cuda_copy_on_stream(V(ctx), None, b, ctypes.c_size_t(8), 0, None)", "must not be NULL"),
+    ]
+    for call, message in cases:
+        r = run_snippet(pre + call)
+        assert r.returncode == -6 and message in r.stderr, (call, r.returncode, r.stderr[-300:])
+    # empty work returns before CUDA is touched
+    ok = run_snippet(pre + "lib.piquant_cuda_copy_on_stream(V(ctx), b, b, ctypes.c_size_t(0), 0, None)")
+    assert ok.returncode == 0 and "survived" in ok.stdout, ok.stderr
+
+
 def test_compute_without_a_gpu_aborts_loudly(lib):
     import piquant
 
