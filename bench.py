@@ -863,6 +863,7 @@ def ring_allreduce_leg(torch, dist, ctx, world, rank, dev) -> dict:
                     ("quantized_u8_ring_p2p_fused_2_lanes", dict(transport="p2p", algorithm="ring", lanes=2)),
                     ("quantized_u8_ring_p2p_fused_2_lanes_stochastic_per_element",
                      dict(transport="p2p", algorithm="ring", lanes=2, round_mode="stochastic_per_element")),
+                    ("quantized_u8_direct_over_nccl_collectives", dict(transport="nccl", algorithm="direct")),
                     ("quantized_u8_direct_all_to_all", dict(transport="p2p", algorithm="direct")),
                     ("quantized_u8_direct_all_to_all_stochastic_per_element", dict(transport="p2p", algorithm="direct", round_mode="stochastic_per_element")),
                     ("quantized_u8_direct_all_to_all_cuda_graph", dict(graph=True)),
@@ -894,6 +895,7 @@ def ring_allreduce_leg(torch, dist, ctx, world, rank, dev) -> dict:
                 "ring": replay.ring_all_reduce(host, orc.UINT8, orc.F32, pd.shard_bounds, pd.SHARD_ALIGN, 1)}
         checks = {}
         for name, run in (("direct", lambda t: pd.quantized_all_reduce_(t, dtype=torch.quint8, ctx=ctx, transport="p2p", algorithm="direct", lanes=1)),
+                          ("direct_over_nccl", lambda t: pd.quantized_all_reduce_(t, dtype=torch.quint8, ctx=ctx, transport="nccl", algorithm="direct")),
                           ("direct_cuda_graph", lambda t: pd.QuantizedAllReduce(t, dtype=torch.quint8, ctx=ctx, lanes=1)()),
                           ("ring", lambda t: pd.quantized_all_reduce_(t, dtype=torch.quint8, ctx=ctx, transport="p2p", algorithm="ring", lanes=1))):
             t = small.clone()
@@ -908,6 +910,7 @@ def ring_allreduce_leg(torch, dist, ctx, world, rank, dev) -> dict:
     res["note"] = ("ring reduce-scatter + all-gather, [64 B params | u8 payload] per hop, no host sync; a reduce-scatter hop = quantize + ONE fused "
                    "dequantize-ADD/min-max/params kernel; p2p_fused = kernels store into / forward to the neighbour's slot over NVLink peer memory, "
                    "nothing is sent; abs_mean_err shows the bias nearest rounding accumulates per hop and per-element stochastic rounding does not; "
+                   "direct_over_nccl_collectives = the direct algorithm with one all_to_all_single + one all_gather_into_tensor (no peer memory needed); "
                    "direct_all_to_all = the NVSwitch form: quantize each chunk once, copy engines move it to its owner, ONE multi-source "
                    "dequantize-sum kernel reduces, the packed sums are broadcast by copy engines and dequantized: 2 quantizations per value "
                    "whatever the world size, 1 barrier + per-slot arrival flags written by the copy engine; cuda_graph = the same collective of a "

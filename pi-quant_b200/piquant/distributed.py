@@ -154,8 +154,11 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
     every value is quantized twice in total instead of ``world`` times, and the reduce step is one pass.  Measured on
     8 B200s, 2^28 f32, uint8 transport: 1.09 ms against 1.40 ms for the ring below and 2.6 ms for NCCL's f32 all-reduce
     (profiles/r2_allreduce_probe_n8.txt); captured into a CUDA graph (``QuantizedAllReduce``) 1.06 ms.
-    ``algorithm="auto"`` (default): direct when the GPUs can map each other's memory, else the ring over NCCL send/recv
-    -- a fallback for boxes without peer access that is SLOWER than NCCL's own f32 all-reduce beyond 2 GPUs (0.39x at 8).
+    ``algorithm="auto"`` (default) = direct.  Its ``transport``: ``"p2p"`` (copy engines into peer memory; ``"auto"`` picks it
+    when the GPUs can map each other's memory) or ``"nccl"`` -- the same algorithm, same results bit for bit, with the two
+    exchanges done by ONE ``all_to_all_single`` and ONE ``all_gather_into_tensor`` of the packed slots: the form for boxes
+    without peer access (the 2 * (world - 1) send/recv hops of the ring over NCCL are slower than NCCL's own f32 all-reduce
+    beyond 2 GPUs: 0.39x at 8).
     ``multicast=True`` (direct form, opt-in): broadcast the reduced chunks through the NVSwitch multicast address of the symmetric
     buffer; bit-identical results, measured slower than the default at 8 GPUs (see ``_DirectPlan``).
     ``lanes=None``: 2 for the direct form on 2 GPUs and tensors of 256 MB or more, else 1.  The rest of this text describes
@@ -196,11 +199,13 @@ def quantized_all_reduce_(tensor: torch.Tensor, *, dtype: torch.dtype = torch.qu
         raise ValueError(f"unknown transport {transport!r}")
     if algorithm not in ("ring", "direct", "auto"):
         raise ValueError(f"unknown algorithm {algorithm!r}")
-    if algorithm == "direct" and transport == "nccl":
-        raise ValueError("algorithm='direct' moves the chunks with copy engines through peer memory; transport must be 'p2p' or 'auto'")
     if algorithm == "auto":
-        algorithm = "direct" if transport != "nccl" and _peer_memory_available(tensor.device, group) else "ring"
+        algorithm = "direct"
     if algorithm == "direct":
+        if transport == "auto":
+            transport = "p2p" if _peer_memory_available(tensor.device, group) else "nccl"
+        if transport == "nccl":
+            return _direct_all_reduce_nccl(tensor, dtype, group, ctx, rmode)
         return _direct_all_reduce(tensor, dtype, group, ctx, rmode, lanes if lanes is not None else _auto_lanes(tensor, world), multicast)
     lanes = 1 if lanes is None else lanes
     fdt, qdt = torch_to_piquant_dtype(tensor.dtype), torch_to_piquant_dtype(dtype)
@@ -560,6 +565,49 @@ class _DirectPlan:
 
 
 _DIRECT_PLANS: dict = {}
+
+
+def _direct_all_reduce_nccl(tensor: torch.Tensor, dtype: torch.dtype, group, ctx: Context, rmode: RoundMode) -> torch.Tensor:
+    """The direct algorithm (``_DirectPlan``: chunk c owned by rank c, every value quantized twice, one-pass multi-source
+    reduce) with its two exchanges handed to NCCL: ONE ``all_to_all_single`` of ``[parameters | packed chunk]`` slots and ONE
+    ``all_gather_into_tensor`` of the reduced slots.  Same arithmetic in the same order as the peer-memory form -- results are
+    bit-identical to it and to the CPU replay -- for boxes where the GPUs cannot map each other's memory; nothing overlaps
+    (NCCL needs all of a rank's slots before it starts), so the peer-memory form is the faster one where it exists."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    fdt, qdt = torch_to_piquant_dtype(tensor.dtype), torch_to_piquant_dtype(dtype)
+    meta, dev = Context.META_BYTES, tensor.device
+    device, st = dev.index, torch.cuda.current_stream(dev).cuda_stream
+    LOCAL, REVERSE = Context.FLAG_LOCAL, Context.FLAG_REVERSE
+    flat = tensor.view(-1)
+    bounds = [shard_bounds(flat.numel(), world, i) for i in range(world)]
+    qbytes = [qdt.storage_bytes(e - b) for b, e in bounds]
+    slot_bytes = (meta + max(qbytes) + 255) // 256 * 256
+    send = torch.empty(world * slot_bytes, dtype=torch.uint8, device=dev)      # slot j: my chunk j for its owner, rank j
+    recv = torch.empty_like(send)                                              # slot k: rank k's version of MY chunk
+    for j in range(world):
+        b, e = bounds[j]
+        if j != rank and e > b:
+            base = send.data_ptr() + j * slot_bytes
+            ctx.compute_meta_on_stream(flat[b:e].data_ptr(), fdt, e - b, qdt, base, LOCAL, device, st)
+            ctx.quantize_meta_on_stream(flat[b:e].data_ptr(), fdt, base + meta, qdt, e - b, rmode, base, REVERSE, device, st)
+    dist.all_to_all_single(recv, send, group=group)
+    b, e = bounds[rank]
+    mine = torch.empty(slot_bytes, dtype=torch.uint8, device=dev)              # [parameters | packed sums] of my chunk
+    gathered = send                                                            # (its slots have been delivered: reuse the buffer)
+    if e > b:
+        srcs = [recv.data_ptr() + k * slot_bytes for k in range(world) if k != rank]
+        for g in range(0, len(srcs), Context.MAX_SUM_SOURCES):
+            part = srcs[g:g + Context.MAX_SUM_SOURCES]
+            ctx.dequantize_sum_minmax_on_stream([p + meta for p in part], qdt, flat[b:e].data_ptr(), fdt, e - b, part, qdt, mine.data_ptr(), 0,
+                                                device, st)
+        ctx.quantize_meta_on_stream(flat[b:e].data_ptr(), fdt, mine.data_ptr() + meta, qdt, e - b, rmode, mine.data_ptr(), REVERSE, device, st)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    for j in range(world):                                                     # owners too: every rank dequantizes the same bytes
+        bj, ej = bounds[j]
+        if ej > bj:
+            src = gathered.data_ptr() + j * slot_bytes
+            ctx.dequantize_meta_on_stream(src + meta, qdt, flat[bj:ej].data_ptr(), fdt, ej - bj, ReduceOp.SET, src, device, st)
+    return tensor
 
 
 def _auto_lanes(tensor: torch.Tensor, world: int) -> int:

@@ -134,6 +134,16 @@ def _worker(rank: int, world: int, port: int, numel: int, q) -> None:
             # every input is rounded once (<= step/2 each, at the input's own scale 2/levels), the sum once more
             bound = (0.5 if rmode == "nearest" else 1.0) * ((world - 1) * 2.0 / levels + step) + (0.05 * world if tdt == torch.bfloat16 else 1e-5)
             res[key] = (identical, err <= bound)
+        # the direct algorithm with its exchanges handed to NCCL (all_to_all_single + all_gather_into_tensor): same bits
+        for tdt, qdt, numel in ((torch.float32, torch.quint8, 1_000_003), (torch.bfloat16, torch.quint4x2, 300_007),
+                                (torch.float32, torch.quint2x4, 70_001), (torch.float32, torch.quint8, 100)):
+            g = torch.Generator(device="cuda").manual_seed(300 + rank)
+            t = (torch.rand(numel, device="cuda", generator=g) * 2 - 1).to(tdt)
+            inputs = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(inputs, t)
+            pd.quantized_all_reduce_(t, dtype=qdt, ctx=ctx, transport="nccl", algorithm="direct")
+            want = _direct_on_the_oracle(orc, pd, [i.cpu() for i in inputs], qdt, 1)
+            res[f"direct_over_nccl_{tdt}_{qdt}_{numel}"] = (bool(np.array_equal(_bits(t.cpu()), want)),)
         # the same collective captured into a CUDA graph for a persistent tensor, replayed with new contents
         for tdt, qdt, numel, lanes in ((torch.float32, torch.quint8, 1_000_003, 2), (torch.bfloat16, torch.quint4x2, 300_007, 1)):
             t = torch.zeros(numel, device="cuda", dtype=tdt)
